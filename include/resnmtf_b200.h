@@ -1,0 +1,162 @@
+/*
+ * resnmtf_b200.h -- C ABI of the B200-native ResNMTF multiplicative-update loop.
+ *
+ * The reference (eso28599/resnmtf) is pure R and has no FFI; the seam this library replaces is the
+ * loop body of res_nmtf_inner(), R/main.r:50-109, whose only callees are update_matrices()
+ * (R/update_steps.r:272-319) and calculate_error() (R/utils.r:157-166).  A drop-in R package keeps
+ * res_nmtf_inner()/apply_resnmtf() unchanged and turns R/main.r:50-109 into one .Call that lands on
+ * the functions below (see INTEGRATION.md for the .Call shim and the ctypes binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All host matrices are column-major doubles, exactly
+ *     as R stores them; host buffers are borrowed for the duration of the call only.
+ *   - Views, rows and columns are 0-based here (R is 1-based; the shim subtracts 1).
+ *   - Every function returns 0 (RESNMTF_OK) or a negative RESNMTF_E_* code; the message is available
+ *     from resnmtf_last_error() (thread-local).  No C++ exception crosses the ABI.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     RESNMTF_E_CUDA.
+ *   - Entry points on one ctx are not re-entrant; different ctx are independent.
+ */
+#ifndef RESNMTF_B200_H
+#define RESNMTF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RESNMTF_OK 0
+#define RESNMTF_E_INVALID (-1)     /* bad argument (NULL, out of range, shape mismatch)              */
+#define RESNMTF_E_CUDA (-2)        /* CUDA runtime error, or no CUDA device                          */
+#define RESNMTF_E_NOMEM (-3)       /* host or device allocation failed                               */
+#define RESNMTF_E_STATE (-4)       /* call sequence error (data / factors not set before run)        */
+#define RESNMTF_E_NAN (-5)         /* mean error became NaN in convergence mode: the reference's     */
+                                   /* while(NA) at R/main.r:55 throws "missing value where           */
+                                   /* TRUE/FALSE needed"; the R shim turns this code into that error */
+#define RESNMTF_E_UNSUPPORTED (-6) /* k outside 1..RESNMTF_MAX_K                                     */
+#define RESNMTF_E_COMM (-7)        /* NCCL error on the row-sharded path                             */
+
+#define RESNMTF_MAX_K 16
+
+/* which index space a shared-name map refers to (replaces the per-view `hash` objects built by
+ * produce_indices(), R/utils.r:560-601, and consumed by star_prod_relevant(), R/utils.r:63-78) */
+#define RESNMTF_MAP_ROW 0 /* rows of F (phi coupling)    -- row_indices[[v]]    */
+#define RESNMTF_MAP_COL 1 /* rows of G (psi coupling)    -- column_indices[[v]] */
+
+/* how the per-iteration error of calculate_error() (R/utils.r:157-166) is evaluated */
+#define RESNMTF_ERR_AUTO 0      /* algebraic (no pass over X); re-done by a direct pass when < 1e-3  */
+#define RESNMTF_ERR_ALGEBRAIC 1 /* ||X||^2 - 2<A,S> + <(F'F) S (G'G), S>, always                     */
+#define RESNMTF_ERR_DIRECT 2    /* sum (X - F S G')^2 streamed over X, always (one extra pass)       */
+
+/* streaming-kernel implementation of the two tall-skinny products */
+#define RESNMTF_IMPL_AUTO 0
+#define RESNMTF_IMPL_DFMA 1 /* CUDA-core FP64 FMA                                    */
+#define RESNMTF_IMPL_DMMA 2 /* FP64 tensor-core mma.sync m8n8k4, k padded to 8 or 16 */
+
+typedef struct resnmtf_ctx resnmtf_ctx;
+typedef struct resnmtf_fit resnmtf_fit;
+
+/* Counters of the last resnmtf_fit_run / resnmtf_fit_step on a fit. */
+typedef struct resnmtf_counters {
+  int64_t iterations;       /* update-iterations (update_matrices sweeps) done since set_factors      */
+  int64_t kernel_launches;  /* CUDA kernels launched by the last run (graph nodes counted per replay) */
+  double device_ms;         /* CUDA-event time of the last run on the fit's stream                    */
+  double alg_bytes_per_iter;/* algorithmic HBM bytes per update-iteration (SURVEY 8d B_alg)           */
+  int64_t direct_error_passes; /* how many times the direct residual pass ran in the last run        */
+  int32_t converged;        /* 1 when the last run stopped on |d err| <= tol                          */
+  int32_t impl;             /* RESNMTF_IMPL_* actually used                                           */
+} resnmtf_counters;
+
+/* ---- context: one CUDA device, one stream ------------------------------------------------------- */
+
+/* device < 0 selects the current CUDA device. */
+int resnmtf_ctx_create(int device, resnmtf_ctx** out);
+int resnmtf_ctx_destroy(resnmtf_ctx* ctx);
+/* cudaStream_t the context launches on, as an opaque pointer (for CUDA-event timing by the caller). */
+void* resnmtf_ctx_stream(resnmtf_ctx* ctx);
+int resnmtf_ctx_synchronize(resnmtf_ctx* ctx);
+/* Thread-local message of the last failure on the calling thread (never NULL). */
+const char* resnmtf_last_error(void);
+/* Library version string, and the number of CUDA devices visible (0 when none / no driver). */
+const char* resnmtf_version(void);
+int resnmtf_device_count(void);
+
+/* ---- fit: device-resident X, F, S, G, lambda, mu of all views of one res_nmtf_inner() call -------- */
+
+/* n[v] x p[v] is the shape of view v, k[v] its number of clusters (k_vec of R/main.r:35). */
+int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* n, const int64_t* p,
+                       const int32_t* k, resnmtf_fit** out);
+int resnmtf_fit_destroy(resnmtf_fit* fit);
+
+/* Copies view v (column-major, leading dimension ld >= n[v]) to the device and computes
+ * data_norms[v] = ||X||_F^2 (R/main.r:48) there.  x may be pageable or pinned host memory. */
+int resnmtf_fit_set_data(resnmtf_fit* fit, int v, const double* x, int64_t ld);
+/* Same, but x is a DEVICE pointer on the fit's device (no host round trip). */
+int resnmtf_fit_set_data_device(resnmtf_fit* fit, int v, const double* x_dev, int64_t ld);
+
+/* Initial factors of view v: F n x k, S k x k, G p x k, lambda k, mu k (what init_mats(),
+ * R/update_steps.r:36-66, hands to the loop).  lambda / mu may be NULL: they are then set to
+ * colSums(F) / colSums(G) as R/update_steps.r:53-54 does.  Resets the iteration counter. */
+int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f, const double* s,
+                            const double* g, const double* lambda, const double* mu);
+
+/* phi, xi, psi: n_views x n_views column-major, ALREADY symmetrised by init_rest_mats()
+ * (R/update_steps.r:12-24).  NULL means all-zero. */
+int resnmtf_fit_set_restrictions(resnmtf_fit* fit, const double* phi, const double* xi,
+                                 const double* psi);
+
+/* Shared names between views v and w as index pairs: row (kind ROW) / column (kind COL) idx_v[i] of
+ * view v carries the same name as idx_w[i] of view w.  len == 0 stores R's NA (the pair shares
+ * nothing and is skipped by star_prod_relevant, R/utils.r:70).  Must be set for both (v,w) and (w,v)
+ * when both directions are coupled.  A pair that was never set behaves like R's `indices = NULL`
+ * (quirk of R/main.r:312: nothing is overwritten, the view is pulled towards itself). */
+int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int w, const int32_t* idx_v,
+                               const int32_t* idx_w, int64_t len);
+
+/* Options: err_mode RESNMTF_ERR_*, impl RESNMTF_IMPL_* (both default AUTO). */
+int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl);
+
+/* Runs the loop of R/main.r:50-109 on the device.
+ *   n_iters >= 0 : exactly n_iters sweeps (R/main.r:83-108).
+ *   n_iters <  0 : until |mean_err - previous| <= tol (R/main.r:55-81; previous starts at 0);
+ *                  max_iters > 0 adds a cap the reference does not have (<= 0: none).
+ * iters_done receives the number of sweeps of this call.  Returns RESNMTF_E_NAN when the mean error
+ * became NaN in convergence mode. */
+int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, int64_t max_iters,
+                    int64_t* iters_done);
+/* One update_matrices() sweep + calculate_error() (for per-iteration parity checks). */
+int resnmtf_fit_step(resnmtf_fit* fit);
+
+/* Current (un-normalised) factors of view v, column-major, any pointer may be NULL. */
+int resnmtf_fit_get_factors(resnmtf_fit* fit, int v, double* f, double* s, double* g,
+                            double* lambda, double* mu);
+/* normalisation_check() (R/utils.r:176-195) applied on the device to all views. */
+int resnmtf_fit_normalise(resnmtf_fit* fit);
+/* Mean error of every sweep since set_factors (All_Error of R/main.r:134); writes min(cap, count)
+ * values, *count receives the total. */
+int resnmtf_fit_get_errors(resnmtf_fit* fit, double* out, int64_t cap, int64_t* count);
+/* Per-view error of the last sweep (calculate_error's vector) and data_norms. */
+int resnmtf_fit_get_view_errors(resnmtf_fit* fit, double* err, double* data_norms);
+int resnmtf_fit_get_counters(resnmtf_fit* fit, resnmtf_counters* out);
+
+/* Runs n_iters sweeps with CUDA events between the kernel launches (no graph) and returns the summed
+ * device time per kernel class: ms[0] F step (X.G + F update), ms[1] G stream (X'.F), ms[2] G epilogue
+ * (G, S, lambda, mu update + algebraic error), ms[3] direct residual pass, ms[4] iteration
+ * bookkeeping; launches[i] is the number of timed intervals of that class. */
+int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[5], int64_t launches[5]);
+
+/* ---- row-sharded view across ranks (one process per GPU; NCCL all-reduce of the p x k partials) ---- */
+
+/* Size of the opaque NCCL unique id and its creation on rank 0 (to be broadcast by the host). */
+int resnmtf_comm_id_size(void);
+int resnmtf_comm_id_create(void* id_out);
+/* Joins the communicator.  After this, every view of every fit created on ctx is treated as
+ * ROW-SHARDED: n[v] passed to fit_create is the local row count, F rows are local, G/S/lambda/mu are
+ * replicated and X'F, F'F, colSums(F), ||X||^2 and the residual are all-reduced each sweep. */
+int resnmtf_ctx_join(resnmtf_ctx* ctx, const void* id, int rank, int n_ranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESNMTF_B200_H */

@@ -1,0 +1,130 @@
+"""ctypes binding of the C-ABI shared library (include/resnmtf_b200.h).
+
+The library is built in-tree by ``resnmtf_b200/csrc/build.sh`` (``__graft_entry__.build()``).  There is
+no CPU fallback anywhere in this package: if the library is missing, or no CUDA device is visible, the
+compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libresnmtf_b200.so")
+
+OK = 0
+E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_NAN, E_UNSUPPORTED, E_COMM = -1, -2, -3, -4, -5, -6, -7
+MAX_K = 16
+MAP_ROW, MAP_COL = 0, 1
+ERR_AUTO, ERR_ALGEBRAIC, ERR_DIRECT = 0, 1, 2
+IMPL_AUTO, IMPL_DFMA, IMPL_DMMA = 0, 1, 2
+
+# every symbol include/resnmtf_b200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "resnmtf_ctx_create", "resnmtf_ctx_destroy", "resnmtf_ctx_stream", "resnmtf_ctx_synchronize",
+    "resnmtf_last_error", "resnmtf_version", "resnmtf_device_count",
+    "resnmtf_fit_create", "resnmtf_fit_destroy", "resnmtf_fit_set_data", "resnmtf_fit_set_data_device",
+    "resnmtf_fit_set_factors", "resnmtf_fit_set_restrictions", "resnmtf_fit_set_shared_map",
+    "resnmtf_fit_set_options", "resnmtf_fit_run", "resnmtf_fit_step", "resnmtf_fit_get_factors",
+    "resnmtf_fit_normalise", "resnmtf_fit_get_errors", "resnmtf_fit_get_view_errors",
+    "resnmtf_fit_get_counters", "resnmtf_fit_profile",
+    "resnmtf_comm_id_size", "resnmtf_comm_id_create", "resnmtf_ctx_join",
+)
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int64),
+        ("kernel_launches", C.c_int64),
+        ("device_ms", C.c_double),
+        ("alg_bytes_per_iter", C.c_double),
+        ("direct_error_passes", C.c_int64),
+        ("converged", C.c_int32),
+        ("impl", C.c_int32),
+    ]
+
+
+class ResnmtfError(RuntimeError):
+    """A C-ABI call returned a negative RESNMTF_E_* code."""
+
+    def __init__(self, code, message):
+        super().__init__(f"resnmtf_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class ResnmtfNaNError(ResnmtfError, FloatingPointError):
+    """The mean error became NaN in convergence mode (the reference's while(NA) at R/main.r:55)."""
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Raises when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with resnmtf_b200/csrc/build.sh "
+            "(or __graft_entry__.build()).  resnmtf_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pd, pi32, pi64 = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    sig = {
+        "resnmtf_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "resnmtf_ctx_destroy": (C.c_int, [vp]),
+        "resnmtf_ctx_stream": (vp, [vp]),
+        "resnmtf_ctx_synchronize": (C.c_int, [vp]),
+        "resnmtf_last_error": (C.c_char_p, []),
+        "resnmtf_version": (C.c_char_p, []),
+        "resnmtf_device_count": (C.c_int, []),
+        "resnmtf_fit_create": (C.c_int, [vp, C.c_int, pi64, pi64, pi32, C.POINTER(vp)]),
+        "resnmtf_fit_destroy": (C.c_int, [vp]),
+        "resnmtf_fit_set_data": (C.c_int, [vp, C.c_int, vp, i64]),
+        "resnmtf_fit_set_data_device": (C.c_int, [vp, C.c_int, vp, i64]),
+        "resnmtf_fit_set_factors": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+        "resnmtf_fit_set_restrictions": (C.c_int, [vp, vp, vp, vp]),
+        "resnmtf_fit_set_shared_map": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, i64]),
+        "resnmtf_fit_set_options": (C.c_int, [vp, C.c_int, C.c_int]),
+        "resnmtf_fit_run": (C.c_int, [vp, i64, dbl, i64, pi64]),
+        "resnmtf_fit_step": (C.c_int, [vp]),
+        "resnmtf_fit_get_factors": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+        "resnmtf_fit_normalise": (C.c_int, [vp]),
+        "resnmtf_fit_get_errors": (C.c_int, [vp, vp, i64, pi64]),
+        "resnmtf_fit_get_view_errors": (C.c_int, [vp, vp, vp]),
+        "resnmtf_fit_get_counters": (C.c_int, [vp, C.POINTER(Counters)]),
+        "resnmtf_fit_profile": (C.c_int, [vp, i64, pd, pi64]),
+        "resnmtf_comm_id_size": (C.c_int, []),
+        "resnmtf_comm_id_create": (C.c_int, [vp]),
+        "resnmtf_ctx_join": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    """Turns a negative return code into the matching Python exception."""
+    if code == OK:
+        return
+    msg = load().resnmtf_last_error().decode("utf-8", "replace")
+    if code == E_NAN:
+        raise ResnmtfNaNError(code, msg)
+    raise ResnmtfError(code, msg)
+
+
+def device_count():
+    return int(load().resnmtf_device_count())
+
+
+def require_device():
+    """Fails loudly when the CUDA path cannot run (no library, no GPU)."""
+    lib = load()
+    if lib.resnmtf_device_count() < 1:
+        raise RuntimeError("resnmtf_b200: no CUDA device visible and there is no CPU fallback")
+    return lib

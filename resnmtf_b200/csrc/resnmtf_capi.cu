@@ -1,0 +1,914 @@
+// Host side of the C ABI declared in include/resnmtf_b200.h: owns the device-resident X, F, S, G,
+// lambda, mu of every view of a fit, the per-iteration CUDA graph and the convergence loop of
+// R/main.r:50-109.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/resnmtf_b200.h"
+#include "rn_kernels.cuh"
+
+#ifdef RESNMTF_WITH_NCCL
+#include <nccl.h>
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err = "";
+
+static int rn_fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define RN_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return rn_fail(e__ == cudaErrorMemoryAllocation ? RESNMTF_E_NOMEM : RESNMTF_E_CUDA,     \
+                     std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+#define RN_CHECK(cond, code, msg) \
+  do {                            \
+    if (!(cond)) return rn_fail(code, msg); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct resnmtf_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int rank = 0, n_ranks = 1;
+#ifdef RESNMTF_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+};
+
+struct ViewHost {
+  RnView d;  // device pointers + geometry (passed by value to the kernels)
+  bool has_data = false, has_factors = false;
+  std::vector<int32_t*> rowmaps, colmaps;  // [V] device maps of this view into view w (or null)
+  double* xpart = nullptr;                 // ||X||^2 partials
+  int32_t* xticket = nullptr;
+};
+
+struct resnmtf_fit {
+  resnmtf_ctx* ctx = nullptr;
+  int V = 0;
+  std::vector<ViewHost> views;
+  std::vector<void*> allocs;
+  RnFit d;               // passed by value to the kernels
+  RnView* d_views = nullptr;
+  RnCtrl* d_ctrl = nullptr;
+  double *d_phi = nullptr, *d_xi = nullptr, *d_psi = nullptr;
+  const int32_t** d_rowmap = nullptr;
+  const int32_t** d_colmap = nullptr;
+  int8_t *d_rowmode = nullptr, *d_colmode = nullptr;
+  std::vector<const int32_t*> h_rowmap, h_colmap;
+  std::vector<int8_t> h_rowmode, h_colmode;
+  std::vector<double> h_phi, h_xi, h_psi;
+  double* d_hist = nullptr;
+  int64_t hist_cap = 4096;
+  std::vector<double> errors;  // All_Error
+  int err_mode = RESNMTF_ERR_AUTO;
+  int impl_req = RESNMTF_IMPL_AUTO;
+  int impl = RESNMTF_IMPL_DMMA;
+  bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
+  bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int64_t launches_per_iter = 0;
+  resnmtf_counters counters{};
+  RnCtrl h_ctrl{};
+};
+
+template <typename T>
+static int rn_alloc(resnmtf_fit* f, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  RN_CUDA(cudaMalloc(&p, bytes));
+  f->allocs.push_back(p);
+  if (zero) RN_CUDA(cudaMemsetAsync(p, 0, bytes, f->ctx->stream));
+  *out = static_cast<T*>(p);
+  return RESNMTF_OK;
+}
+
+static int rn_free(resnmtf_fit* f, void* p) {
+  if (!p) return RESNMTF_OK;
+  auto it = std::find(f->allocs.begin(), f->allocs.end(), p);
+  if (it != f->allocs.end()) f->allocs.erase(it);
+  RN_CUDA(cudaFree(p));
+  return RESNMTF_OK;
+}
+
+static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch on k
+// ------------------------------------------------------------------------------------------------
+#define RN_K_CASES_LE8(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define RN_K_CASES_GT8(X) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
+static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, cudaStream_t st) {
+  dim3 grid(vh.d.row_tiles, vh.d.cs);
+  const int K = vh.d.k;
+  if (impl == RESNMTF_IMPL_DMMA && K <= 8) {
+    switch (K) {
+#define X(KC) case KC: rn_f_step<KC, 8, true><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
+      RN_K_CASES_LE8(X)
+#undef X
+    }
+  } else {
+    switch (K) {
+#define X(KC) case KC: rn_f_step<KC, 8, false><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
+      RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_f_step<KC, 16, false><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
+      RN_K_CASES_GT8(X)
+#undef X
+    }
+  }
+}
+
+static int launch_g_stream(const ViewHost& vh, const RnFit& ft, int impl, cudaStream_t st) {
+  dim3 grid(vh.d.col_groups, vh.d.rs);
+  const int K = vh.d.k;
+  int n = 1;
+  if (impl == RESNMTF_IMPL_DMMA && K <= 8) {
+    switch (K) {
+#define X(KC) case KC: rn_g_stream_mma<KC><<<grid, 128, 0, st>>>(vh.d, ft); break;
+      RN_K_CASES_LE8(X)
+#undef X
+    }
+  } else {
+    switch (K) {
+#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft); break;
+      RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft); break;
+      RN_K_CASES_GT8(X)
+#undef X
+    }
+    n = 2;
+  }
+  return n;
+}
+
+static void launch_g_epilogue(const ViewHost& vh, const RnFit& ft, int v, cudaStream_t st) {
+  const int K = vh.d.k;
+  switch (K) {
+#define X(KC) case KC: rn_g_epilogue<KC, 8><<<vh.d.gepi_ctas, RN_GEPI_THREADS(KC), 0, st>>>(vh.d, ft, v); break;
+    RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_g_epilogue<KC, 16><<<vh.d.gepi_ctas, RN_GEPI_THREADS(KC), 0, st>>>(vh.d, ft, v); break;
+    RN_K_CASES_GT8(X)
+#undef X
+  }
+}
+
+static void launch_residual(const ViewHost& vh, const RnFit& ft, cudaStream_t st) {
+  dim3 grid(vh.d.row_tiles, vh.d.resid_cs);
+  const int K = vh.d.k;
+  switch (K) {
+#define X(KC) case KC: rn_residual<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft); break;
+    RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_residual<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft); break;
+    RN_K_CASES_GT8(X)
+#undef X
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* resnmtf_last_error(void) { return g_err.c_str(); }
+extern "C" const char* resnmtf_version(void) { return "resnmtf_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int resnmtf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int resnmtf_ctx_create(int device, resnmtf_ctx** out) {
+  RN_CHECK(out != nullptr, RESNMTF_E_INVALID, "resnmtf_ctx_create: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return rn_fail(RESNMTF_E_CUDA,
+                   "resnmtf_ctx_create: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0) RN_CUDA(cudaGetDevice(&device));
+  RN_CHECK(device < n, RESNMTF_E_INVALID, "resnmtf_ctx_create: device index out of range");
+  RN_CUDA(cudaSetDevice(device));
+  resnmtf_ctx* c = new (std::nothrow) resnmtf_ctx();
+  RN_CHECK(c != nullptr, RESNMTF_E_NOMEM, "resnmtf_ctx_create: out of host memory");
+  c->device = device;
+  cudaDeviceProp prop;
+  RN_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  RN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  RN_CUDA(cudaEventCreate(&c->ev0));
+  RN_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_ctx_destroy(resnmtf_ctx* ctx) {
+  if (!ctx) return RESNMTF_OK;
+  cudaSetDevice(ctx->device);
+#ifdef RESNMTF_WITH_NCCL
+  if (ctx->comm) ncclCommDestroy(ctx->comm);
+#endif
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return RESNMTF_OK;
+}
+
+extern "C" void* resnmtf_ctx_stream(resnmtf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int resnmtf_ctx_synchronize(resnmtf_ctx* ctx) {
+  RN_CHECK(ctx != nullptr, RESNMTF_E_INVALID, "resnmtf_ctx_synchronize: ctx is NULL");
+  RN_CUDA(cudaSetDevice(ctx->device));
+  RN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RESNMTF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fit: creation, data, factors, restrictions
+// ------------------------------------------------------------------------------------------------
+extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* n, const int64_t* p,
+                                  const int32_t* k, resnmtf_fit** out) {
+  RN_CHECK(ctx && n && p && k && out, RESNMTF_E_INVALID, "resnmtf_fit_create: NULL argument");
+  RN_CHECK(n_views >= 1, RESNMTF_E_INVALID, "resnmtf_fit_create: n_views must be >= 1");
+  for (int v = 0; v < n_views; ++v) {
+    RN_CHECK(n[v] >= 1 && p[v] >= 1, RESNMTF_E_INVALID, "resnmtf_fit_create: empty view");
+    RN_CHECK(k[v] >= 1 && k[v] <= RESNMTF_MAX_K, RESNMTF_E_UNSUPPORTED,
+             "resnmtf_fit_create: k must be in 1..16");
+    RN_CHECK(n[v] < (int64_t)1 << 31 && p[v] < (int64_t)1 << 31, RESNMTF_E_UNSUPPORTED,
+             "resnmtf_fit_create: a view dimension exceeds the int32 gather-map range");
+  }
+  RN_CUDA(cudaSetDevice(ctx->device));
+  resnmtf_fit* f = new (std::nothrow) resnmtf_fit();
+  RN_CHECK(f != nullptr, RESNMTF_E_NOMEM, "resnmtf_fit_create: out of host memory");
+  f->ctx = ctx;
+  f->V = n_views;
+  f->views.resize(n_views);
+  int rc = RESNMTF_OK;
+  auto fail = [&](int code) {
+    resnmtf_fit_destroy(f);
+    return code;
+  };
+  const int V = n_views;
+  for (int v = 0; v < V && rc == RESNMTF_OK; ++v) {
+    ViewHost& vh = f->views[v];
+    std::memset(&vh.d, 0, sizeof(RnView));
+    vh.d.n = n[v];
+    vh.d.p = p[v];
+    vh.d.k = k[v];
+    vh.d.kp = k[v] <= 8 ? 8 : 16;
+    vh.d.ldx = rn_round_up(n[v], RN_ROW_TILE);
+    vh.d.pp = rn_round_up(p[v], 8);
+    vh.d.sharded = ctx->n_ranks > 1 ? 1 : 0;
+    vh.rowmaps.assign(V, nullptr);
+    vh.colmaps.assign(V, nullptr);
+    const int K = k[v], KP = vh.d.kp;
+    if ((rc = rn_alloc(f, &vh.d.X, (size_t)vh.d.ldx * vh.d.pp))) break;
+    if ((rc = rn_alloc(f, &vh.d.F, (size_t)vh.d.ldx * KP))) break;
+    if ((rc = rn_alloc(f, &vh.d.G, (size_t)vh.d.pp * KP))) break;
+    if ((rc = rn_alloc(f, &vh.d.T, (size_t)vh.d.pp * KP + K * K + K))) break;
+    double* small = nullptr;
+    if ((rc = rn_alloc(f, &small, (size_t)4 * K * K + 4 * K + 8))) break;
+    vh.d.S = small;
+    vh.d.FtF = small + K * K;
+    vh.d.GtG = small + 2 * K * K;
+    vh.d.A = small + 3 * K * K;
+    vh.d.lam = small + 4 * K * K;
+    vh.d.mu = vh.d.lam + K;
+    vh.d.csF = vh.d.mu + K;
+    vh.d.csG = vh.d.csF + K;
+    vh.d.scal = vh.d.csG + K;
+    if ((rc = rn_alloc(f, &vh.d.misc_ticket, 4))) break;
+    if ((rc = rn_alloc(f, &vh.d.flags, 4))) break;
+    if ((rc = rn_alloc(f, &vh.xpart, 1024))) break;
+    if ((rc = rn_alloc(f, &vh.xticket, 1))) break;
+  }
+  if (rc) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_views, (size_t)V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_ctrl, 1))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_phi, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_xi, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_psi, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_rowmap, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_colmap, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_rowmode, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_colmode, (size_t)V * V))) return fail(rc);
+  if ((rc = rn_alloc(f, &f->d_hist, (size_t)f->hist_cap))) return fail(rc);
+  f->h_rowmap.assign((size_t)V * V, nullptr);
+  f->h_colmap.assign((size_t)V * V, nullptr);
+  f->h_rowmode.assign((size_t)V * V, RN_MODE_NULL);
+  f->h_colmode.assign((size_t)V * V, RN_MODE_NULL);
+  f->h_phi.assign((size_t)V * V, 0.0);
+  f->h_xi.assign((size_t)V * V, 0.0);
+  f->h_psi.assign((size_t)V * V, 0.0);
+  std::memset(&f->d, 0, sizeof(RnFit));
+  std::memset(&f->h_ctrl, 0, sizeof(RnCtrl));
+  *out = f;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_destroy(resnmtf_fit* fit) {
+  if (!fit) return RESNMTF_OK;
+  cudaSetDevice(fit->ctx->device);
+  cudaStreamSynchronize(fit->ctx->stream);
+  if (fit->graph_exec) cudaGraphExecDestroy(fit->graph_exec);
+  if (fit->graph) cudaGraphDestroy(fit->graph);
+  for (void* p : fit->allocs) cudaFree(p);
+  delete fit;
+  return RESNMTF_OK;
+}
+
+static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld, cudaMemcpyKind kind,
+                           const char* who) {
+  RN_CHECK(fit && x, RESNMTF_E_INVALID, std::string(who) + ": NULL argument");
+  RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, std::string(who) + ": view index out of range");
+  ViewHost& vh = fit->views[v];
+  RN_CHECK(ld >= vh.d.n, RESNMTF_E_INVALID, std::string(who) + ": ld < n");
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  cudaStream_t st = fit->ctx->stream;
+  // padding rows/columns were zeroed at allocation and are never written
+  RN_CUDA(cudaMemcpy2DAsync(vh.d.X, (size_t)vh.d.ldx * sizeof(double), x, (size_t)ld * sizeof(double),
+                            (size_t)vh.d.n * sizeof(double), (size_t)vh.d.p, kind, st));
+  const int nblk = 1024;
+  rn_xnorm2<<<nblk, 256, 0, st>>>(vh.d, vh.xpart, vh.xticket);
+  RN_CUDA(cudaGetLastError());
+  RN_CUDA(cudaStreamSynchronize(st));  // the host buffer is only borrowed for the call
+  vh.has_data = true;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_set_data(resnmtf_fit* fit, int v, const double* x, int64_t ld) {
+  return set_data_common(fit, v, x, ld, cudaMemcpyHostToDevice, "resnmtf_fit_set_data");
+}
+extern "C" int resnmtf_fit_set_data_device(resnmtf_fit* fit, int v, const double* x, int64_t ld) {
+  return set_data_common(fit, v, x, ld, cudaMemcpyDeviceToDevice, "resnmtf_fit_set_data_device");
+}
+
+extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f, const double* s,
+                                       const double* g, const double* lambda, const double* mu) {
+  RN_CHECK(fit && f && s && g, RESNMTF_E_INVALID, "resnmtf_fit_set_factors: NULL argument");
+  RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, "resnmtf_fit_set_factors: view index out of range");
+  ViewHost& vh = fit->views[v];
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  cudaStream_t st = fit->ctx->stream;
+  const int K = vh.d.k, KP = vh.d.kp;
+  const int64_t n = vh.d.n, p = vh.d.p;
+  RN_CUDA(cudaMemsetAsync(vh.d.F, 0, (size_t)vh.d.ldx * KP * sizeof(double), st));
+  RN_CUDA(cudaMemcpy2DAsync(vh.d.F, (size_t)vh.d.ldx * sizeof(double), f, (size_t)n * sizeof(double),
+                            (size_t)n * sizeof(double), (size_t)K, cudaMemcpyHostToDevice, st));
+  std::vector<double> gt((size_t)vh.d.pp * KP, 0.0);  // G is row-major [pp][kp] on the device
+  for (int c = 0; c < K; ++c)
+    for (int64_t j = 0; j < p; ++j) gt[(size_t)j * KP + c] = g[(size_t)c * p + j];
+  RN_CUDA(cudaMemcpyAsync(vh.d.G, gt.data(), gt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(vh.d.S, s, (size_t)K * K * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (lambda) RN_CUDA(cudaMemcpyAsync(vh.d.lam, lambda, K * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mu) RN_CUDA(cudaMemcpyAsync(vh.d.mu, mu, K * sizeof(double), cudaMemcpyHostToDevice, st));
+  rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);
+  rn_default_lm<<<1, 32, 0, st>>>(vh.d, lambda ? 0 : 1, mu ? 0 : 1);
+  RN_CUDA(cudaGetLastError());
+  RN_CUDA(cudaStreamSynchronize(st));
+  vh.has_factors = true;
+  // a new set of factors starts a new loop: reset the history and the stop-rule state
+  fit->errors.clear();
+  std::memset(&fit->h_ctrl, 0, sizeof(RnCtrl));
+  fit->counters.iterations = 0;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_set_restrictions(resnmtf_fit* fit, const double* phi, const double* xi,
+                                            const double* psi) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_restrictions: fit is NULL");
+  const size_t VV = (size_t)fit->V * fit->V;
+  auto put = [&](std::vector<double>& dst, const double* src, const char* name) -> int {
+    for (size_t i = 0; i < VV; ++i) {
+      const double x = src ? src[i] : 0.0;
+      RN_CHECK(!(x < 0.0), RESNMTF_E_INVALID, std::string(name) + " must be a non-negative matrix");
+      dst[i] = x;
+    }
+    return RESNMTF_OK;
+  };
+  int rc;
+  if ((rc = put(fit->h_phi, phi, "phi"))) return rc;
+  if ((rc = put(fit->h_xi, xi, "xi"))) return rc;
+  if ((rc = put(fit->h_psi, psi, "psi"))) return rc;
+  // xi couples S matrices element-wise: the coupled views must share k (star_prod, R/utils.r:39-47)
+  for (int v = 0; v < fit->V; ++v)
+    for (int w = 0; w < fit->V; ++w)
+      if (fit->h_xi[w + (size_t)v * fit->V] != 0.0 && w != v)
+        RN_CHECK(fit->views[v].d.k == fit->views[w].d.k, RESNMTF_E_INVALID,
+                 "xi couples views with different k (non-conformable arrays in the reference)");
+  fit->meta_dirty = true;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int w, const int32_t* idx_v,
+                                          const int32_t* idx_w, int64_t len) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_shared_map: fit is NULL");
+  RN_CHECK(kind == RESNMTF_MAP_ROW || kind == RESNMTF_MAP_COL, RESNMTF_E_INVALID,
+           "resnmtf_fit_set_shared_map: bad kind");
+  RN_CHECK(v >= 0 && v < fit->V && w >= 0 && w < fit->V && v != w, RESNMTF_E_INVALID,
+           "resnmtf_fit_set_shared_map: bad view pair");
+  RN_CHECK(len >= 0 && (len == 0 || (idx_v && idx_w)), RESNMTF_E_INVALID,
+           "resnmtf_fit_set_shared_map: NULL index array");
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  const bool row = kind == RESNMTF_MAP_ROW;
+  ViewHost& vh = fit->views[v];
+  const ViewHost& wh = fit->views[w];
+  const int64_t dim_v = row ? vh.d.n : vh.d.p, dim_w = row ? wh.d.n : wh.d.p;
+  const size_t slot = (size_t)w + (size_t)v * fit->V;
+  std::vector<int8_t>& modes = row ? fit->h_rowmode : fit->h_colmode;
+  std::vector<const int32_t*>& ptrs = row ? fit->h_rowmap : fit->h_colmap;
+  std::vector<int32_t*>& own = row ? vh.rowmaps : vh.colmaps;
+  if (len == 0) {
+    modes[slot] = RN_MODE_NA;
+    ptrs[slot] = nullptr;
+    fit->meta_dirty = true;
+    return RESNMTF_OK;
+  }
+  std::vector<int32_t> map((size_t)dim_v, -1);
+  for (int64_t i = 0; i < len; ++i) {
+    RN_CHECK(idx_v[i] >= 0 && idx_v[i] < dim_v && idx_w[i] >= 0 && idx_w[i] < dim_w, RESNMTF_E_INVALID,
+             "resnmtf_fit_set_shared_map: index out of range");
+    map[(size_t)idx_v[i]] = idx_w[i];
+  }
+  if (!own[w]) {
+    int rc = rn_alloc(fit, &own[w], (size_t)dim_v, false);
+    if (rc) return rc;
+  }
+  RN_CUDA(cudaMemcpyAsync(own[w], map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                          fit->ctx->stream));
+  RN_CUDA(cudaStreamSynchronize(fit->ctx->stream));
+  modes[slot] = RN_MODE_MAP;
+  ptrs[slot] = own[w];
+  fit->meta_dirty = true;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_options: fit is NULL");
+  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 2, RESNMTF_E_INVALID,
+           "resnmtf_fit_set_options: unknown option value");
+  if (fit->err_mode != err_mode) fit->meta_dirty = true;
+  if (fit->impl_req != impl) fit->plan_dirty = true;
+  fit->err_mode = err_mode;
+  fit->impl_req = impl;
+  return RESNMTF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: grids, workspaces, device metadata, per-iteration graph
+// ------------------------------------------------------------------------------------------------
+static int rn_env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : dflt;
+}
+
+static int build_plan(resnmtf_fit* fit) {
+  const int sms = fit->ctx->sm_count;
+  int impl = fit->impl_req;
+  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_DMMA);
+  if (impl != RESNMTF_IMPL_DFMA && impl != RESNMTF_IMPL_DMMA) impl = RESNMTF_IMPL_DMMA;
+  fit->impl = impl;
+  const int f_target = sms * rn_env_int("RESNMTF_F_CTAS_PER_SM", 3);
+  const int g_target_mma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM", 4);
+  const int g_target_dfma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM_DFMA", 3);
+  int rc;
+  for (int v = 0; v < fit->V; ++v) {
+    ViewHost& vh = fit->views[v];
+    RnView& d = vh.d;
+    const bool mma = impl == RESNMTF_IMPL_DMMA && d.k <= 8;
+    const int K = d.k, KP = d.kp;
+    // F step: one CTA per 64-row tile; split the columns only when there are too few tiles to fill
+    // the machine (each split keeps >= 64 data columns)
+    d.row_tiles = (int)(d.ldx / RN_ROW_TILE);
+    int cs = 1;
+    if (d.row_tiles < f_target) cs = (f_target + d.row_tiles - 1) / d.row_tiles;
+    cs = std::max(1, std::min<int>(cs, (int)std::max<int64_t>(1, d.pp / 64)));
+    cs = rn_env_int("RESNMTF_F_CS", cs);
+    d.cs = cs;
+    // G stream: one CTA per column group; split the row steps to fill the machine
+    const int grp_cols = mma ? RN_COL_GROUP : RN_COL_GROUP_DFMA;
+    d.col_groups = (int)((d.pp + grp_cols - 1) / grp_cols);
+    const int target = mma ? g_target_mma : g_target_dfma;
+    int rs = std::max(1, (target + d.col_groups / 2) / d.col_groups);
+    const int min_steps = mma ? 4 : 1;
+    rs = std::max(1, std::min<int>(rs, std::max(1, d.row_tiles / min_steps)));
+    rs = rn_env_int("RESNMTF_G_RS", rs);
+    rs = std::max(1, std::min(rs, d.row_tiles));
+    d.rs = rs;
+    d.nff = mma ? rs : std::max(1, std::min(sms, (int)((d.ldx + 255) / 256)));
+    d.gepi_ctas = (int)((d.p + RN_GEPI_THREADS(K) - 1) / RN_GEPI_THREADS(K));
+    d.resid_cs = cs;
+    // workspaces (old ones are released first when the plan is rebuilt)
+    if ((rc = rn_free(fit, d.Ppart))) return rc;
+    if ((rc = rn_free(fit, d.Tpart))) return rc;
+    if ((rc = rn_free(fit, d.FFpart))) return rc;
+    if ((rc = rn_free(fit, d.GGpart))) return rc;
+    if ((rc = rn_free(fit, d.Rpart))) return rc;
+    if ((rc = rn_free(fit, d.tile_ticket))) return rc;
+    if ((rc = rn_free(fit, d.group_ticket))) return rc;
+    d.Ppart = d.Tpart = d.FFpart = d.GGpart = d.Rpart = nullptr;
+    d.tile_ticket = d.group_ticket = nullptr;
+    if (d.cs > 1 && (rc = rn_alloc(fit, &d.Ppart, (size_t)d.cs * d.ldx * KP))) return rc;
+    if (d.rs > 1 && (rc = rn_alloc(fit, &d.Tpart, (size_t)d.rs * d.pp * KP))) return rc;
+    if ((rc = rn_alloc(fit, &d.FFpart, (size_t)d.nff * (K * K + K)))) return rc;
+    if ((rc = rn_alloc(fit, &d.GGpart, (size_t)d.gepi_ctas * (2 * K * K + K)))) return rc;
+    if ((rc = rn_alloc(fit, &d.Rpart, (size_t)d.row_tiles * d.resid_cs))) return rc;
+    if ((rc = rn_alloc(fit, &d.tile_ticket, (size_t)d.row_tiles))) return rc;
+    if ((rc = rn_alloc(fit, &d.group_ticket, (size_t)d.col_groups))) return rc;
+  }
+  fit->plan_dirty = false;
+  fit->meta_dirty = true;
+  if (fit->graph_exec) {
+    cudaGraphExecDestroy(fit->graph_exec);
+    fit->graph_exec = nullptr;
+  }
+  if (fit->graph) {
+    cudaGraphDestroy(fit->graph);
+    fit->graph = nullptr;
+  }
+  return RESNMTF_OK;
+}
+
+static int sync_meta(resnmtf_fit* fit) {
+  cudaStream_t st = fit->ctx->stream;
+  const int V = fit->V;
+  const size_t VV = (size_t)V * V;
+  std::vector<RnView> hv(V);
+  for (int v = 0; v < V; ++v) hv[v] = fit->views[v].d;
+  RN_CUDA(cudaMemcpyAsync(fit->d_views, hv.data(), V * sizeof(RnView), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_phi, fit->h_phi.data(), VV * sizeof(double), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_xi, fit->h_xi.data(), VV * sizeof(double), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_psi, fit->h_psi.data(), VV * sizeof(double), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_rowmap, fit->h_rowmap.data(), VV * sizeof(int32_t*), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_colmap, fit->h_colmap.data(), VV * sizeof(int32_t*), cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_rowmode, fit->h_rowmode.data(), VV, cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaMemcpyAsync(fit->d_colmode, fit->h_colmode.data(), VV, cudaMemcpyHostToDevice, st));
+  RN_CUDA(cudaStreamSynchronize(st));
+  RnFit& d = fit->d;
+  d.n_views = V;
+  d.err_mode = fit->err_mode;
+  d.views = fit->d_views;
+  d.ctrl = fit->d_ctrl;
+  d.phi = fit->d_phi;
+  d.xi = fit->d_xi;
+  d.psi = fit->d_psi;
+  d.rowmap = fit->d_rowmap;
+  d.colmap = fit->d_colmap;
+  d.rowmode = fit->d_rowmode;
+  d.colmode = fit->d_colmode;
+  d.hist = fit->d_hist;
+  d.hist_cap = fit->hist_cap;
+  double ps = 0.0, xs = 0.0;  // whole-matrix sums: the branch tests of update_g / update_s
+  for (size_t i = 0; i < VV; ++i) {
+    ps += fit->h_psi[i];
+    xs += fit->h_xi[i];
+  }
+  d.psi_total = ps;
+  d.xi_total = xs;
+  fit->meta_dirty = false;
+  // kernel parameters are baked into the graph: rebuild it
+  if (fit->graph_exec) {
+    cudaGraphExecDestroy(fit->graph_exec);
+    fit->graph_exec = nullptr;
+  }
+  if (fit->graph) {
+    cudaGraphDestroy(fit->graph);
+    fit->graph = nullptr;
+  }
+  return RESNMTF_OK;
+}
+
+// Enqueues one update-iteration (all views, Gauss-Seidel order) on `st`.  When ev is non-null it holds
+// 2 events per launch for the profiling entry point.
+static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<cudaEvent_t>* ev,
+                                 std::vector<int>* ev_class) {
+  int64_t launches = 0;
+  auto mark = [&](int cls) {
+    if (!ev) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev->push_back(e);
+    ev_class->push_back(cls);
+  };
+  for (int v = 0; v < fit->V; ++v) {
+    const ViewHost& vh = fit->views[v];
+    mark(0);
+    launch_f_step(vh, fit->d, v, fit->impl, st);
+    launches += 1;
+    mark(1);
+    launches += launch_g_stream(vh, fit->d, fit->impl, st);
+    mark(2);
+    launch_g_epilogue(vh, fit->d, v, st);
+    launches += 1;
+    if (fit->err_mode != RESNMTF_ERR_ALGEBRAIC) {
+      mark(3);
+      launch_residual(vh, fit->d, st);
+      launches += 1;
+    }
+  }
+  mark(4);
+  rn_finish<<<1, 1, 0, st>>>(fit->d);
+  launches += 1;
+  mark(-1);
+  return launches;
+}
+
+static int prepare(resnmtf_fit* fit) {
+  for (int v = 0; v < fit->V; ++v) {
+    RN_CHECK(fit->views[v].has_data, RESNMTF_E_STATE, "resnmtf: set_data was not called for every view");
+    RN_CHECK(fit->views[v].has_factors, RESNMTF_E_STATE, "resnmtf: set_factors was not called for every view");
+  }
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  int rc;
+  if (fit->plan_dirty && (rc = build_plan(fit))) return rc;
+  if (fit->meta_dirty && (rc = sync_meta(fit))) return rc;
+  if (!fit->graph_exec && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
+    cudaStream_t st = fit->ctx->stream;
+    RN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    fit->launches_per_iter = enqueue_iteration(fit, st, nullptr, nullptr);
+    cudaError_t le = cudaGetLastError();
+    cudaError_t ce = cudaStreamEndCapture(st, &fit->graph);
+    if (le != cudaSuccess) return rn_fail(RESNMTF_E_CUDA, std::string("kernel launch during capture: ") + cudaGetErrorString(le));
+    RN_CUDA(ce);
+    RN_CUDA(cudaGraphInstantiate(&fit->graph_exec, fit->graph, 0));
+  }
+  return RESNMTF_OK;
+}
+
+static int push_ctrl(resnmtf_fit* fit) {
+  RN_CUDA(cudaMemcpyAsync(fit->d_ctrl, &fit->h_ctrl, sizeof(RnCtrl), cudaMemcpyHostToDevice, fit->ctx->stream));
+  return RESNMTF_OK;
+}
+
+// Reads the control block and drains the error history accumulated since the last call.
+static int pull_ctrl(resnmtf_fit* fit) {
+  cudaStream_t st = fit->ctx->stream;
+  RN_CUDA(cudaMemcpyAsync(&fit->h_ctrl, fit->d_ctrl, sizeof(RnCtrl), cudaMemcpyDeviceToHost, st));
+  RN_CUDA(cudaStreamSynchronize(st));
+  const int64_t cnt = std::min<int64_t>(fit->h_ctrl.hist_count, fit->hist_cap);
+  if (cnt > 0) {
+    const size_t old = fit->errors.size();
+    fit->errors.resize(old + (size_t)cnt);
+    RN_CUDA(cudaMemcpy(fit->errors.data() + old, fit->d_hist, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  fit->h_ctrl.hist_count = 0;
+  if (cnt > 0) {  // nothing is in flight here: hand the drained history buffer back to the device
+    RN_CUDA(cudaMemcpyAsync(fit->d_ctrl, &fit->h_ctrl, sizeof(RnCtrl), cudaMemcpyHostToDevice, st));
+  }
+  return RESNMTF_OK;
+}
+
+static int run_batch(resnmtf_fit* fit, int64_t iters) {
+  cudaStream_t st = fit->ctx->stream;
+  for (int64_t i = 0; i < iters; ++i) {
+    if (fit->graph_exec) {
+      RN_CUDA(cudaGraphLaunch(fit->graph_exec, st));
+    } else {
+      fit->launches_per_iter = enqueue_iteration(fit, st, nullptr, nullptr);
+      RN_CUDA(cudaGetLastError());
+    }
+  }
+  fit->counters.kernel_launches += iters * fit->launches_per_iter;
+  return RESNMTF_OK;
+}
+
+static double alg_bytes_per_iter(const resnmtf_fit* fit) {
+  // B_alg = sum_v 8 * [2 n p + 4 n k + 4 p k + C_v]
+  double b = 0.0;
+  const int V = fit->V;
+  for (int v = 0; v < V; ++v) {
+    const RnView& d = fit->views[v].d;
+    double cv = 0.0;
+    for (int w = 0; w < V; ++w) {
+      if (w == v) continue;
+      if (fit->h_phi[w + (size_t)v * V] != 0.0 && fit->h_rowmode[w + (size_t)v * V] != RN_MODE_NA) cv += (double)d.n * d.k;
+      if (fit->h_psi[w + (size_t)v * V] != 0.0 && fit->h_colmode[w + (size_t)v * V] != RN_MODE_NA) cv += (double)d.p * d.k;
+    }
+    b += 8.0 * (2.0 * d.n * d.p + 4.0 * d.n * d.k + 4.0 * d.p * d.k + cv);
+  }
+  return b;
+}
+
+extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, int64_t max_iters,
+                               int64_t* iters_done) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_run: fit is NULL");
+  int rc;
+  if ((rc = prepare(fit))) return rc;
+  cudaStream_t st = fit->ctx->stream;
+  const bool conv = n_iters < 0;
+  fit->h_ctrl.done = 0;
+  fit->h_ctrl.conv_mode = conv ? 1 : 0;
+  fit->h_ctrl.tol = tol;
+  fit->h_ctrl.hist_count = 0;
+  fit->h_ctrl.direct_passes = 0;
+  if ((rc = push_ctrl(fit))) return rc;
+  fit->counters.kernel_launches = 0;
+  const int64_t it0 = fit->h_ctrl.iters;
+  RN_CUDA(cudaEventRecord(fit->ctx->ev0, st));
+  if (!conv) {
+    int64_t left = n_iters;
+    while (left > 0) {
+      const int64_t b = std::min<int64_t>(left, fit->hist_cap);
+      if ((rc = run_batch(fit, b))) return rc;
+      left -= b;
+      if (left > 0 && (rc = pull_ctrl(fit))) return rc;
+    }
+  } else {
+    const int64_t batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 8));
+    for (;;) {
+      int64_t b = batch;
+      const int64_t donei = fit->h_ctrl.iters - it0;
+      if (max_iters > 0) b = std::min(b, max_iters - donei);
+      if (b <= 0) break;
+      if ((rc = run_batch(fit, b))) return rc;
+      if ((rc = pull_ctrl(fit))) return rc;
+      if (fit->h_ctrl.done) break;
+    }
+  }
+  RN_CUDA(cudaEventRecord(fit->ctx->ev1, st));
+  if ((rc = pull_ctrl(fit))) return rc;
+  float ms = 0.f;
+  RN_CUDA(cudaEventElapsedTime(&ms, fit->ctx->ev0, fit->ctx->ev1));
+  fit->counters.device_ms = ms;
+  fit->counters.iterations = fit->h_ctrl.iters;
+  fit->counters.converged = fit->h_ctrl.done == 1;
+  fit->counters.impl = fit->impl;
+  fit->counters.direct_error_passes = fit->h_ctrl.direct_passes;
+  fit->counters.alg_bytes_per_iter = alg_bytes_per_iter(fit);
+  if (iters_done) *iters_done = fit->h_ctrl.iters - it0;
+  if (conv && fit->h_ctrl.done == 2)
+    return rn_fail(RESNMTF_E_NAN, "mean error is NaN: missing value where TRUE/FALSE needed (R/main.r:55)");
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_step(resnmtf_fit* fit) { return resnmtf_fit_run(fit, 1, 0.0, 0, nullptr); }
+
+extern "C" int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[5], int64_t launches[5]) {
+  RN_CHECK(fit && ms && launches, RESNMTF_E_INVALID, "resnmtf_fit_profile: NULL argument");
+  int rc;
+  if ((rc = prepare(fit))) return rc;
+  cudaStream_t st = fit->ctx->stream;
+  fit->h_ctrl.done = 0;
+  fit->h_ctrl.conv_mode = 0;
+  fit->h_ctrl.hist_count = 0;
+  if ((rc = push_ctrl(fit))) return rc;
+  for (int i = 0; i < 5; ++i) {
+    ms[i] = 0.0;
+    launches[i] = 0;
+  }
+  for (int64_t it = 0; it < n_iters; ++it) {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+    enqueue_iteration(fit, st, &ev, &cls);
+    RN_CUDA(cudaGetLastError());
+    RN_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i + 1 < ev.size(); ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      if (cls[i] >= 0 && cls[i] < 5) {
+        ms[cls[i]] += t;
+        launches[cls[i]] += 1;
+      }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (((it + 1) % fit->hist_cap) == 0 && (rc = pull_ctrl(fit))) return rc;
+  }
+  if ((rc = pull_ctrl(fit))) return rc;
+  fit->counters.iterations = fit->h_ctrl.iters;
+  return RESNMTF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+extern "C" int resnmtf_fit_get_factors(resnmtf_fit* fit, int v, double* f, double* s, double* g,
+                                       double* lambda, double* mu) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_get_factors: fit is NULL");
+  RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, "resnmtf_fit_get_factors: view index out of range");
+  const ViewHost& vh = fit->views[v];
+  RN_CHECK(vh.has_factors, RESNMTF_E_STATE, "resnmtf_fit_get_factors: factors were never set");
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  cudaStream_t st = fit->ctx->stream;
+  const int K = vh.d.k, KP = vh.d.kp;
+  const int64_t n = vh.d.n, p = vh.d.p;
+  std::vector<double> gt;
+  if (f)
+    RN_CUDA(cudaMemcpy2DAsync(f, (size_t)n * sizeof(double), vh.d.F, (size_t)vh.d.ldx * sizeof(double),
+                              (size_t)n * sizeof(double), (size_t)K, cudaMemcpyDeviceToHost, st));
+  if (g) {
+    gt.resize((size_t)vh.d.pp * KP);
+    RN_CUDA(cudaMemcpyAsync(gt.data(), vh.d.G, gt.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  if (s) RN_CUDA(cudaMemcpyAsync(s, vh.d.S, (size_t)K * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (lambda) RN_CUDA(cudaMemcpyAsync(lambda, vh.d.lam, K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (mu) RN_CUDA(cudaMemcpyAsync(mu, vh.d.mu, K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RN_CUDA(cudaStreamSynchronize(st));
+  if (g)
+    for (int c = 0; c < K; ++c)
+      for (int64_t j = 0; j < p; ++j) g[(size_t)c * p + j] = gt[(size_t)j * KP + c];
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_normalise(resnmtf_fit* fit) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_normalise: fit is NULL");
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  cudaStream_t st = fit->ctx->stream;
+  for (int v = 0; v < fit->V; ++v) {
+    const ViewHost& vh = fit->views[v];
+    RN_CHECK(vh.has_factors, RESNMTF_E_STATE, "resnmtf_fit_normalise: factors were never set");
+    rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);
+    const int64_t m = std::max(vh.d.n, vh.d.p);
+    rn_normalise<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(vh.d);
+    rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);  // keep G'G / colsums consistent with the scaled factors
+  }
+  RN_CUDA(cudaGetLastError());
+  RN_CUDA(cudaStreamSynchronize(st));
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_get_errors(resnmtf_fit* fit, double* out, int64_t cap, int64_t* count) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_get_errors: fit is NULL");
+  const int64_t n = (int64_t)fit->errors.size();
+  if (count) *count = n;
+  if (out && cap > 0) std::memcpy(out, fit->errors.data(), (size_t)std::min(n, cap) * sizeof(double));
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_get_view_errors(resnmtf_fit* fit, double* err, double* data_norms) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_get_view_errors: fit is NULL");
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  for (int v = 0; v < fit->V; ++v) {
+    double sc[2];
+    RN_CUDA(cudaMemcpy(sc, fit->views[v].d.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (data_norms) data_norms[v] = sc[0];
+    if (err) err[v] = sc[1];
+  }
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_get_counters(resnmtf_fit* fit, resnmtf_counters* out) {
+  RN_CHECK(fit && out, RESNMTF_E_INVALID, "resnmtf_fit_get_counters: NULL argument");
+  fit->counters.alg_bytes_per_iter = alg_bytes_per_iter(fit);
+  *out = fit->counters;
+  return RESNMTF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-sharded path (NCCL) -- see DESIGN.md "Multi-GPU"
+// ------------------------------------------------------------------------------------------------
+extern "C" int resnmtf_comm_id_size(void) {
+#ifdef RESNMTF_WITH_NCCL
+  return (int)sizeof(ncclUniqueId);
+#else
+  return 0;
+#endif
+}
+
+extern "C" int resnmtf_comm_id_create(void* id_out) {
+#ifdef RESNMTF_WITH_NCCL
+  RN_CHECK(id_out != nullptr, RESNMTF_E_INVALID, "resnmtf_comm_id_create: NULL argument");
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) return rn_fail(RESNMTF_E_COMM, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+  std::memcpy(id_out, &id, sizeof(id));
+  return RESNMTF_OK;
+#else
+  (void)id_out;
+  return rn_fail(RESNMTF_E_UNSUPPORTED, "library was built without NCCL");
+#endif
+}
+
+extern "C" int resnmtf_ctx_join(resnmtf_ctx* ctx, const void* id, int rank, int n_ranks) {
+  (void)ctx; (void)id; (void)rank; (void)n_ranks;
+  return rn_fail(RESNMTF_E_UNSUPPORTED, "row-sharded views are not implemented yet");
+}

@@ -1,0 +1,82 @@
+// Device-side descriptors shared by the kernels and the host C-ABI (resnmtf_capi.cu).
+// Data layout in HBM (see DESIGN.md "Data layout"):
+//   X   [pp][ldx]  column-major like R, rows padded to a multiple of 64 (ldx), columns to a multiple
+//                  of 8 (pp); all padding is zero so the streaming kernels need no bounds checks.
+//   F   [kp][ldx]  column-major, kp = 8 (k<=8) or 16; padding rows/columns zero.
+//   G,T [pp][kp]   row-major (one 64 B / 128 B row per data column) so that a column's k values are one
+//                  uniform / vector load in the X.G pass and one gather in the psi coupling.
+//   S, F'F, G'G, A  k x k column-major compact, lambda/mu/colsums length k.
+#pragma once
+#include <stdint.h>
+
+#define RN_MAXK 16
+#define RN_ROW_TILE 64   // rows per F-step tile and per G-stream row step
+#define RN_COL_GROUP 64  // data columns per G-stream CTA (tensor-core path)
+#define RN_COL_GROUP_DFMA 32
+#define RN_GEPI_THREADS(k) ((k) <= 8 ? 256 : 128)
+
+#define RN_MODE_NULL 0  // pair never set: R's `indices = NULL` (nothing overwritten)
+#define RN_MODE_NA 1    // pair shares no names: skipped
+#define RN_MODE_MAP 2   // int32 gather map, -1 = name not shared
+
+struct RnCtrl {
+  int32_t done;       // 0 running, 1 converged, 2 mean error is NaN (convergence mode only)
+  int32_t conv_mode;  // 1: apply the stop rule of R/main.r:55
+  int64_t iters;      // sweeps since set_factors
+  int64_t hist_count; // entries in hist[] since the host last drained it
+  double prev_err;    // err_temp of R/main.r:54,80
+  double tol;
+  double last_diff;
+  int64_t direct_passes;
+};
+
+struct RnView {
+  int64_t n, p, ldx, pp;
+  int32_t k, kp;
+  double* X;
+  double* F;
+  double* G;
+  double* T;
+  double* S;    // k*k
+  double* FtF;  // k*k
+  double* GtG;  // k*k
+  double* A;    // k*k   A = (F'X)G = T'G
+  double* lam;  // k
+  double* mu;   // k
+  double* csF;  // k
+  double* csG;  // k
+  double* scal; // [0] ||X||^2  [1] err  [2] err algebraic  [3] err direct  [4] global F'F etc scratch
+  double* Ppart;   // [cs][ldx][kp]   F-step partial X.G per column split (cs > 1 only)
+  double* Tpart;   // [rs][pp][kp]    G-stream partial X'F per row split
+  double* FFpart;  // [nff][k*k+k]    partial F'F | colSums(F)
+  double* GGpart;  // [gepi_ctas][2*k*k+k]  partial G'G | A | colSums(G)
+  double* Rpart;   // [resid ctas]    partial residual sums
+  int32_t* tile_ticket;   // [row tiles]
+  int32_t* group_ticket;  // [col groups]
+  int32_t* misc_ticket;   // [0] G-epilogue  [1] residual
+  int32_t* flags;         // [0] need_direct
+  int32_t row_tiles, cs;       // F-step grid
+  int32_t col_groups, rs;      // G-stream grid
+  int32_t nff;                 // number of FFpart rows
+  int32_t gepi_ctas;           // G-epilogue grid
+  int32_t resid_cs;            // residual grid y
+  int32_t sharded;             // 1: rows are sharded over ranks (epilogue scalars come from all-reduce)
+};
+
+struct RnFit {
+  int32_t n_views;
+  int32_t err_mode;
+  const RnView* views;   // device array [n_views]
+  RnCtrl* ctrl;
+  const double* phi;     // [V*V] column-major, symmetrised
+  const double* xi;
+  const double* psi;
+  const int32_t* const* rowmap;  // [V*V]: rowmap[w + v*V] = map of view v's rows into view w
+  const int32_t* const* colmap;
+  const int8_t* rowmode;         // [V*V]
+  const int8_t* colmode;
+  double* hist;          // mean error per sweep (drained by the host)
+  int64_t hist_cap;
+  double psi_total, xi_total;    // whole-matrix sums (branch tests of R/update_steps.r:190,226)
+  int64_t n_total_rows_scale;    // unused (kept for ABI stability of the struct)
+};

@@ -1,0 +1,189 @@
+"""Thin object layer over the C ABI: a ``Context`` (one GPU, one stream) and a ``DeviceFit`` that owns the
+device-resident X, F, S, G, lambda, mu of all views of one ``res_nmtf_inner`` call."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _f64(a):
+    """Column-major float64 copy/view of ``a`` (what R would hand over)."""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    def __init__(self, device=-1):
+        lib = L.require_device()
+        self._lib = lib
+        h = C.c_void_p()
+        L.check(lib.resnmtf_ctx_create(int(device), C.byref(h)))
+        self._h = h
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) the context launches on."""
+        return int(self._lib.resnmtf_ctx_stream(self._h) or 0)
+
+    def synchronize(self):
+        L.check(self._lib.resnmtf_ctx_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.resnmtf_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class DeviceFit:
+    """Device-resident state of one fit.  Shapes: view v is n[v] x p[v] with k[v] clusters."""
+
+    def __init__(self, ctx, n, p, k):
+        self._lib = L.require_device()
+        self.ctx = ctx
+        self.n = [int(x) for x in n]
+        self.p = [int(x) for x in p]
+        self.k = [int(x) for x in k]
+        self.n_views = len(self.n)
+        if not (len(self.p) == self.n_views == len(self.k)):
+            raise ValueError("n, p, k must have one entry per view")
+        V = self.n_views
+        an = (C.c_int64 * V)(*self.n)
+        ap = (C.c_int64 * V)(*self.p)
+        ak = (C.c_int32 * V)(*self.k)
+        h = C.c_void_p()
+        L.check(self._lib.resnmtf_fit_create(ctx._h, V, an, ap, ak, C.byref(h)))
+        self._h = h
+
+    # ---- inputs ------------------------------------------------------------------------------
+    def set_data(self, v, x):
+        """Host matrix (any layout; converted to column-major float64 if it is not already)."""
+        x = _f64(x)
+        if x.shape != (self.n[v], self.p[v]):
+            raise ValueError(f"view {v}: expected shape {(self.n[v], self.p[v])}, got {x.shape}")
+        L.check(self._lib.resnmtf_fit_set_data(self._h, v, _ptr(x), x.shape[0]))
+
+    def set_data_device(self, v, dev_ptr, ld):
+        """Column-major float64 matrix already resident on this context's GPU."""
+        L.check(self._lib.resnmtf_fit_set_data_device(self._h, v, C.c_void_p(int(dev_ptr)), int(ld)))
+
+    def set_factors(self, v, f, s, g, lam=None, mu=None):
+        f, s, g = _f64(f), _f64(s), _f64(g)
+        k = self.k[v]
+        if f.shape != (self.n[v], k) or g.shape != (self.p[v], k) or s.shape != (k, k):
+            raise ValueError(f"view {v}: factor shapes do not match n={self.n[v]}, p={self.p[v]}, k={k}")
+        lam = None if lam is None else np.ascontiguousarray(lam, dtype=np.float64)
+        mu = None if mu is None else np.ascontiguousarray(mu, dtype=np.float64)
+        L.check(self._lib.resnmtf_fit_set_factors(self._h, v, _ptr(f), _ptr(s), _ptr(g), _ptr(lam), _ptr(mu)))
+
+    def set_restrictions(self, phi=None, xi=None, psi=None):
+        mats = [None if m is None else _f64(m) for m in (phi, xi, psi)]
+        for m in mats:
+            if m is not None and m.shape != (self.n_views, self.n_views):
+                raise ValueError("restriction matrices must be n_views x n_views")
+        L.check(self._lib.resnmtf_fit_set_restrictions(self._h, *[_ptr(m) for m in mats]))
+
+    def set_shared_map(self, kind, v, w, idx_v, idx_w):
+        iv = np.ascontiguousarray(idx_v, dtype=np.int32)
+        iw = np.ascontiguousarray(idx_w, dtype=np.int32)
+        if iv.shape != iw.shape:
+            raise ValueError("idx_v and idx_w must have the same length")
+        L.check(self._lib.resnmtf_fit_set_shared_map(self._h, int(kind), int(v), int(w), _ptr(iv), _ptr(iw), iv.size))
+
+    def set_options(self, err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO):
+        L.check(self._lib.resnmtf_fit_set_options(self._h, int(err_mode), int(impl)))
+
+    # ---- the loop ----------------------------------------------------------------------------
+    def run(self, n_iters=None, tol=1.0e-6, max_iters=0):
+        """n_iters=None: until |d mean err| <= tol (R/main.r:55-81); else exactly n_iters sweeps."""
+        done = C.c_int64(0)
+        ni = -1 if n_iters is None else int(n_iters)
+        L.check(self._lib.resnmtf_fit_run(self._h, ni, float(tol), int(max_iters), C.byref(done)))
+        return int(done.value)
+
+    def step(self):
+        L.check(self._lib.resnmtf_fit_step(self._h))
+
+    def profile(self, n_iters):
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
+        L.check(self._lib.resnmtf_fit_profile(self._h, int(n_iters), ms, cnt))
+        names = ("f_step", "g_stream", "g_epilogue", "residual", "finish")
+        return {nm: {"ms": float(ms[i]), "intervals": int(cnt[i])} for i, nm in enumerate(names)}
+
+    # ---- outputs -----------------------------------------------------------------------------
+    def get_factors(self, v):
+        k = self.k[v]
+        f = np.empty((self.n[v], k), dtype=np.float64, order="F")
+        g = np.empty((self.p[v], k), dtype=np.float64, order="F")
+        s = np.empty((k, k), dtype=np.float64, order="F")
+        lam = np.empty(k, dtype=np.float64)
+        mu = np.empty(k, dtype=np.float64)
+        L.check(self._lib.resnmtf_fit_get_factors(self._h, v, _ptr(f), _ptr(s), _ptr(g), _ptr(lam), _ptr(mu)))
+        return f, s, g, lam, mu
+
+    def normalise(self):
+        L.check(self._lib.resnmtf_fit_normalise(self._h))
+
+    def errors(self):
+        cnt = C.c_int64(0)
+        L.check(self._lib.resnmtf_fit_get_errors(self._h, None, 0, C.byref(cnt)))
+        out = np.empty(int(cnt.value), dtype=np.float64)
+        if out.size:
+            L.check(self._lib.resnmtf_fit_get_errors(self._h, _ptr(out), out.size, C.byref(cnt)))
+        return out
+
+    def view_errors(self):
+        err = np.empty(self.n_views, dtype=np.float64)
+        norms = np.empty(self.n_views, dtype=np.float64)
+        L.check(self._lib.resnmtf_fit_get_view_errors(self._h, _ptr(err), _ptr(norms)))
+        return err, norms
+
+    def counters(self):
+        c = L.Counters()
+        L.check(self._lib.resnmtf_fit_get_counters(self._h, C.byref(c)))
+        return {name: getattr(c, name) for name, _ in L.Counters._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.resnmtf_fit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

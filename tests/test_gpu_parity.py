@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, sweep by sweep.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import RTOL, Problem, compare_trace, rel_err
+from oracle import resnmtf_oracle as O
+from resnmtf_b200 import _lib as L
+from resnmtf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def single_view_problem(n, p, k, seed, n_planted=4, sigma=1.0):
+    rng = np.random.default_rng(seed)
+    x, _, _ = synth.planted_view(n, p, n_planted, rng, row_prob=0.3, col_prob=0.3, sigma=sigma)
+    x = synth.prep(x)
+    f, s, g = synth.random_factors(n, p, k, rng)
+    return Problem([x], [k], [f], [s], [g])
+
+
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_single_view_every_k(ctx, k, impl):
+    prob = single_view_problem(300, 200, k, seed=100 + k)
+    compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=impl)
+
+
+@pytest.mark.parametrize("k", [9, 12, 16])
+def test_single_view_k_above_8(ctx, k):
+    prob = single_view_problem(200, 150, k, seed=200 + k, n_planted=6)
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT)
+
+
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (63, 7), (64, 8), (65, 9), (129, 65), (257, 93), (1000, 37)])
+def test_ragged_shapes(ctx, shape, impl):
+    n, p = shape
+    k = min(3, n, p)
+    prob = single_view_problem(n, p, k, seed=300 + n + p, n_planted=2)
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=impl)
+
+
+@pytest.mark.parametrize("err_mode", [L.ERR_AUTO, L.ERR_ALGEBRAIC, L.ERR_DIRECT])
+def test_error_modes(ctx, err_mode):
+    prob = single_view_problem(500, 260, 4, seed=42)
+    compare_trace(prob, ctx, n_iters=8, err_mode=err_mode)
+
+
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+def test_forced_splits(ctx, impl, monkeypatch):
+    """Column-split F step and row-split G stream (the cross-CTA partial + last-CTA paths)."""
+    monkeypatch.setenv("RESNMTF_F_CS", "3")
+    monkeypatch.setenv("RESNMTF_G_RS", "5")
+    prob = single_view_problem(1500, 700, 5, seed=7)
+    compare_trace(prob, ctx, n_iters=5, err_mode=L.ERR_DIRECT, impl=impl)
+    monkeypatch.setenv("RESNMTF_F_CS", "1")
+    monkeypatch.setenv("RESNMTF_G_RS", "1")
+    compare_trace(prob, ctx, n_iters=5, err_mode=L.ERR_DIRECT, impl=impl)
+
+
+def two_view_problem(seed, k=3, phi=0.0, psi=0.0, xi=0.0, partial=False):
+    views, _ = synth.block_views(2, block=40, n_blocks=3, seed=seed)
+    n = views[0].shape[0]
+    data = [synth.prep(x) for x in views]
+    rng = np.random.default_rng(seed + 1)
+    inits = [synth.random_factors(n, n, k, rng) for _ in range(2)]
+    rn = cn = None
+    if partial:
+        m = 2 * n // 3
+        rn = [[f"row_{i}" for i in range(1, n + 1)],
+              [f"row_{i}" for i in range(1, m + 1)] + [f"row_{i}" for i in range(n + 1, 2 * n - m + 1)]]
+        cn = [[f"col_{i}" for i in range(1, n + 1)],
+              [f"col_{i}" for i in range(1, m + 1)] + [f"col_{i}" for i in range(n + 1, 2 * n - m + 1)]]
+        # scramble view 2's order so the gather map is a real permutation
+        perm = rng.permutation(n)
+        data[1] = np.asfortranarray(data[1][perm][:, perm])
+        rn[1] = [rn[1][i] for i in perm]
+        cn[1] = [cn[1][i] for i in perm]
+    else:
+        rn = [[f"row_{i}" for i in range(1, n + 1)]] * 2
+        cn = [[f"col_{i}" for i in range(1, n + 1)]] * 2
+
+    def rest(val):
+        m_ = np.zeros((2, 2))
+        m_[0, 1] = val
+        return O.init_rest_mats(m_, 2)
+
+    return Problem(data, [k, k], [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
+                   phi=rest(phi), xi=rest(xi), psi=rest(psi), row_names=rn, col_names=cn)
+
+
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("cfg", [
+    dict(phi=200.0), dict(psi=200.0), dict(xi=50.0), dict(phi=200.0, psi=100.0, xi=50.0),
+    dict(phi=1000.0, psi=1000.0, partial=True), dict(phi=5.0, partial=True),
+])
+def test_two_views_coupled(ctx, cfg, impl):
+    prob = two_view_problem(seed=11, **cfg)
+    compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=impl)
+
+
+def test_three_views_mixed_k_and_na_pairs(ctx):
+    """Unequal shapes, unequal k (no xi), one pair sharing nothing (R's NA -> skipped)."""
+    rng = np.random.default_rng(5)
+    shapes = [(120, 80), (120, 50), (90, 80)]
+    ks = [3, 4, 2]
+    data = [synth.prep(synth.planted_view(n, p, 3, rng, 0.3, 0.3)[0]) for n, p in shapes]
+    inits = [synth.random_factors(n, p, k, rng) for (n, p), k in zip(shapes, ks)]
+    rn = [[f"r{i}" for i in range(120)], [f"r{i}" for i in range(120)], [f"q{i}" for i in range(90)]]
+    cn = [[f"c{i}" for i in range(80)], [f"d{i}" for i in range(50)], [f"c{i}" for i in range(80)]]
+    phi = np.zeros((3, 3)); phi[0, 1] = 30.0; phi[0, 2] = 7.0   # (0,2) share no row names -> NA
+    psi = np.zeros((3, 3)); psi[0, 2] = 40.0
+    prob = Problem(data, ks, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
+                   phi=O.init_rest_mats(phi, 3), psi=O.init_rest_mats(psi, 3), row_names=rn, col_names=cn)
+    compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT)
+
+
+def test_convergence_matches_oracle(ctx):
+    """Stop rule of R/main.r:55: same number of sweeps, same All_Error, identical binarised output."""
+    views, _ = synth.block_views(2, seed=3)
+    data = [synth.prep(x) for x in views]
+    rng = np.random.default_rng(9)
+    k = 3
+    noise = [np.abs(np.sqrt(0.05) * rng.standard_normal((k, k))) for _ in range(2)]
+    fs, ss, gs, _, _ = O.init_mats_inner(data, [k, k], noise)
+    prob = Problem(data, [k, k], fs, ss, gs)
+    ref = prob.oracle()
+    fit = prob.device_fit(ctx)
+    try:
+        done = fit.run(None, 1.0e-6)
+        errs = fit.errors()
+        assert done == len(ref["All_Error"]) == len(errs)
+        assert rel_err(errs, ref["All_Error"]) <= RTOL
+        fit.normalise()
+        outs = [fit.get_factors(v) for v in range(2)]
+        for v in range(2):
+            assert rel_err(outs[v][0], ref["output_f"][v]) <= RTOL
+            assert rel_err(outs[v][1], ref["output_s"][v]) <= RTOL
+            assert rel_err(outs[v][2], ref["output_g"][v]) <= RTOL
+        rows_d, cols_d, _ = O.binarise([o[0] for o in outs], [o[2] for o in outs], [o[1] for o in outs])
+        rows_o, cols_o, _ = O.binarise(ref["output_f"], ref["output_g"], ref["output_s"])
+        for v in range(2):
+            assert np.array_equal(rows_d[v], rows_o[v]) and np.array_equal(cols_d[v], cols_o[v])
+            assert sorted(rows_d[v].sum(0)) == [60, 60, 60] and sorted(cols_d[v].sum(0)) == [60, 60, 60]
+        c = fit.counters()
+        assert c["converged"] == 1 and c["kernel_launches"] > 0
+    finally:
+        fit.close()
+
+
+def test_medium_single_view_bitwise_repeatable(ctx):
+    """4000 x 1500, k=8: parity with the oracle and run-to-run bit-reproducibility (fixed-order sums)."""
+    prob = single_view_problem(4000, 1500, 8, seed=77, n_planted=5)
+    compare_trace(prob, ctx, n_iters=3, err_mode=L.ERR_AUTO)
+    outs = []
+    for _ in range(2):
+        fit = prob.device_fit(ctx)
+        fit.run(20)
+        outs.append((fit.get_factors(0), fit.errors()))
+        fit.close()
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_nan_error_is_reported(ctx):
+    """An all-zero G makes the coupled update 0/0: the reference's while(NA) throws; we return E_NAN."""
+    prob = two_view_problem(seed=2, phi=10.0, psi=10.0)
+    prob.init_g = [np.zeros_like(g) for g in prob.init_g]
+    prob.init_f = [np.zeros_like(f) for f in prob.init_f]
+    with pytest.raises(FloatingPointError):
+        prob.oracle(max_iters=5)
+    fit = prob.device_fit(ctx)
+    try:
+        with pytest.raises(L.ResnmtfNaNError):
+            fit.run(None, 1.0e-6, max_iters=5)
+    finally:
+        fit.close()
+
+
+def test_state_errors(ctx):
+    from resnmtf_b200.device import DeviceFit
+
+    fit = DeviceFit(ctx, [10], [5], [2])
+    with pytest.raises(L.ResnmtfError) as e:
+        fit.run(1)
+    assert e.value.code == L.E_STATE
+    fit.close()
+    with pytest.raises(L.ResnmtfError) as e:
+        DeviceFit(ctx, [10], [5], [17])
+    assert e.value.code == L.E_UNSUPPORTED
