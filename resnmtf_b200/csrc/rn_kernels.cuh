@@ -486,26 +486,39 @@ template <int K>
 __global__ void __launch_bounds__(256) rn_gram_f(const RnView vw, const RnFit ft) {
   const int tid = threadIdx.x;
   if (ft.ctrl->done) return;
+  constexpr int NOUT = K * K + K;
+  constexpr int PER = (NOUT + 255) / 256;  // outputs per thread (2 for k = 16)
   __shared__ double rows[256 * K];
   const int64_t ldx = vw.ldx;
-  const int nchunks = (int)(ldx / 256) + ((ldx % 256) ? 1 : 0);
+  const int nchunks = (int)((ldx + 255) / 256);
   const int c0 = (int)((int64_t)nchunks * blockIdx.x / gridDim.x);
   const int c1 = (int)((int64_t)nchunks * (blockIdx.x + 1) / gridDim.x);
-  double acc = 0.0;
-  const int a = (tid < K * K) ? tid % K : 0, b = (tid < K * K) ? tid / K : tid - K * K;
+  double acc[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) acc[q] = 0.0;
   for (int ch = c0; ch < c1; ++ch) {
     const int64_t r = (int64_t)ch * 256 + tid;
 #pragma unroll
     for (int c = 0; c < K; ++c) rows[tid * K + c] = (r < vw.n) ? vw.F[(int64_t)c * ldx + r] : 0.0;
     __syncthreads();
-    if (tid < K * K) {
-      for (int i = 0; i < 256; ++i) acc = fma(rows[i * K + a], rows[i * K + b], acc);
-    } else if (tid < K * K + K) {
-      for (int i = 0; i < 256; ++i) acc += rows[i * K + b];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int o = tid + 256 * q;
+      if (o < K * K) {
+        const int a = o % K, b = o / K;
+        for (int i = 0; i < 256; ++i) acc[q] = fma(rows[i * K + a], rows[i * K + b], acc[q]);
+      } else if (o < NOUT) {
+        const int b = o - K * K;
+        for (int i = 0; i < 256; ++i) acc[q] += rows[i * K + b];
+      }
     }
     __syncthreads();
   }
-  if (tid < K * K + K) vw.FFpart[(int64_t)blockIdx.x * (K * K + K) + tid] = acc;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int o = tid + 256 * q;
+    if (o < NOUT) vw.FFpart[(int64_t)blockIdx.x * NOUT + o] = acc[q];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,16 +542,16 @@ __global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView
   double* const fin = Tsm;  // only used by the last CTA, after every thread is done with Tsm / Gsm
   double* const red = Gsm;
 
-  if (tid < KK) Ssm[tid] = vw.S[tid];
+  for (int o = tid; o < KK; o += NT) Ssm[o] = vw.S[o];
   if (tid < K) muh[tid] = 0.5 * vw.mu[tid];
-  if (tid < KK + K) {  // F'F | colSums(F): fixed-order sum of the partials
+  for (int o = tid; o < KK + K; o += NT) {  // F'F | colSums(F): fixed-order sum of the partials
     double s = 0.0;
-    for (int i = 0; i < vw.nff; ++i) s += vw.FFpart[(int64_t)i * (KK + K) + tid];
-    FtFs[tid] = s;
+    for (int i = 0; i < vw.nff; ++i) s += vw.FFpart[(int64_t)i * (KK + K) + o];
+    FtFs[o] = s;
   }
   __syncthreads();
-  if (tid < KK) {  // V = crossprod(F) %*% S
-    const int a = tid % K, c = tid / K;
+  for (int o = tid; o < KK; o += NT) {  // V = crossprod(F) %*% S
+    const int a = o % K, c = o / K;
     double s = 0.0;
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
     Vs[a + c * K] = s;
@@ -660,25 +673,25 @@ __global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView
     else if (o < 2 * KK) vw.A[o - KK] = s;
     else vw.csG[o - 2 * KK] = s;
   }
-  if (tid < KK) vw.FtF[tid] = FtFs[tid];
+  for (int o = tid; o < KK; o += NT) vw.FtF[o] = FtFs[o];
   if (tid < K) vw.csF[tid] = FtFs[KK + tid];
   __syncthreads();
   const double* GtGn = fin;
   const double* An = fin + KK;
   const double* csGn = fin + 2 * KK;
-  if (tid < KK) {  // U = crossprod(F) %*% S
-    const int a = tid % K, c = tid / K;
+  for (int o = tid; o < KK; o += NT) {  // U = crossprod(F) %*% S
+    const int a = o % K, c = o / K;
     double s = 0.0;
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
     Us[a + c * K] = s;
   }
   __syncthreads();
-  if (tid < KK) {  // update_s
-    const int a = tid % K, b = tid / K;
+  for (int o = tid; o < KK; o += NT) {  // update_s
+    const int a = o % K, b = o / K;
     double D = 0.0;
     for (int c = 0; c < K; ++c) D = fma(Us[a + c * K], GtGn[c + b * K], D);
-    const double N = An[tid];
-    const double sv = Ssm[tid];
+    const double N = An[o];
+    const double sv = Ssm[o];
     double out;
     if (ft.xi_total == 0.0) {
       double ratio = N / D;
@@ -689,31 +702,31 @@ __global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView
       for (int w = 0; w < V; ++w) xisum += ft.xi[w + v * V];
       for (int w = 0; w < V; ++w) {
         const double x = ft.xi[w + v * V];
-        if (x != 0.0) xs += x * ft.views[w].S[tid];
+        if (x != 0.0) xs += x * ft.views[w].S[o];
       }
       out = fabs(sv * ((N + xs) / (D + xisum * sv)));
     }
-    Sn[tid] = out;
+    Sn[o] = out;
   }
   __syncthreads();
-  if (tid < KK) vw.S[tid] = Sn[tid];
+  for (int o = tid; o < KK; o += NT) vw.S[o] = Sn[o];
   if (tid < K) {  // update_lm
     vw.lam[tid] = FtFs[KK + tid] * vw.lam[tid];
     vw.mu[tid] = csGn[tid] * vw.mu[tid];
   }
   // algebraic error: (||X||^2 - 2 <A,S'> + <(F'F S') G'G, S'>) / ||X||^2
-  if (tid < KK) {
-    const int a = tid % K, c = tid / K;
+  for (int o = tid; o < KK; o += NT) {
+    const int a = o % K, c = o / K;
     double s = 0.0;
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Sn[b + c * K], s);
     Us[a + c * K] = s;
   }
   __syncthreads();
-  if (tid < KK) {
-    const int a = tid % K, b = tid / K;
+  for (int o = tid; o < KK; o += NT) {
+    const int a = o % K, b = o / K;
     double q = 0.0;
     for (int c = 0; c < K; ++c) q = fma(Us[a + c * K], GtGn[c + b * K], q);
-    red[tid] = (q - 2.0 * An[tid]) * Sn[tid];
+    red[o] = (q - 2.0 * An[o]) * Sn[o];
   }
   __syncthreads();
   if (tid == 0) {
