@@ -86,6 +86,7 @@ struct resnmtf_fit {
   int impl = RESNMTF_IMPL_DMMA;
   bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
   bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
+  bool auto_direct = false; // AUTO error mode has handed over to the direct residual pass
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int64_t launches_per_iter = 0;
@@ -120,71 +121,85 @@ static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m
 #define RN_K_CASES_LE8(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #define RN_K_CASES_GT8(X) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
-static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, cudaStream_t st) {
-  dim3 grid(vh.d.row_tiles, vh.d.cs);
-  const int K = vh.d.k;
-  if (impl == RESNMTF_IMPL_DMMA && K <= 8) {
-    switch (K) {
-#define X(KC) case KC: rn_f_step<KC, 8, true><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
-      RN_K_CASES_LE8(X)
-#undef X
-    }
-  } else {
-    switch (K) {
-#define X(KC) case KC: rn_f_step<KC, 8, false><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
-      RN_K_CASES_LE8(X)
-#undef X
-#define X(KC) case KC: rn_f_step<KC, 16, false><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
-      RN_K_CASES_GT8(X)
-#undef X
-    }
-  }
-}
+typedef void (*FStepSkFn)(const RnView, const RnFit, const int);
+typedef void (*GStepSkFn)(const RnView, const RnFit, const int, const int);
 
-static int launch_g_stream(const ViewHost& vh, const RnFit& ft, int impl, cudaStream_t st) {
-  dim3 grid(vh.d.col_groups, vh.d.rs);
-  const int K = vh.d.k;
-  int n = 1;
-  if (impl == RESNMTF_IMPL_DMMA && K <= 8) {
-    switch (K) {
-#define X(KC) case KC: rn_g_stream_mma<KC><<<grid, 128, 0, st>>>(vh.d, ft); break;
-      RN_K_CASES_LE8(X)
-#undef X
-    }
-  } else {
-    switch (K) {
-#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft); break;
-      RN_K_CASES_LE8(X)
-#undef X
-#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft); break;
-      RN_K_CASES_GT8(X)
-#undef X
-    }
-    n = 2;
-  }
-  return n;
-}
-
-static void launch_g_epilogue(const ViewHost& vh, const RnFit& ft, int v, cudaStream_t st) {
-  const int K = vh.d.k;
+static FStepSkFn f_step_sk_fn(int K) {
   switch (K) {
-#define X(KC) case KC: rn_g_epilogue<KC, 8><<<vh.d.gepi_ctas, RN_GEPI_THREADS(KC), 0, st>>>(vh.d, ft, v); break;
+#define X(KC) case KC: return rn_f_step_sk<KC>;
     RN_K_CASES_LE8(X)
 #undef X
-#define X(KC) case KC: rn_g_epilogue<KC, 16><<<vh.d.gepi_ctas, RN_GEPI_THREADS(KC), 0, st>>>(vh.d, ft, v); break;
+  }
+  return nullptr;
+}
+static GStepSkFn g_step_sk_fn(int K) {
+  switch (K) {
+#define X(KC) case KC: return rn_g_step_sk<KC>;
+    RN_K_CASES_LE8(X)
+#undef X
+  }
+  return nullptr;
+}
+
+static inline bool use_mma(const ViewHost& vh, int impl) { return impl == RESNMTF_IMPL_DMMA && vh.d.k <= 8; }
+
+static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, cudaStream_t st) {
+  const int K = vh.d.k;
+  if (use_mma(vh, impl)) {
+    f_step_sk_fn(K)<<<vh.d.f_ctas, 256, 0, st>>>(vh.d, ft, v);
+    return;
+  }
+  dim3 grid(vh.d.row_tiles, vh.d.cs);
+  switch (K) {
+#define X(KC) case KC: rn_f_step_dfma<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
+    RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_f_step_dfma<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft, v); break;
     RN_K_CASES_GT8(X)
 #undef X
   }
 }
 
-static void launch_residual(const ViewHost& vh, const RnFit& ft, cudaStream_t st) {
+static void launch_g_epilogue(const ViewHost& vh, const RnFit& ft, int v, int fuse, cudaStream_t st) {
+  const int K = vh.d.k;
+  switch (K) {
+#define X(KC) case KC: rn_g_epilogue<KC, 8><<<vh.d.gepi_ctas, RN_GEPI_THREADS(KC), 0, st>>>(vh.d, ft, v, fuse); break;
+    RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_g_epilogue<KC, 16><<<vh.d.gepi_ctas, RN_GEPI_THREADS(KC), 0, st>>>(vh.d, ft, v, fuse); break;
+    RN_K_CASES_GT8(X)
+#undef X
+  }
+}
+
+// G step of one view: returns the number of kernels launched.
+static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, int fuse, cudaStream_t st) {
+  const int K = vh.d.k;
+  if (use_mma(vh, impl)) {
+    g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, fuse);
+    return 1;
+  }
+  dim3 grid(vh.d.col_groups, vh.d.rs);
+  switch (K) {
+#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft); break;
+    RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft); break;
+    RN_K_CASES_GT8(X)
+#undef X
+  }
+  launch_g_epilogue(vh, ft, v, fuse, st);
+  return 3;
+}
+
+static void launch_residual(const ViewHost& vh, const RnFit& ft, int force, cudaStream_t st) {
   dim3 grid(vh.d.row_tiles, vh.d.resid_cs);
   const int K = vh.d.k;
   switch (K) {
-#define X(KC) case KC: rn_residual<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft); break;
+#define X(KC) case KC: rn_residual<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft, force); break;
     RN_K_CASES_LE8(X)
 #undef X
-#define X(KC) case KC: rn_residual<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft); break;
+#define X(KC) case KC: rn_residual<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft, force); break;
     RN_K_CASES_GT8(X)
 #undef X
   }
@@ -285,8 +300,10 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
     vh.d.p = p[v];
     vh.d.k = k[v];
     vh.d.kp = k[v] <= 8 ? 8 : 16;
+    vh.d.n_glob = n[v];
     vh.d.ldx = rn_round_up(n[v], RN_ROW_TILE);
-    vh.d.pp = rn_round_up(p[v], 8);
+    vh.d.pp = rn_round_up(p[v], 32);
+    vh.d.row_tiles = (int)(vh.d.ldx / RN_ROW_TILE);
     vh.d.sharded = ctx->n_ranks > 1 ? 1 : 0;
     vh.rowmaps.assign(V, nullptr);
     vh.colmaps.assign(V, nullptr);
@@ -346,7 +363,7 @@ extern "C" int resnmtf_fit_destroy(resnmtf_fit* fit) {
   return RESNMTF_OK;
 }
 
-static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld, cudaMemcpyKind kind,
+static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld, bool on_device,
                            const char* who) {
   RN_CHECK(fit && x, RESNMTF_E_INVALID, std::string(who) + ": NULL argument");
   RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, std::string(who) + ": view index out of range");
@@ -354,22 +371,49 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
   RN_CHECK(ld >= vh.d.n, RESNMTF_E_INVALID, std::string(who) + ": ld < n");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
   cudaStream_t st = fit->ctx->stream;
-  // padding rows/columns were zeroed at allocation and are never written
-  RN_CUDA(cudaMemcpy2DAsync(vh.d.X, (size_t)vh.d.ldx * sizeof(double), x, (size_t)ld * sizeof(double),
-                            (size_t)vh.d.n * sizeof(double), (size_t)vh.d.p, kind, st));
-  const int nblk = 1024;
-  rn_xnorm2<<<nblk, 256, 0, st>>>(vh.d, vh.xpart, vh.xticket);
+  const int64_t n = vh.d.n, p = vh.d.p;
+  // padding columns / rows were zeroed at allocation; rn_to_panels rewrites the padding rows as zero
+  if (on_device) {
+    const int blocks = (int)std::min<int64_t>(((int64_t)vh.d.row_tiles * p * 32 + 255) / 256, 1 << 20);
+    rn_to_panels<<<blocks, 256, 0, st>>>(vh.d, x, ld, 0, p);
+    RN_CUDA(cudaGetLastError());
+  } else {
+    // stage column chunks (<= 256 MB) in device memory, re-tile each into the panel layout
+    const int64_t max_cols = std::max<int64_t>(1, ((int64_t)256 << 20) / (n * (int64_t)sizeof(double)));
+    const int64_t chunk = std::min<int64_t>(p, max_cols);
+    double* stage = nullptr;
+    RN_CUDA(cudaMalloc(&stage, (size_t)chunk * n * sizeof(double)));
+    for (int64_t c0 = 0; c0 < p; c0 += chunk) {
+      const int64_t nc = std::min(chunk, p - c0);
+      cudaError_t e = cudaMemcpy2DAsync(stage, (size_t)n * sizeof(double), x + c0 * ld, (size_t)ld * sizeof(double),
+                                        (size_t)n * sizeof(double), (size_t)nc, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        const int blocks = (int)std::min<int64_t>(((int64_t)vh.d.row_tiles * nc * 32 + 255) / 256, 1 << 20);
+        rn_to_panels<<<blocks, 256, 0, st>>>(vh.d, stage, n, c0, nc);
+        e = cudaGetLastError();
+      }
+      if (e != cudaSuccess) {
+        cudaStreamSynchronize(st);
+        cudaFree(stage);
+        return rn_fail(RESNMTF_E_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(stage);
+    if (e != cudaSuccess) return rn_fail(RESNMTF_E_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  }
+  rn_xnorm2<<<1024, 256, 0, st>>>(vh.d, vh.xpart, vh.xticket);
   RN_CUDA(cudaGetLastError());
-  RN_CUDA(cudaStreamSynchronize(st));  // the host buffer is only borrowed for the call
+  RN_CUDA(cudaStreamSynchronize(st));  // the caller's buffer is only borrowed for the call
   vh.has_data = true;
   return RESNMTF_OK;
 }
 
 extern "C" int resnmtf_fit_set_data(resnmtf_fit* fit, int v, const double* x, int64_t ld) {
-  return set_data_common(fit, v, x, ld, cudaMemcpyHostToDevice, "resnmtf_fit_set_data");
+  return set_data_common(fit, v, x, ld, false, "resnmtf_fit_set_data");
 }
 extern "C" int resnmtf_fit_set_data_device(resnmtf_fit* fit, int v, const double* x, int64_t ld) {
-  return set_data_common(fit, v, x, ld, cudaMemcpyDeviceToDevice, "resnmtf_fit_set_data_device");
+  return set_data_common(fit, v, x, ld, true, "resnmtf_fit_set_data_device");
 }
 
 extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f, const double* s,
@@ -400,6 +444,10 @@ extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f,
   fit->errors.clear();
   std::memset(&fit->h_ctrl, 0, sizeof(RnCtrl));
   fit->counters.iterations = 0;
+  if (fit->auto_direct) {
+    fit->auto_direct = false;
+    fit->meta_dirty = true;
+  }
   return RESNMTF_OK;
 }
 
@@ -476,7 +524,10 @@ extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl)
   RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_options: fit is NULL");
   RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 2, RESNMTF_E_INVALID,
            "resnmtf_fit_set_options: unknown option value");
-  if (fit->err_mode != err_mode) fit->meta_dirty = true;
+  if (fit->err_mode != err_mode) {
+    fit->meta_dirty = true;
+    fit->auto_direct = false;
+  }
   if (fit->impl_req != impl) fit->plan_dirty = true;
   fit->err_mode = err_mode;
   fit->impl_req = impl;
@@ -497,36 +548,59 @@ static int build_plan(resnmtf_fit* fit) {
   if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_DMMA);
   if (impl != RESNMTF_IMPL_DFMA && impl != RESNMTF_IMPL_DMMA) impl = RESNMTF_IMPL_DMMA;
   fit->impl = impl;
-  const int f_target = sms * rn_env_int("RESNMTF_F_CTAS_PER_SM", 3);
-  const int g_target_mma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM", 4);
+  const int f_target = sms * rn_env_int("RESNMTF_F_CTAS_PER_SM", 2);
   const int g_target_dfma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM_DFMA", 3);
   int rc;
   for (int v = 0; v < fit->V; ++v) {
     ViewHost& vh = fit->views[v];
     RnView& d = vh.d;
-    const bool mma = impl == RESNMTF_IMPL_DMMA && d.k <= 8;
+    const bool mma = use_mma(vh, impl);
     const int K = d.k, KP = d.kp;
-    // F step: one CTA per 64-row tile; split the columns only when there are too few tiles to fill
-    // the machine (each split keeps >= 64 data columns)
-    d.row_tiles = (int)(d.ldx / RN_ROW_TILE);
-    int cs = 1;
-    if (d.row_tiles < f_target) cs = (f_target + d.row_tiles - 1) / d.row_tiles;
-    cs = std::max(1, std::min<int>(cs, (int)std::max<int64_t>(1, d.pp / 64)));
-    cs = rn_env_int("RESNMTF_F_CS", cs);
-    d.cs = cs;
-    // G stream: one CTA per column group; split the row steps to fill the machine
-    const int grp_cols = mma ? RN_COL_GROUP : RN_COL_GROUP_DFMA;
-    d.col_groups = (int)((d.pp + grp_cols - 1) / grp_cols);
-    const int target = mma ? g_target_mma : g_target_dfma;
-    int rs = std::max(1, (target + d.col_groups / 2) / d.col_groups);
-    const int min_steps = mma ? 4 : 1;
-    rs = std::max(1, std::min<int>(rs, std::max(1, d.row_tiles / min_steps)));
-    rs = rn_env_int("RESNMTF_G_RS", rs);
-    rs = std::max(1, std::min(rs, d.row_tiles));
-    d.rs = rs;
-    d.nff = mma ? rs : std::max(1, std::min(sms, (int)((d.ldx + 255) / 256)));
-    d.gepi_ctas = (int)((d.p + RN_GEPI_THREADS(K) - 1) / RN_GEPI_THREADS(K));
-    d.resid_cs = cs;
+    size_t n_ppart, n_tpart, n_ffpart, n_ggpart;
+    if (mma) {
+      // persistent stream-K grids: exactly the CTAs that are resident at once (never more than units)
+      int occ_f = 1, occ_g = 1;
+      RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, f_step_sk_fn(K), 256, 0));
+      RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, g_step_sk_fn(K), 128, 0));
+      occ_f = std::max(1, rn_env_int("RESNMTF_F_OCC", occ_f));
+      occ_g = std::max(1, rn_env_int("RESNMTF_G_OCC", occ_g));
+      d.col_groups = (int)((d.pp + RN_COL_GROUP - 1) / RN_COL_GROUP);
+      const int64_t f_units = (int64_t)d.row_tiles * (d.pp / 32);
+      const int64_t g_units = (int64_t)d.row_tiles * d.col_groups;
+      d.f_ctas = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * occ_f, f_units));
+      d.g_ctas = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * occ_g, g_units));
+      d.f_ctas = std::max(1, std::min<int>(rn_env_int("RESNMTF_F_CTAS", d.f_ctas), (int)f_units));
+      d.g_ctas = std::max(1, std::min<int>(rn_env_int("RESNMTF_G_CTAS", d.g_ctas), (int)g_units));
+      d.cs = d.rs = 1;
+      d.nff = 0;
+      d.gepi_ctas = 0;
+      n_ppart = (size_t)d.f_ctas * 2 * RN_ROW_TILE * KP;
+      n_tpart = (size_t)d.g_ctas * 2 * RN_COL_GROUP * KP;
+      n_ffpart = (size_t)d.g_ctas * (K * K + K);
+      n_ggpart = (size_t)d.col_groups * (2 * K * K + K);
+    } else {
+      // F step: one CTA per 64-row tile; split the columns only when there are too few tiles to fill
+      // the machine (each split keeps >= 64 data columns)
+      int cs = 1;
+      if (d.row_tiles < f_target) cs = (f_target + d.row_tiles - 1) / d.row_tiles;
+      cs = std::max(1, std::min<int>(cs, (int)std::max<int64_t>(1, d.pp / 64)));
+      cs = rn_env_int("RESNMTF_F_CS", cs);
+      d.cs = std::max(1, std::min<int>(cs, (int)(d.pp / 8)));
+      // G stream: one CTA per 32-column group; split the row steps to fill the machine
+      d.col_groups = (int)((d.pp + RN_COL_GROUP_DFMA - 1) / RN_COL_GROUP_DFMA);
+      int rs = std::max(1, (g_target_dfma + d.col_groups / 2) / d.col_groups);
+      rs = rn_env_int("RESNMTF_G_RS", rs);
+      d.rs = std::max(1, std::min(rs, d.row_tiles));
+      d.nff = std::max(1, std::min(sms, (int)((d.ldx + 255) / 256)));
+      d.gepi_ctas = (int)((d.p + RN_GEPI_THREADS(K) - 1) / RN_GEPI_THREADS(K));
+      d.f_ctas = d.g_ctas = 0;
+      n_ppart = d.cs > 1 ? (size_t)d.cs * d.row_tiles * RN_ROW_TILE * KP : 0;
+      n_tpart = d.rs > 1 ? (size_t)d.rs * d.pp * KP : 0;
+      n_ffpart = (size_t)d.nff * (K * K + K);
+      n_ggpart = (size_t)d.gepi_ctas * (2 * K * K + K);
+    }
+    d.resid_cs = std::max(1, std::min<int>((2 * sms + d.row_tiles - 1) / d.row_tiles, (int)(d.pp / 64)));
+    d.resid_cs = std::max(1, d.resid_cs);
     // workspaces (old ones are released first when the plan is rebuilt)
     if ((rc = rn_free(fit, d.Ppart))) return rc;
     if ((rc = rn_free(fit, d.Tpart))) return rc;
@@ -537,13 +611,14 @@ static int build_plan(resnmtf_fit* fit) {
     if ((rc = rn_free(fit, d.group_ticket))) return rc;
     d.Ppart = d.Tpart = d.FFpart = d.GGpart = d.Rpart = nullptr;
     d.tile_ticket = d.group_ticket = nullptr;
-    if (d.cs > 1 && (rc = rn_alloc(fit, &d.Ppart, (size_t)d.cs * d.ldx * KP))) return rc;
-    if (d.rs > 1 && (rc = rn_alloc(fit, &d.Tpart, (size_t)d.rs * d.pp * KP))) return rc;
-    if ((rc = rn_alloc(fit, &d.FFpart, (size_t)d.nff * (K * K + K)))) return rc;
-    if ((rc = rn_alloc(fit, &d.GGpart, (size_t)d.gepi_ctas * (2 * K * K + K)))) return rc;
+    if (n_ppart && (rc = rn_alloc(fit, &d.Ppart, n_ppart))) return rc;
+    if (n_tpart && (rc = rn_alloc(fit, &d.Tpart, n_tpart))) return rc;
+    if ((rc = rn_alloc(fit, &d.FFpart, n_ffpart))) return rc;
+    if ((rc = rn_alloc(fit, &d.GGpart, n_ggpart))) return rc;
     if ((rc = rn_alloc(fit, &d.Rpart, (size_t)d.row_tiles * d.resid_cs))) return rc;
     if ((rc = rn_alloc(fit, &d.tile_ticket, (size_t)d.row_tiles))) return rc;
     if ((rc = rn_alloc(fit, &d.group_ticket, (size_t)d.col_groups))) return rc;
+    RN_CUDA(cudaMemsetAsync(d.misc_ticket, 0, 4 * sizeof(int32_t), fit->ctx->stream));
   }
   fit->plan_dirty = false;
   fit->meta_dirty = true;
@@ -575,7 +650,7 @@ static int sync_meta(resnmtf_fit* fit) {
   RN_CUDA(cudaStreamSynchronize(st));
   RnFit& d = fit->d;
   d.n_views = V;
-  d.err_mode = fit->err_mode;
+  d.err_mode = (fit->err_mode == RESNMTF_ERR_AUTO && fit->auto_direct) ? RESNMTF_ERR_DIRECT : fit->err_mode;
   d.views = fit->d_views;
   d.ctrl = fit->d_ctrl;
   d.phi = fit->d_phi;
@@ -607,8 +682,10 @@ static int sync_meta(resnmtf_fit* fit) {
   return RESNMTF_OK;
 }
 
-// Enqueues one update-iteration (all views, Gauss-Seidel order) on `st`.  When ev is non-null it holds
-// 2 events per launch for the profiling entry point.
+// Enqueues one update-iteration (all views, Gauss-Seidel order) on `st`.  When ev is non-null an event
+// is recorded before every kernel class for the profiling entry point.
+// Error mode ALGEBRAIC / AUTO: the last view's G step also does the iteration bookkeeping (fused finish).
+// Error mode DIRECT: every view is followed by the residual pass, then rn_finish.
 static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<cudaEvent_t>* ev,
                                  std::vector<int>* ev_class) {
   int64_t launches = 0;
@@ -620,25 +697,26 @@ static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<
     ev->push_back(e);
     ev_class->push_back(cls);
   };
+  const bool direct = fit->d.err_mode == RESNMTF_ERR_DIRECT;
   for (int v = 0; v < fit->V; ++v) {
     const ViewHost& vh = fit->views[v];
     mark(0);
     launch_f_step(vh, fit->d, v, fit->impl, st);
     launches += 1;
     mark(1);
-    launches += launch_g_stream(vh, fit->d, fit->impl, st);
-    mark(2);
-    launch_g_epilogue(vh, fit->d, v, st);
-    launches += 1;
-    if (fit->err_mode != RESNMTF_ERR_ALGEBRAIC) {
+    const int fuse = (!direct && v == fit->V - 1) ? 1 : 0;
+    launches += launch_g_step(vh, fit->d, v, fit->impl, fuse, st);
+    if (direct) {
       mark(3);
-      launch_residual(vh, fit->d, st);
+      launch_residual(vh, fit->d, 0, st);
       launches += 1;
     }
   }
-  mark(4);
-  rn_finish<<<1, 1, 0, st>>>(fit->d);
-  launches += 1;
+  if (direct) {
+    mark(4);
+    rn_finish<<<1, 1, 0, st>>>(fit->d, 0);
+    launches += 1;
+  }
   mark(-1);
   return launches;
 }
@@ -648,6 +726,17 @@ static int prepare(resnmtf_fit* fit) {
     RN_CHECK(fit->views[v].has_data, RESNMTF_E_STATE, "resnmtf: set_data was not called for every view");
     RN_CHECK(fit->views[v].has_factors, RESNMTF_E_STATE, "resnmtf: set_factors was not called for every view");
   }
+  // phi / psi overwrite rows of one view's factor with another's (R/utils.r:72): the coupled views
+  // must have the same k unless the pair shares nothing (NA pairs are skipped)
+  for (int v = 0; v < fit->V; ++v)
+    for (int w = 0; w < fit->V; ++w) {
+      if (w == v || fit->views[v].d.k == fit->views[w].d.k) continue;
+      const size_t slot = (size_t)w + (size_t)v * fit->V;
+      RN_CHECK(!(fit->h_phi[slot] != 0.0 && fit->h_rowmode[slot] != RN_MODE_NA), RESNMTF_E_INVALID,
+               "phi couples views with different k (non-conformable in the reference)");
+      RN_CHECK(!(fit->h_psi[slot] != 0.0 && fit->h_colmode[slot] != RN_MODE_NA), RESNMTF_E_INVALID,
+               "psi couples views with different k (non-conformable in the reference)");
+    }
   RN_CUDA(cudaSetDevice(fit->ctx->device));
   int rc;
   if (fit->plan_dirty && (rc = build_plan(fit))) return rc;
@@ -719,6 +808,25 @@ static double alg_bytes_per_iter(const resnmtf_fit* fit) {
   return b;
 }
 
+// AUTO error mode hand-over: the device paused (done == 3) at the end of a sweep whose algebraic error
+// fell below 1e-3.  Re-evaluate that sweep's error with the direct residual pass, do its bookkeeping,
+// and continue in DIRECT mode for the rest of the fit.
+static int handle_pause(resnmtf_fit* fit) {
+  cudaStream_t st = fit->ctx->stream;
+  fit->h_ctrl.done = 0;
+  fit->h_ctrl.want_direct = 0;
+  int rc;
+  if ((rc = push_ctrl(fit))) return rc;
+  for (int v = 0; v < fit->V; ++v) launch_residual(fit->views[v], fit->d, 1, st);
+  rn_finish<<<1, 1, 0, st>>>(fit->d, 0);
+  RN_CUDA(cudaGetLastError());
+  fit->counters.kernel_launches += fit->V + 1;
+  fit->auto_direct = true;
+  fit->meta_dirty = true;
+  if ((rc = pull_ctrl(fit))) return rc;
+  return prepare(fit);
+}
+
 extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, int64_t max_iters,
                                int64_t* iters_done) {
   RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_run: fit is NULL");
@@ -731,29 +839,29 @@ extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, in
   fit->h_ctrl.tol = tol;
   fit->h_ctrl.hist_count = 0;
   fit->h_ctrl.direct_passes = 0;
+  fit->h_ctrl.want_direct = 0;
   if ((rc = push_ctrl(fit))) return rc;
   fit->counters.kernel_launches = 0;
   const int64_t it0 = fit->h_ctrl.iters;
   RN_CUDA(cudaEventRecord(fit->ctx->ev0, st));
-  if (!conv) {
-    int64_t left = n_iters;
-    while (left > 0) {
-      const int64_t b = std::min<int64_t>(left, fit->hist_cap);
-      if ((rc = run_batch(fit, b))) return rc;
-      left -= b;
-      if (left > 0 && (rc = pull_ctrl(fit))) return rc;
-    }
-  } else {
-    const int64_t batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 8));
-    for (;;) {
-      int64_t b = batch;
-      const int64_t donei = fit->h_ctrl.iters - it0;
+  const int64_t conv_batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 8));
+  for (;;) {
+    const int64_t donei = fit->h_ctrl.iters - it0;
+    int64_t b;
+    if (!conv) {
+      b = std::min<int64_t>(n_iters - donei, fit->hist_cap);
+    } else {
+      b = conv_batch;
       if (max_iters > 0) b = std::min(b, max_iters - donei);
-      if (b <= 0) break;
-      if ((rc = run_batch(fit, b))) return rc;
-      if ((rc = pull_ctrl(fit))) return rc;
-      if (fit->h_ctrl.done) break;
     }
+    if (b <= 0) break;
+    if ((rc = run_batch(fit, b))) return rc;
+    // fixed mode without AUTO hand-over pending needs no read-back until the end
+    if ((rc = pull_ctrl(fit))) return rc;
+    if (fit->h_ctrl.done == 3) {
+      if ((rc = handle_pause(fit))) return rc;
+    }
+    if (fit->h_ctrl.done == 1 || fit->h_ctrl.done == 2) break;
   }
   RN_CUDA(cudaEventRecord(fit->ctx->ev1, st));
   if ((rc = pull_ctrl(fit))) return rc;
@@ -801,7 +909,8 @@ extern "C" int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[
       }
     }
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
-    if (((it + 1) % fit->hist_cap) == 0 && (rc = pull_ctrl(fit))) return rc;
+    if ((rc = pull_ctrl(fit))) return rc;
+    if (fit->h_ctrl.done == 3 && (rc = handle_pause(fit))) return rc;
   }
   if ((rc = pull_ctrl(fit))) return rc;
   fit->counters.iterations = fit->h_ctrl.iters;

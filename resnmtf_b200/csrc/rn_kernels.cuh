@@ -1,16 +1,21 @@
 // Hand-written sm_100a kernels of the ResNMTF update sweep (FP64 throughout).
 //
-// One update-iteration of view v (reference: update_matrices, R/update_steps.r:272-319) is
-//   rn_f_step      P = X.G streamed over X once, fused with the F update (update_f, :141-165) incl. the
-//                  phi coupling gather (star_prod_relevant, R/utils.r:63-78)
-//   rn_g_stream_*  T = X'.F streamed over X once (+ F'F and colSums(F) on the tensor-core path)
-//   rn_g_epilogue  G update (update_g, :180-207) incl. psi coupling, G'G, A = T'G, then in the last CTA
+// One update-iteration of view v (reference: update_matrices, R/update_steps.r:272-319) is, on the
+// tensor-core path (k <= 8):
+//   rn_f_step_sk   P = X.G streamed over X once (FP64 mma.sync), fused with the F update (update_f,
+//                  :141-165) incl. the phi coupling gather (star_prod_relevant, R/utils.r:63-78)
+//   rn_g_step_sk   T = X'.F streamed over X once, F'F and colSums(F) from the same fragments, fused with
+//                  the G update (update_g, :180-207) incl. psi coupling, G'G, A = T'G, and in the last CTA
 //                  the S update (update_s, :220-240; its numerator crossprod(F,X) G equals A, so X is not
-//                  read a third time), lambda/mu (update_lm, :249-251) and the algebraic error
-//   rn_residual    optional direct error pass (calculate_error, R/utils.r:157-166)
-//   rn_finish      mean error, history, stop rule (R/main.r:74-80)
-// All cross-CTA reductions are two-stage with a fixed summation order (no floating-point atomics), so
-// results are bit-reproducible run to run.
+//                  read a third time), lambda/mu (update_lm, :249-251), the algebraic error and the
+//                  iteration bookkeeping (R/main.r:74-80)
+// Both are persistent "stream-K" kernels: the grid is the number of resident CTAs, every CTA streams an
+// equal, contiguous share of the 64x32 (F) / 64x64 (G) element units of X, and tiles that straddle two
+// CTAs are combined by the last CTA to arrive, in CTA order.
+// CUDA-core fallbacks (k 9..16, or RESNMTF_IMPL_DFMA): rn_f_step_dfma, rn_gram_f, rn_g_stream_dfma,
+// rn_g_epilogue.  Optional direct error pass: rn_residual (calculate_error, R/utils.r:157-166).
+// All cross-CTA reductions have a fixed summation order (no floating-point atomics), so results are
+// bit-reproducible run to run.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -44,641 +49,213 @@ __device__ __forceinline__ double rn_warp_sum(double v) {
   return v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// F step:  P = X.G  (streaming)  +  update_f epilogue
-//   grid (row_tiles, cs), 256 threads.  A CTA owns 64 rows and the data columns of split `cs`; its 8
-//   warps interleave over the columns.  With cs > 1 the last CTA to arrive for a row tile sums the
-//   partials in split order and runs the epilogue.
-// ------------------------------------------------------------------------------------------------
-template <int K, int KP, bool MMA>
-__global__ void __launch_bounds__(256) rn_f_step(const RnView vw, const RnFit ft, const int v) {
-  static_assert(!MMA || KP == 8, "tensor-core path holds k in one 8-wide fragment");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, cs = blockIdx.y, ncs = gridDim.y;
-  if (ft.ctrl->done) return;  // state is frozen once the stop rule fired (uniform over the grid)
+__device__ __forceinline__ int rn_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
-  __shared__ double Ps[RN_ROW_TILE * KP];
-  __shared__ double Ssm[K * K], Wsm[K * K], lamh[K];
-  __shared__ int s_last;
+// stream-K partition of U units over C CTAs: CTA c owns [begin(c), begin(c+1)); the first U % C CTAs
+// get one unit more.
+struct RnSplit {
+  int64_t q, rem;
+  __device__ __forceinline__ RnSplit(int64_t U, int64_t C) : q(U / C), rem(U % C) {}
+  __device__ __forceinline__ int64_t begin(int64_t c) const { return c * q + (c < rem ? c : rem); }
+  __device__ __forceinline__ int64_t owner(int64_t u) const {
+    const int64_t cut = rem * (q + 1);
+    return u < cut ? u / (q + 1) : rem + (u - cut) / q;
+  }
+};
 
+// ------------------------------------------------------------------------------------------------
+// shared per-row math of the two multiplicative updates
+// ------------------------------------------------------------------------------------------------
+
+// update_f for one row r (R/update_steps.r:141-165).  P = (X G)[r,], Ssm = S, Wsm = crossprod(G) t(S),
+// lamh = lambda/2.  Writes |F_new| in place.
+template <int K>
+__device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& ft, const int v, const int64_t r,
+                                                const double* P, const double* Ssm, const double* Wsm,
+                                                const double* lamh) {
   const int64_t ldx = vw.ldx;
-  const int64_t r0 = (int64_t)tile * RN_ROW_TILE;
-  const int nb = (int)(vw.pp >> 3);
-  const int64_t jbeg = 8 * ((int64_t)nb * cs / ncs);
-  const int64_t jend = 8 * ((int64_t)nb * (cs + 1) / ncs);
-  const double* __restrict__ X = vw.X;
-  const double* __restrict__ G = vw.G;
-
-  for (int i = tid; i < RN_ROW_TILE * KP; i += 256) Ps[i] = 0.0;
-
-  if constexpr (MMA) {
-    // lane (g,t): rows r0 + 16m + 2g + {0,1} (m = 0..3), data column 4q + t.
-    const int g = lane >> 2, t = lane & 3;
-    double acc[4][2][2];
+  const int V = ft.n_views;
+  double f[K], N[K], FS[K], D[K];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+  for (int c = 0; c < K; ++c) f[c] = vw.F[(int64_t)c * ldx + r];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) acc[m][h][0] = acc[m][h][1] = 0.0;
-    const double* xb = X + r0 + 2 * g;
-    int64_t q = (jbeg >> 2) + warp;
-    const int64_t qend = jend >> 2;
-    for (; q + 8 < qend; q += 16) {
-      const int64_t ja = q * 4 + t, jb = ja + 32;
-      const double* pa = xb + ja * ldx;
-      const double* pb = xb + jb * ldx;
-      double2 xa[4], xbv[4];
+  for (int c = 0; c < K; ++c) {  // (X G) t(S)
+    double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) xa[m] = rn_ld_stream2(pa + 16 * m);
+    for (int a = 0; a < K; ++a) s = fma(P[a], Ssm[c + a * K], s);
+    N[c] = s;
+  }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) xbv[m] = rn_ld_stream2(pb + 16 * m);
-      const double ba = G[ja * KP + g], bb = G[jb * KP + g];
+  for (int a = 0; a < K; ++a) {  // F S
+    double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        rn_dmma(acc[m][0][0], acc[m][0][1], xa[m].x, ba);
-        rn_dmma(acc[m][1][0], acc[m][1][1], xa[m].y, ba);
-      }
+    for (int b = 0; b < K; ++b) s = fma(f[b], Ssm[b + a * K], s);
+    FS[a] = s;
+  }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        rn_dmma(acc[m][0][0], acc[m][0][1], xbv[m].x, bb);
-        rn_dmma(acc[m][1][0], acc[m][1][1], xbv[m].y, bb);
-      }
-    }
-    for (; q < qend; q += 8) {
-      const int64_t ja = q * 4 + t;
-      const double* pa = xb + ja * ldx;
-      double2 xa[4];
+  for (int c = 0; c < K; ++c) {  // (F S) W
+    double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) xa[m] = rn_ld_stream2(pa + 16 * m);
-      const double ba = G[ja * KP + g];
+    for (int a = 0; a < K; ++a) s = fma(FS[a], Wsm[a + c * K], s);
+    D[c] = s;
+  }
+  double phisum = 0.0;
+  for (int w = 0; w < V; ++w) phisum += ft.phi[w + v * V];
+  if (phisum == 0.0) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        rn_dmma(acc[m][0][0], acc[m][0][1], xa[m].x, ba);
-        rn_dmma(acc[m][1][0], acc[m][1][1], xa[m].y, ba);
-      }
-    }
-    __syncthreads();
-    for (int w = 0; w < 8; ++w) {
-      if (warp == w) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int row = 16 * m + 2 * g + h;
-            Ps[row * KP + 2 * t] += acc[m][h][0];
-            Ps[row * KP + 2 * t + 1] += acc[m][h][1];
-          }
-      }
-      __syncthreads();
+    for (int c = 0; c < K; ++c) {
+      double ratio = N[c] / (D[c] + lamh[c]);
+      if (isnan(ratio)) ratio = 1.0;
+      vw.F[(int64_t)c * ldx + r] = fabs(f[c] * ratio);
     }
   } else {
-    // lane: rows r0 + 2*lane + {0,1}; warp w takes data columns jbeg + w, + 8, ...
-    double a0[K], a1[K];
+    double pc[K];
 #pragma unroll
-    for (int c = 0; c < K; ++c) a0[c] = a1[c] = 0.0;
-    const double* xr = X + r0 + 2 * lane;
-    constexpr int U = 4;
-    int64_t j = jbeg + warp;
-    for (; j + 8 * (U - 1) < jend; j += 8 * U) {
-      double2 x[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) x[u] = rn_ld_stream2(xr + (j + 8 * u) * ldx);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const double* gr = G + (j + 8 * u) * KP;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const double gv = gr[c];
-          a0[c] = fma(x[u].x, gv, a0[c]);
-          a1[c] = fma(x[u].y, gv, a1[c]);
-        }
-      }
-    }
-    for (; j < jend; j += 8) {
-      const double2 x = rn_ld_stream2(xr + j * ldx);
-      const double* gr = G + j * KP;
+    for (int c = 0; c < K; ++c) pc[c] = 0.0;
+    for (int w = 0; w < V; ++w) {
+      const double ph = ft.phi[w + v * V];
+      if (ph == 0.0) continue;
+      const int mode = ft.rowmode[w + v * V];
+      if (mode == RN_MODE_NA) continue;
+      const RnView* ow = ft.views + w;
+      const double nw = (double)ow->n_glob;
+      int64_t src = -1;
+      if (mode == RN_MODE_MAP) src = ft.rowmap[w + v * V][r];
+      const double* fw = ow->F;
+      const int64_t ldw = ow->ldx;
 #pragma unroll
       for (int c = 0; c < K; ++c) {
-        const double gv = gr[c];
-        a0[c] = fma(x.x, gv, a0[c]);
-        a1[c] = fma(x.y, gv, a1[c]);
+        const double m = (src >= 0) ? fw[(int64_t)c * ldw + src] : f[c];
+        pc[c] += (ph * m) * nw;
       }
     }
-    __syncthreads();
-    for (int w = 0; w < 8; ++w) {
-      if (warp == w) {
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          Ps[(2 * lane) * KP + c] += a0[c];
-          Ps[(2 * lane + 1) * KP + c] += a1[c];
-        }
-      }
-      __syncthreads();
-    }
-  }
-
-  if (ncs > 1) {
-    double* mine = vw.Ppart + ((int64_t)cs * ldx + r0) * KP;
-    for (int i = tid; i < RN_ROW_TILE * KP; i += 256) mine[i] = Ps[i];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&vw.tile_ticket[tile], 1) == ncs - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int i = tid; i < RN_ROW_TILE * KP; i += 256) {
-      double s = 0.0;
-      for (int c2 = 0; c2 < ncs; ++c2) s += __ldcg(vw.Ppart + ((int64_t)c2 * ldx + r0) * KP + i);
-      Ps[i] = s;
-    }
-    if (tid == 0) vw.tile_ticket[tile] = 0;
-  }
-
-  // ---- epilogue: update_f (R/update_steps.r:141-165) -------------------------------------------
-  if (tid < K * K) Ssm[tid] = vw.S[tid];
-  if (tid < K) lamh[tid] = 0.5 * vw.lam[tid];
-  __syncthreads();
-  if (tid < K * K) {  // W = crossprod(G) %*% t(S)
-    const int a = tid % K, b = tid / K;
-    double s = 0.0;
-    for (int c = 0; c < K; ++c) s = fma(vw.GtG[a + c * K], Ssm[b + c * K], s);
-    Wsm[a + b * K] = s;
-  }
-  __syncthreads();
-
-  const int V = ft.n_views;
-  if (tid < RN_ROW_TILE) {
-    const int64_t r = r0 + tid;
-    if (r < vw.n) {
-      double P[K], f[K], N[K], FS[K], D[K];
-#pragma unroll
-      for (int c = 0; c < K; ++c) {
-        P[c] = Ps[tid * KP + c];
-        f[c] = vw.F[(int64_t)c * ldx + r];
-      }
-#pragma unroll
-      for (int c = 0; c < K; ++c) {  // (X G) t(S)
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < K; ++a) s = fma(P[a], Ssm[c + a * K], s);
-        N[c] = s;
-      }
-#pragma unroll
-      for (int a = 0; a < K; ++a) {  // F S
-        double s = 0.0;
-#pragma unroll
-        for (int b = 0; b < K; ++b) s = fma(f[b], Ssm[b + a * K], s);
-        FS[a] = s;
-      }
-#pragma unroll
-      for (int c = 0; c < K; ++c) {  // (F S) W
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < K; ++a) s = fma(FS[a], Wsm[a + c * K], s);
-        D[c] = s;
-      }
-      double phisum = 0.0;
-      for (int w = 0; w < V; ++w) phisum += ft.phi[w + v * V];
-      if (phisum == 0.0) {
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          double ratio = N[c] / (D[c] + lamh[c]);
-          if (isnan(ratio)) ratio = 1.0;
-          vw.F[(int64_t)c * ldx + r] = fabs(f[c] * ratio);
-        }
-      } else {
-        double pc[K];
-#pragma unroll
-        for (int c = 0; c < K; ++c) pc[c] = 0.0;
-        for (int w = 0; w < V; ++w) {
-          const double ph = ft.phi[w + v * V];
-          if (ph == 0.0) continue;
-          const int mode = ft.rowmode[w + v * V];
-          if (mode == RN_MODE_NA) continue;
-          const RnView* ow = ft.views + w;
-          const double nw = (double)ow->n;
-          int64_t src = -1;
-          if (mode == RN_MODE_MAP) src = ft.rowmap[w + v * V][r];
-          const double* fw = ow->F;
-          const int64_t ldw = ow->ldx;
-#pragma unroll
-          for (int c = 0; c < K; ++c) {
-            const double m = (src >= 0) ? fw[(int64_t)c * ldw + src] : f[c];
-            pc[c] += (ph * m) * nw;
-          }
-        }
-        const double nv = (double)vw.n;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const double num = N[c] + pc[c] / nv;
-          const double den = (D[c] + phisum * f[c]) + lamh[c];
-          vw.F[(int64_t)c * ldx + r] = fabs(f[c] * (num / den));
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// G stream, tensor-core path:  T = X'.F  (+ F'F and colSums(F) from the CTAs of column group 0)
-//   grid (col_groups, rs), 128 threads.  A CTA owns 64 data columns and the 64-row steps of split rs;
-//   its 4 warps interleave over the steps.  Lane (g,t) of a warp feeds, for every 8-column block jb,
-//   column 8*jb+g and rows 8i + 2t + {0,1} (i = 0..7) of the step, so that each LDG.128 of a warp covers
-//   whole 32 B sectors and each column is read in 512 B contiguous pieces.
-// ------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(128) rn_g_stream_mma(const RnView vw, const RnFit ft) {
-  constexpr int KP = 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = blockIdx.x, rs = blockIdx.y, nrs = gridDim.y;
-  const int g = lane >> 2, t = lane & 3;
-  if (ft.ctrl->done) return;
-
-  __shared__ double Ts[RN_COL_GROUP * KP];
-  __shared__ double FFs[K * K + K];
-  __shared__ int s_last;
-
-  const int64_t ldx = vw.ldx;
-  const int ns = (int)(ldx / RN_ROW_TILE);
-  const int s0 = (int)((int64_t)ns * rs / nrs), s1 = (int)((int64_t)ns * (rs + 1) / nrs);
-  const int64_t j0 = (int64_t)grp * RN_COL_GROUP;
-  const int njb = (int)min((int64_t)8, (vw.pp - j0) >> 3);
-  const bool doFF = (grp == 0);
-  const double* __restrict__ X = vw.X;
-  const double* __restrict__ F = vw.F;
-
-  double acc[8][2];
-#pragma unroll
-  for (int jb = 0; jb < 8; ++jb) acc[jb][0] = acc[jb][1] = 0.0;
-  double aff0 = 0.0, aff1 = 0.0, acs0 = 0.0, acs1 = 0.0;
-
-  for (int i = tid; i < RN_COL_GROUP * KP; i += 128) Ts[i] = 0.0;
-  if (tid < K * K + K) FFs[tid] = 0.0;
-
-  for (int s = s0 + warp; s < s1; s += 4) {
-    const int64_t rr = (int64_t)s * RN_ROW_TILE + 2 * t;
-    const double* fp = F + (int64_t)g * ldx + rr;
-    double2 f2[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f2[i] = *reinterpret_cast<const double2*>(fp + 8 * i);
-    if (doFF) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rn_dmma(aff0, aff1, f2[i].x, f2[i].x);
-        rn_dmma(aff0, aff1, f2[i].y, f2[i].y);
-        rn_dmma(acs0, acs1, 1.0, f2[i].x);
-        rn_dmma(acs0, acs1, 1.0, f2[i].y);
-      }
-    }
-    const double* xp = X + (j0 + g) * ldx + rr;
-    double2 xa[8], xb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xp + 8 * i);
-#pragma unroll
-    for (int jb = 0; jb < 8; jb += 2) {
-      if (jb + 1 < njb) {
-        const double* xq = xp + (int64_t)(8 * (jb + 1)) * ldx;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xb[i] = rn_ld_stream2(xq + 8 * i);
-      }
-      if (jb < njb) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rn_dmma(acc[jb][0], acc[jb][1], xa[i].x, f2[i].x);
-          rn_dmma(acc[jb][0], acc[jb][1], xa[i].y, f2[i].y);
-        }
-      }
-      if (jb + 2 < njb) {
-        const double* xq = xp + (int64_t)(8 * (jb + 2)) * ldx;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xq + 8 * i);
-      }
-      if (jb + 1 < njb) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rn_dmma(acc[jb + 1][0], acc[jb + 1][1], xb[i].x, f2[i].x);
-          rn_dmma(acc[jb + 1][0], acc[jb + 1][1], xb[i].y, f2[i].y);
-        }
-      }
-    }
-  }
-
-  __syncthreads();
-  for (int w = 0; w < 4; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int jb = 0; jb < 8; ++jb) {
-        Ts[(8 * jb + g) * KP + 2 * t] += acc[jb][0];
-        Ts[(8 * jb + g) * KP + 2 * t + 1] += acc[jb][1];
-      }
-      if (doFF) {
-        if (g < K) {
-          if (2 * t < K) FFs[g + (2 * t) * K] += aff0;
-          if (2 * t + 1 < K) FFs[g + (2 * t + 1) * K] += aff1;
-        }
-        if (g == 0) {
-          if (2 * t < K) FFs[K * K + 2 * t] += acs0;
-          if (2 * t + 1 < K) FFs[K * K + 2 * t + 1] += acs1;
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  if (doFF && tid < K * K + K) vw.FFpart[(int64_t)rs * (K * K + K) + tid] = FFs[tid];
-
-  if (nrs == 1) {
-    double* out = vw.T + j0 * KP;
-    for (int i = tid; i < 8 * njb * KP; i += 128) out[i] = Ts[i];
-    return;
-  }
-  double* mine = vw.Tpart + ((int64_t)rs * vw.pp + j0) * KP;
-  for (int i = tid; i < 8 * njb * KP; i += 128) mine[i] = Ts[i];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&vw.group_ticket[grp], 1) == nrs - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < 8 * njb * KP; i += 128) {
-    double s = 0.0;
-    for (int r2 = 0; r2 < nrs; ++r2) s += __ldcg(vw.Tpart + ((int64_t)r2 * vw.pp + j0) * KP + i);
-    vw.T[j0 * KP + i] = s;
-  }
-  if (tid == 0) vw.group_ticket[grp] = 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// G stream, CUDA-core path:  T = X'.F.  grid (col_groups32, rs), 256 threads.  Warp w owns data
-// columns j0 + 4w .. +3, lanes own rows 2*lane + {0,1} of every 64-row step; F rows come through L1.
-// ------------------------------------------------------------------------------------------------
-template <int K, int KP>
-__global__ void __launch_bounds__(256) rn_g_stream_dfma(const RnView vw, const RnFit ft) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = blockIdx.x, rs = blockIdx.y, nrs = gridDim.y;
-  if (ft.ctrl->done) return;
-  __shared__ double Ts[RN_COL_GROUP_DFMA * KP];
-  __shared__ int s_last;
-
-  const int64_t ldx = vw.ldx;
-  const int ns = (int)(ldx / RN_ROW_TILE);
-  const int s0 = (int)((int64_t)ns * rs / nrs), s1 = (int)((int64_t)ns * (rs + 1) / nrs);
-  const int64_t j0 = (int64_t)grp * RN_COL_GROUP_DFMA;
-  const int64_t jc = j0 + 4 * warp;
-  const int ncols = (int)min((int64_t)RN_COL_GROUP_DFMA, vw.pp - j0);
-  const bool active = jc < vw.pp;
-  const double* __restrict__ X = vw.X;
-  const double* __restrict__ F = vw.F;
-
-  double acc[4][K];
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-    for (int c = 0; c < K; ++c) acc[jj][c] = 0.0;
-
-  if (active) {
-    for (int s = s0; s < s1; ++s) {
-      const int64_t rr = (int64_t)s * RN_ROW_TILE + 2 * lane;
-      double2 x[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) x[jj] = rn_ld_stream2(X + (jc + jj) * ldx + rr);
-      double2 f2[K];
-#pragma unroll
-      for (int c = 0; c < K; ++c) f2[c] = *reinterpret_cast<const double2*>(F + (int64_t)c * ldx + rr);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-        for (int c = 0; c < K; ++c) acc[jj][c] = fma(x[jj].y, f2[c].y, fma(x[jj].x, f2[c].x, acc[jj][c]));
-    }
-  }
-  for (int i = tid; i < RN_COL_GROUP_DFMA * KP; i += 256) Ts[i] = 0.0;
-  __syncthreads();
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj)
+    const double nv = (double)vw.n_glob;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      const double s = rn_warp_sum(acc[jj][c]);
-      if (lane == 0) Ts[(4 * warp + jj) * KP + c] = s;
+      const double num = N[c] + pc[c] / nv;
+      const double den = (D[c] + phisum * f[c]) + lamh[c];
+      vw.F[(int64_t)c * ldx + r] = fabs(f[c] * (num / den));
     }
-  __syncthreads();
-
-  if (nrs == 1) {
-    for (int i = tid; i < ncols * KP; i += 256) vw.T[j0 * KP + i] = Ts[i];
-    return;
   }
-  double* mine = vw.Tpart + ((int64_t)rs * vw.pp + j0) * KP;
-  for (int i = tid; i < ncols * KP; i += 256) mine[i] = Ts[i];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&vw.group_ticket[grp], 1) == nrs - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < ncols * KP; i += 256) {
-    double s = 0.0;
-    for (int r2 = 0; r2 < nrs; ++r2) s += __ldcg(vw.Tpart + ((int64_t)r2 * vw.pp + j0) * KP + i);
-    vw.T[j0 * KP + i] = s;
-  }
-  if (tid == 0) vw.group_ticket[grp] = 0;
 }
 
-// F'F and colSums(F) partials for the CUDA-core path.  grid (nff), 256 threads; FFpart[cta][k*k+k].
+// update_g for one data column j (R/update_steps.r:180-207).  Tj = crossprod(X, F)[j,], Ssm = S,
+// Vs = crossprod(F) S, muh = mu/2.  Returns |G_new[j,]| in gn and writes it in place.
 template <int K>
-__global__ void __launch_bounds__(256) rn_gram_f(const RnView vw, const RnFit ft) {
-  const int tid = threadIdx.x;
-  if (ft.ctrl->done) return;
-  constexpr int NOUT = K * K + K;
-  constexpr int PER = (NOUT + 255) / 256;  // outputs per thread (2 for k = 16)
-  __shared__ double rows[256 * K];
-  const int64_t ldx = vw.ldx;
-  const int nchunks = (int)((ldx + 255) / 256);
-  const int c0 = (int)((int64_t)nchunks * blockIdx.x / gridDim.x);
-  const int c1 = (int)((int64_t)nchunks * (blockIdx.x + 1) / gridDim.x);
-  double acc[PER];
+__device__ __forceinline__ void rn_update_g_row(const RnView& vw, const RnFit& ft, const int v, const int64_t j,
+                                                const double* Tj, const double* Ssm, const double* Vs,
+                                                const double* muh, double* gn) {
+  const int KP = vw.kp;
+  const int V = ft.n_views;
+  double gj[K], N[K], GS[K], D[K];
 #pragma unroll
-  for (int q = 0; q < PER; ++q) acc[q] = 0.0;
-  for (int ch = c0; ch < c1; ++ch) {
-    const int64_t r = (int64_t)ch * 256 + tid;
+  for (int c = 0; c < K; ++c) gj[c] = vw.G[j * KP + c];
 #pragma unroll
-    for (int c = 0; c < K; ++c) rows[tid * K + c] = (r < vw.n) ? vw.F[(int64_t)c * ldx + r] : 0.0;
-    __syncthreads();
+  for (int c = 0; c < K; ++c) {  // crossprod(X, F) %*% S
+    double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-      const int o = tid + 256 * q;
-      if (o < K * K) {
-        const int a = o % K, b = o / K;
-        for (int i = 0; i < 256; ++i) acc[q] = fma(rows[i * K + a], rows[i * K + b], acc[q]);
-      } else if (o < NOUT) {
-        const int b = o - K * K;
-        for (int i = 0; i < 256; ++i) acc[q] += rows[i * K + b];
+    for (int a = 0; a < K; ++a) s = fma(Tj[a], Ssm[a + c * K], s);
+    N[c] = s;
+  }
+#pragma unroll
+  for (int a = 0; a < K; ++a) {  // G t(S)
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < K; ++b) s = fma(gj[b], Ssm[a + b * K], s);
+    GS[a] = s;
+  }
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < K; ++a) s = fma(GS[a], Vs[a + c * K], s);
+    D[c] = s;
+  }
+  if (ft.psi_total == 0.0) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      double ratio = N[c] / (D[c] + muh[c]);
+      if (isnan(ratio)) ratio = 1.0;
+      gn[c] = fabs(gj[c] * ratio);
+    }
+  } else {
+    double psisum = 0.0;
+    for (int w = 0; w < V; ++w) psisum += ft.psi[w + v * V];
+    double pc[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) pc[c] = 0.0;
+    for (int w = 0; w < V; ++w) {
+      const double ps = ft.psi[w + v * V];
+      if (ps == 0.0) continue;
+      const int mode = ft.colmode[w + v * V];
+      if (mode == RN_MODE_NA) continue;
+      const RnView* ow = ft.views + w;
+      const double pw = (double)ow->p;
+      int64_t src = -1;
+      if (mode == RN_MODE_MAP) src = ft.colmap[w + v * V][j];
+      const double* gw = ow->G;
+      const int kpw = ow->kp;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const double m = (src >= 0) ? gw[src * kpw + c] : gj[c];
+        pc[c] += (ps * m) * pw;
       }
     }
-    __syncthreads();
+    const double pv = (double)vw.p;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const double num = N[c] + pc[c] / pv;
+      const double den = (D[c] + psisum * gj[c]) + muh[c];
+      gn[c] = fabs(gj[c] * (num / den));
+    }
   }
 #pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const int o = tid + 256 * q;
-    if (o < NOUT) vw.FFpart[(int64_t)blockIdx.x * NOUT + o] = acc[q];
+  for (int c = 0; c < K; ++c) vw.G[j * KP + c] = gn[c];
+}
+
+// Iteration bookkeeping (R/main.r:74-80): mean error over the views, history, stop rule.  One thread.
+__device__ __forceinline__ void rn_finish_dev(const RnFit& ft) {
+  RnCtrl* c = ft.ctrl;
+  double s = 0.0;
+  for (int v = 0; v < ft.n_views; ++v) s += ft.views[v].scal[1];
+  const double mean = s / (double)ft.n_views;
+  if (c->hist_count < ft.hist_cap) ft.hist[c->hist_count] = mean;
+  c->hist_count += 1;
+  c->iters += 1;
+  const double diff = fabs(mean - c->prev_err);
+  c->last_diff = diff;
+  c->prev_err = mean;
+  if (c->conv_mode) {
+    if (isnan(mean)) c->done = 2;
+    else if (!(diff > c->tol)) c->done = 1;
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// G epilogue: update_g (R/update_steps.r:180-207), partial G'G | A | colSums(G); the last CTA then
-// finishes the view: update_s (:220-240), update_lm (:249-251), algebraic error.
-//   grid (gepi_ctas), 256 threads (128 for k > 8), one data column (row of G) per thread.
-// ------------------------------------------------------------------------------------------------
-template <int K, int KP>
-__global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView vw, const RnFit ft, const int v) {
-  constexpr int NT = RN_GEPI_THREADS(K);
+// Finishes view v once G'G | A | colSums(G) (fin[0..2K^2+K)) and F'F | colSums(F) (FtFs) are complete:
+// update_s (R/update_steps.r:220-240), update_lm (:249-251), algebraic error, and -- when fuse_finish --
+// the iteration bookkeeping.  Called by all NT threads of the last CTA.  Us / Sn / red: K*K scratch.
+template <int K, int NT>
+__device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft, const int v, const int tid,
+                                               const double* fin, const double* FtFs, const double* Ssm,
+                                               double* Us, double* Sn, double* red, const int fuse_finish) {
   constexpr int KK = K * K;
-  constexpr int NOUT = 2 * KK + K;
-  const int tid = threadIdx.x;
-  if (ft.ctrl->done) return;
-
-  __shared__ double Ssm[KK], FtFs[KK + K], Vs[KK], muh[K];
-  __shared__ double Tsm[NT * K], Gsm[NT * K];
-  __shared__ double Us[KK], Sn[KK];
-  __shared__ int s_last;
-  static_assert(NOUT <= NT * K && KK <= NT * K, "last-CTA scratch is aliased onto the row buffers");
-  double* const fin = Tsm;  // only used by the last CTA, after every thread is done with Tsm / Gsm
-  double* const red = Gsm;
-
-  for (int o = tid; o < KK; o += NT) Ssm[o] = vw.S[o];
-  if (tid < K) muh[tid] = 0.5 * vw.mu[tid];
-  for (int o = tid; o < KK + K; o += NT) {  // F'F | colSums(F): fixed-order sum of the partials
-    double s = 0.0;
-    for (int i = 0; i < vw.nff; ++i) s += vw.FFpart[(int64_t)i * (KK + K) + o];
-    FtFs[o] = s;
-  }
-  __syncthreads();
-  for (int o = tid; o < KK; o += NT) {  // V = crossprod(F) %*% S
-    const int a = o % K, c = o / K;
-    double s = 0.0;
-    for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
-    Vs[a + c * K] = s;
-  }
-  __syncthreads();
-
   const int V = ft.n_views;
-  const int64_t j = (int64_t)blockIdx.x * NT + tid;
-  {
-    double Tj[K], gj[K], gn[K];
-    if (j < vw.p) {
-      double N[K], GS[K], D[K];
-#pragma unroll
-      for (int c = 0; c < K; ++c) {
-        Tj[c] = vw.T[j * KP + c];
-        gj[c] = vw.G[j * KP + c];
-      }
-#pragma unroll
-      for (int c = 0; c < K; ++c) {  // crossprod(X, F) %*% S
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < K; ++a) s = fma(Tj[a], Ssm[a + c * K], s);
-        N[c] = s;
-      }
-#pragma unroll
-      for (int a = 0; a < K; ++a) {  // G t(S)
-        double s = 0.0;
-#pragma unroll
-        for (int b = 0; b < K; ++b) s = fma(gj[b], Ssm[a + b * K], s);
-        GS[a] = s;
-      }
-#pragma unroll
-      for (int c = 0; c < K; ++c) {
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < K; ++a) s = fma(GS[a], Vs[a + c * K], s);
-        D[c] = s;
-      }
-      if (ft.psi_total == 0.0) {
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          double ratio = N[c] / (D[c] + muh[c]);
-          if (isnan(ratio)) ratio = 1.0;
-          gn[c] = fabs(gj[c] * ratio);
-        }
-      } else {
-        double psisum = 0.0;
-        for (int w = 0; w < V; ++w) psisum += ft.psi[w + v * V];
-        double pc[K];
-#pragma unroll
-        for (int c = 0; c < K; ++c) pc[c] = 0.0;
-        for (int w = 0; w < V; ++w) {
-          const double ps = ft.psi[w + v * V];
-          if (ps == 0.0) continue;
-          const int mode = ft.colmode[w + v * V];
-          if (mode == RN_MODE_NA) continue;
-          const RnView* ow = ft.views + w;
-          const double pw = (double)ow->p;
-          int64_t src = -1;
-          if (mode == RN_MODE_MAP) src = ft.colmap[w + v * V][j];
-          const double* gw = ow->G;
-          const int kpw = ow->kp;
-#pragma unroll
-          for (int c = 0; c < K; ++c) {
-            const double m = (src >= 0) ? gw[src * kpw + c] : gj[c];
-            pc[c] += (ps * m) * pw;
-          }
-        }
-        const double pv = (double)vw.p;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const double num = N[c] + pc[c] / pv;
-          const double den = (D[c] + psisum * gj[c]) + muh[c];
-          gn[c] = fabs(gj[c] * (num / den));
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < K; ++c) vw.G[j * KP + c] = gn[c];
-    } else {
-#pragma unroll
-      for (int c = 0; c < K; ++c) Tj[c] = gn[c] = 0.0;
-    }
-#pragma unroll
-    for (int c = 0; c < K; ++c) {
-      Tsm[tid * K + c] = Tj[c];
-      Gsm[tid * K + c] = gn[c];
-    }
-  }
-  __syncthreads();
-  // partial G'G | A = T'G | colSums(G) of this CTA's 256 data columns
-  for (int o = tid; o < NOUT; o += NT) {
-    double s = 0.0;
-    if (o < KK) {
-      const int a = o % K, b = o / K;
-      for (int i = 0; i < NT; ++i) s = fma(Gsm[i * K + a], Gsm[i * K + b], s);
-    } else if (o < 2 * KK) {
-      const int a = (o - KK) % K, b = (o - KK) / K;
-      for (int i = 0; i < NT; ++i) s = fma(Tsm[i * K + a], Gsm[i * K + b], s);
-    } else {
-      const int c = o - 2 * KK;
-      for (int i = 0; i < NT; ++i) s += Gsm[i * K + c];
-    }
-    vw.GGpart[(int64_t)blockIdx.x * NOUT + o] = s;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&vw.misc_ticket[0], 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (tid == 0) vw.misc_ticket[0] = 0;
-
-  // ---- last CTA: finish the view ------------------------------------------------------------------
-  for (int o = tid; o < NOUT; o += NT) {
-    double s = 0.0;
-    for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(vw.GGpart + (int64_t)i * NOUT + o);
-    fin[o] = s;
-    if (o < KK) vw.GtG[o] = s;
-    else if (o < 2 * KK) vw.A[o - KK] = s;
-    else vw.csG[o - 2 * KK] = s;
-  }
-  for (int o = tid; o < KK; o += NT) vw.FtF[o] = FtFs[o];
-  if (tid < K) vw.csF[tid] = FtFs[KK + tid];
-  __syncthreads();
   const double* GtGn = fin;
   const double* An = fin + KK;
   const double* csGn = fin + 2 * KK;
+  for (int o = tid; o < KK; o += NT) {
+    vw.GtG[o] = GtGn[o];
+    vw.A[o] = An[o];
+    vw.FtF[o] = FtFs[o];
+  }
+  if (tid < K) {
+    vw.csG[tid] = csGn[tid];
+    vw.csF[tid] = FtFs[KK + tid];
+  }
   for (int o = tid; o < KK; o += NT) {  // U = crossprod(F) %*% S
     const int a = o % K, c = o / K;
     double s = 0.0;
@@ -736,28 +313,690 @@ __global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView
     const double e = (xn + s) / xn;
     vw.scal[1] = e;
     vw.scal[2] = e;
-    int need = 0;
-    if (ft.err_mode == 2) need = 1;
-    else if (ft.err_mode == 0 && e < 1.0e-3) need = 1;
-    vw.flags[0] = need;
+    vw.flags[0] = (ft.err_mode == 2) ? 1 : 0;  // DIRECT: the residual pass that follows overwrites scal[1]
+    if (ft.err_mode == 0 && e < 1.0e-3) ft.ctrl->want_direct = 1;  // AUTO: cancellation would cost digits
+    if (fuse_finish) {
+      __threadfence();
+      if (ft.err_mode == 0 && ft.ctrl->want_direct) ft.ctrl->done = 3;  // pause: host re-does the error
+      else rn_finish_dev(ft);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Direct residual: sum (X - (F S) G')^2, one extra pass over X.  grid (row_tiles, resid_cs), 256 thr.
-// Runs only when flags[0] is set (error mode DIRECT, or AUTO with a small algebraic error).
+// F step, tensor-core path (k <= 8), persistent stream-K.
+//   grid = resident CTAs, 256 threads.  Unit = 64 rows x 32 data columns of X (16 KB, contiguous in
+//   the panel layout).  In a unit warp w owns columns 4w..4w+3; lane (g,t) loads rows 16m+2g+{0,1}
+//   (m = 0..3) of column 4w+t, so a warp reads 2 KB contiguous per unit and the CTA 16 KB.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256, 2) rn_f_step_sk(const RnView vw, const RnFit ft, const int v) {
+  constexpr int KP = 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (ft.ctrl->done) return;  // state is frozen once the stop rule fired (uniform over the grid)
+
+  __shared__ double Ps[RN_ROW_TILE * KP];
+  __shared__ double Ssm[K * K], Wsm[K * K], lamh[K];
+  __shared__ int s_flag;
+
+  if (tid < K * K) Ssm[tid] = vw.S[tid];
+  if (tid < K) lamh[tid] = 0.5 * vw.lam[tid];
+  __syncthreads();
+  if (tid < K * K) {  // W = crossprod(G) %*% t(S)
+    const int a = tid % K, b = tid / K;
+    double s = 0.0;
+    for (int c = 0; c < K; ++c) s = fma(vw.GtG[a + c * K], Ssm[b + c * K], s);
+    Wsm[a + b * K] = s;
+  }
+
+  const int64_t pp = vw.pp;
+  const int64_t UPT = pp >> 5;  // units per row tile
+  const int64_t U = (int64_t)vw.row_tiles * UPT;
+  const int64_t C = gridDim.x, cta = blockIdx.x;
+  const RnSplit sp(U, C);
+  const int64_t u0 = sp.begin(cta), u1 = sp.begin(cta + 1);
+  const double* __restrict__ G = vw.G;
+
+  for (int64_t u = u0; u < u1;) {
+    const int64_t tile = u / UPT;
+    const int64_t cb0 = u - tile * UPT;
+    const int64_t cb1 = min(UPT, cb0 + (u1 - u));
+    const bool first_seg = (u == u0);
+    u += cb1 - cb0;
+
+    double acc[4][2][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) acc[m][h][0] = acc[m][h][1] = 0.0;
+    const double* xt = vw.X + (tile * pp + 4 * warp + t) * RN_ROW_TILE + 2 * g;
+    const double* gt = G + (4 * warp + t) * KP + g;
+    int64_t cb = cb0;
+    for (; cb + 3 < cb1; cb += 4) {
+      double2 x[4][4];
+      double b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double* xp = xt + (cb + q) * (32 * RN_ROW_TILE);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) x[q][m] = rn_ld_stream2(xp + 16 * m);
+        b[q] = gt[(cb + q) * (32 * KP)];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          rn_dmma(acc[m][0][0], acc[m][0][1], x[q][m].x, b[q]);
+          rn_dmma(acc[m][1][0], acc[m][1][1], x[q][m].y, b[q]);
+        }
+    }
+    for (; cb < cb1; ++cb) {
+      const double* xp = xt + cb * (32 * RN_ROW_TILE);
+      double2 x[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) x[m] = rn_ld_stream2(xp + 16 * m);
+      const double b = gt[cb * (32 * KP)];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        rn_dmma(acc[m][0][0], acc[m][0][1], x[m].x, b);
+        rn_dmma(acc[m][1][0], acc[m][1][1], x[m].y, b);
+      }
+    }
+
+    __syncthreads();  // previous segment's epilogue is done with Ps
+    for (int i = tid; i < RN_ROW_TILE * KP; i += 256) Ps[i] = 0.0;
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) {  // fixed warp order
+      if (warp == w) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = 16 * m + 2 * g + h;
+            Ps[row * KP + 2 * t] += acc[m][h][0];
+            Ps[row * KP + 2 * t + 1] += acc[m][h][1];
+          }
+      }
+      __syncthreads();
+    }
+
+    if (!(cb0 == 0 && cb1 == UPT)) {  // the tile straddles CTAs: combine in CTA order
+      double* mine = vw.Ppart + (cta * 2 + (first_seg ? 0 : 1)) * (RN_ROW_TILE * KP);
+      for (int i = tid; i < RN_ROW_TILE * KP; i += 256) mine[i] = Ps[i];
+      __threadfence();
+      __syncthreads();
+      const int64_t c_first = sp.owner(tile * UPT), c_last = sp.owner(tile * UPT + UPT - 1);
+      if (tid == 0) s_flag = (atomicAdd(&vw.tile_ticket[tile], 1) == (int)(c_last - c_first));
+      __syncthreads();
+      if (!s_flag) continue;
+      __threadfence();
+      for (int i = tid; i < RN_ROW_TILE * KP; i += 256) {
+        double s = 0.0;
+        for (int64_t c2 = c_first; c2 <= c_last; ++c2) {
+          const int slot = (sp.begin(c2) / UPT == tile) ? 0 : 1;
+          s += __ldcg(vw.Ppart + (c2 * 2 + slot) * (RN_ROW_TILE * KP) + i);
+        }
+        Ps[i] = s;
+      }
+      if (tid == 0) vw.tile_ticket[tile] = 0;
+      __syncthreads();
+    }
+
+    if (tid < RN_ROW_TILE) {
+      const int64_t r = tile * RN_ROW_TILE + tid;
+      if (r < vw.n) {
+        double P[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) P[c] = Ps[tid * KP + c];
+        rn_update_f_row<K>(vw, ft, v, r, P, Ssm, Wsm, lamh);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G step, tensor-core path (k <= 8), persistent stream-K, fused epilogue.
+//   grid = resident CTAs, 128 threads.  Unit = 64 data columns x 64 rows of X (32 KB contiguous in the
+//   panel layout); units are ordered column-group-major, so a CTA streams consecutive row steps of one
+//   column group.  Lane (g,t) feeds, for every 8-column block jb, column 8jb+g and rows 8i+2t+{0,1}
+//   (i = 0..7).  The F fragment of a step doubles as both operands of F'F (column group 0 only).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const RnFit ft, const int v,
+                                                       const int fuse_finish) {
+  constexpr int KP = 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (ft.ctrl->done) return;
+
+  __shared__ double Ts[RN_COL_GROUP * KP];
+  __shared__ double Gs[RN_COL_GROUP * K];
+  __shared__ double FFs[NFF], FtFs[NFF];
+  __shared__ double Ssm[KK], Vs[KK], muh[K];
+  __shared__ double fin[NOUT], Us[KK], Sn[KK], red[KK];
+  __shared__ int s_flag;
+
+  const int64_t pp = vw.pp, ldx = vw.ldx;
+  const int64_t NS = vw.row_tiles, NG = vw.col_groups;
+  const int64_t U = NS * NG;
+  const int64_t C = gridDim.x, cta = blockIdx.x;
+  const RnSplit sp(U, C);
+  const int64_t u0 = sp.begin(cta), u1 = sp.begin(cta + 1);
+  const int nffc = (int)sp.owner(NS - 1) + 1;  // CTAs that stream part of column group 0
+  const double* __restrict__ F = vw.F;
+  bool ff_ready = false;
+
+  for (int i = tid; i < KK; i += 128) Ssm[i] = vw.S[i];
+  if (tid < K) muh[tid] = 0.5 * vw.mu[tid];
+
+  for (int64_t u = u0; u < u1;) {
+    const int64_t grp = u / NS;
+    const int64_t s0 = u - grp * NS;
+    const int64_t s1 = min(NS, s0 + (u1 - u));
+    const bool first_seg = (u == u0);
+    u += s1 - s0;
+    const int64_t j0 = grp * RN_COL_GROUP;
+    const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
+    const bool doFF = (grp == 0);
+
+    double acc[8][2];
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) acc[jb][0] = acc[jb][1] = 0.0;
+    double aff0 = 0.0, aff1 = 0.0, acs0 = 0.0, acs1 = 0.0;
+
+    for (int64_t s = s0 + warp; s < s1; s += 4) {
+      const double* fp = F + (int64_t)g * ldx + s * RN_ROW_TILE + 2 * t;
+      const double* xp = vw.X + (s * pp + j0 + g) * RN_ROW_TILE + 2 * t;
+      double2 f2[8], xa[8], xb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xp + 8 * i);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f2[i] = *reinterpret_cast<const double2*>(fp + 8 * i);
+      if (doFF) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rn_dmma(aff0, aff1, f2[i].x, f2[i].x);
+          rn_dmma(aff0, aff1, f2[i].y, f2[i].y);
+          rn_dmma(acs0, acs1, 1.0, f2[i].x);
+          rn_dmma(acs0, acs1, 1.0, f2[i].y);
+        }
+      }
+#pragma unroll
+      for (int jb = 0; jb < 8; jb += 2) {
+        if (jb + 1 < njb) {
+          const double* xq = xp + (8 * (jb + 1)) * RN_ROW_TILE;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xb[i] = rn_ld_stream2(xq + 8 * i);
+        }
+        if (jb < njb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rn_dmma(acc[jb][0], acc[jb][1], xa[i].x, f2[i].x);
+            rn_dmma(acc[jb][0], acc[jb][1], xa[i].y, f2[i].y);
+          }
+        }
+        if (jb + 2 < njb) {
+          const double* xq = xp + (8 * (jb + 2)) * RN_ROW_TILE;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xq + 8 * i);
+        }
+        if (jb + 1 < njb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rn_dmma(acc[jb + 1][0], acc[jb + 1][1], xb[i].x, f2[i].x);
+            rn_dmma(acc[jb + 1][0], acc[jb + 1][1], xb[i].y, f2[i].y);
+          }
+        }
+      }
+    }
+
+    __syncthreads();  // previous segment's epilogue is done with Ts / Gs / FFs
+    for (int i = tid; i < RN_COL_GROUP * KP; i += 128) Ts[i] = 0.0;
+    if (tid < NFF) FFs[tid] = 0.0;
+    __syncthreads();
+    for (int w = 0; w < 4; ++w) {  // fixed warp order
+      if (warp == w) {
+#pragma unroll
+        for (int jb = 0; jb < 8; ++jb) {
+          Ts[(8 * jb + g) * KP + 2 * t] += acc[jb][0];
+          Ts[(8 * jb + g) * KP + 2 * t + 1] += acc[jb][1];
+        }
+        if (doFF) {
+          if (g < K) {
+            if (2 * t < K) FFs[g + (2 * t) * K] += aff0;
+            if (2 * t + 1 < K) FFs[g + (2 * t + 1) * K] += aff1;
+          }
+          if (g == 0) {
+            if (2 * t < K) FFs[KK + 2 * t] += acs0;
+            if (2 * t + 1 < K) FFs[KK + 2 * t + 1] += acs1;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (doFF) {  // publish this CTA's F'F | colSums(F) partial
+      if (tid < NFF) vw.FFpart[cta * NFF + tid] = FFs[tid];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(&vw.misc_ticket[2], 1);
+    }
+
+    if (!(s0 == 0 && s1 == NS)) {  // the column group straddles CTAs: combine in CTA order
+      double* mine = vw.Tpart + (cta * 2 + (first_seg ? 0 : 1)) * (RN_COL_GROUP * KP);
+      for (int i = tid; i < RN_COL_GROUP * KP; i += 128) mine[i] = Ts[i];
+      __threadfence();
+      __syncthreads();
+      const int64_t c_first = sp.owner(grp * NS), c_last = sp.owner(grp * NS + NS - 1);
+      if (tid == 0) s_flag = (atomicAdd(&vw.group_ticket[grp], 1) == (int)(c_last - c_first));
+      __syncthreads();
+      if (!s_flag) continue;
+      __threadfence();
+      for (int i = tid; i < RN_COL_GROUP * KP; i += 128) {
+        double s = 0.0;
+        for (int64_t c2 = c_first; c2 <= c_last; ++c2) {
+          const int slot = (sp.begin(c2) / NS == grp) ? 0 : 1;
+          s += __ldcg(vw.Tpart + (c2 * 2 + slot) * (RN_COL_GROUP * KP) + i);
+        }
+        Ts[i] = s;
+      }
+      if (tid == 0) vw.group_ticket[grp] = 0;
+      __syncthreads();
+    }
+
+    // ---- epilogue of this column group: update_g, then the group's G'G | A | colSums(G) partial ----
+    if (!ff_ready) {
+      if (tid == 0) {
+        while (rn_ld_acquire(&vw.misc_ticket[2]) < nffc) __nanosleep(64);
+      }
+      __syncthreads();
+      if (tid < NFF) {
+        double s = 0.0;
+        for (int i = 0; i < nffc; ++i) s += __ldcg(vw.FFpart + (int64_t)i * NFF + tid);
+        FtFs[tid] = s;
+      }
+      __syncthreads();
+      for (int o = tid; o < KK; o += 128) {  // V = crossprod(F) %*% S
+        const int a = o % K, c = o / K;
+        double s = 0.0;
+        for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
+        Vs[a + c * K] = s;
+      }
+      __syncthreads();
+      ff_ready = true;
+    }
+    if (tid < RN_COL_GROUP) {
+      const int64_t j = j0 + tid;
+      double gn[K];
+      if (j < vw.p) {
+        double Tj[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) Tj[c] = Ts[tid * KP + c];
+        rn_update_g_row<K>(vw, ft, v, j, Tj, Ssm, Vs, muh, gn);
+      } else {
+#pragma unroll
+        for (int c = 0; c < K; ++c) gn[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < K; ++c) Gs[tid * K + c] = gn[c];
+    }
+    __syncthreads();
+    for (int o = tid; o < NOUT; o += 128) {
+      double s = 0.0;
+      if (o < KK) {
+        const int a = o % K, b = o / K;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
+      } else if (o < 2 * KK) {
+        const int a = (o - KK) % K, b = (o - KK) / K;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
+      } else {
+        const int c = o - 2 * KK;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s += Gs[i * K + c];
+      }
+      vw.GGpart[grp * NOUT + o] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = (atomicAdd(&vw.misc_ticket[0], 1) == (int)NG - 1);
+    __syncthreads();
+    if (!s_flag) continue;
+    __threadfence();
+    // ---- last column group done: finish the view --------------------------------------------------
+    for (int o = tid; o < NOUT; o += 128) {
+      double s = 0.0;
+      for (int64_t i = 0; i < NG; ++i) s += __ldcg(vw.GGpart + i * NOUT + o);
+      fin[o] = s;
+    }
+    if (tid == 0) {
+      vw.misc_ticket[0] = 0;
+      vw.misc_ticket[2] = 0;
+    }
+    __syncthreads();
+    rn_view_finish<K, 128>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// F step, CUDA-core path (any k <= 16).  grid (row_tiles, cs), 256 threads.  A CTA owns 64 rows and the
+// data columns of split `cs`; lanes own rows 2*lane+{0,1}, warp w takes columns jbeg+w, +8, ...  With
+// cs > 1 the last CTA to arrive for a row tile sums the partials in split order and runs the epilogue.
 // ------------------------------------------------------------------------------------------------
 template <int K, int KP>
-__global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit ft) {
+__global__ void __launch_bounds__(256) rn_f_step_dfma(const RnView vw, const RnFit ft, const int v) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (ft.ctrl->done || !vw.flags[0]) return;
+  const int tile = blockIdx.x, cs = blockIdx.y, ncs = gridDim.y;
+  if (ft.ctrl->done) return;
+
+  __shared__ double Ps[RN_ROW_TILE * KP];
+  __shared__ double Ssm[K * K], Wsm[K * K], lamh[K];
+  __shared__ int s_last;
+
+  const int64_t pp = vw.pp;
+  const int nb = (int)(pp >> 3);
+  const int64_t jbeg = 8 * ((int64_t)nb * cs / ncs);
+  const int64_t jend = 8 * ((int64_t)nb * (cs + 1) / ncs);
+  const double* __restrict__ G = vw.G;
+
+  for (int i = tid; i < RN_ROW_TILE * KP; i += 256) Ps[i] = 0.0;
+
+  double a0[K], a1[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) a0[c] = a1[c] = 0.0;
+  const double* xr = vw.X + (int64_t)tile * pp * RN_ROW_TILE + 2 * lane;
+  constexpr int U = 4;
+  int64_t j = jbeg + warp;
+  for (; j + 8 * (U - 1) < jend; j += 8 * U) {
+    double2 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) x[u] = rn_ld_stream2(xr + (j + 8 * u) * RN_ROW_TILE);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double* gr = G + (j + 8 * u) * KP;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const double gv = gr[c];
+        a0[c] = fma(x[u].x, gv, a0[c]);
+        a1[c] = fma(x[u].y, gv, a1[c]);
+      }
+    }
+  }
+  for (; j < jend; j += 8) {
+    const double2 x = rn_ld_stream2(xr + j * RN_ROW_TILE);
+    const double* gr = G + j * KP;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const double gv = gr[c];
+      a0[c] = fma(x.x, gv, a0[c]);
+      a1[c] = fma(x.y, gv, a1[c]);
+    }
+  }
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        Ps[(2 * lane) * KP + c] += a0[c];
+        Ps[(2 * lane + 1) * KP + c] += a1[c];
+      }
+    }
+    __syncthreads();
+  }
+
+  if (ncs > 1) {
+    double* mine = vw.Ppart + ((int64_t)cs * vw.row_tiles + tile) * (RN_ROW_TILE * KP);
+    for (int i = tid; i < RN_ROW_TILE * KP; i += 256) mine[i] = Ps[i];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&vw.tile_ticket[tile], 1) == ncs - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = tid; i < RN_ROW_TILE * KP; i += 256) {
+      double s = 0.0;
+      for (int c2 = 0; c2 < ncs; ++c2)
+        s += __ldcg(vw.Ppart + ((int64_t)c2 * vw.row_tiles + tile) * (RN_ROW_TILE * KP) + i);
+      Ps[i] = s;
+    }
+    if (tid == 0) vw.tile_ticket[tile] = 0;
+  }
+
+  if (tid < K * K) Ssm[tid] = vw.S[tid];
+  if (tid < K) lamh[tid] = 0.5 * vw.lam[tid];
+  __syncthreads();
+  if (tid < K * K) {  // W = crossprod(G) %*% t(S)
+    const int a = tid % K, b = tid / K;
+    double s = 0.0;
+    for (int c = 0; c < K; ++c) s = fma(vw.GtG[a + c * K], Ssm[b + c * K], s);
+    Wsm[a + b * K] = s;
+  }
+  __syncthreads();
+  if (tid < RN_ROW_TILE) {
+    const int64_t r = (int64_t)tile * RN_ROW_TILE + tid;
+    if (r < vw.n) {
+      double P[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) P[c] = Ps[tid * KP + c];
+      rn_update_f_row<K>(vw, ft, v, r, P, Ssm, Wsm, lamh);
+    }
+  }
+}
+
+// F'F and colSums(F) partials for the CUDA-core path.  grid (nff), 256 threads; FFpart[cta][k*k+k].
+template <int K>
+__global__ void __launch_bounds__(256) rn_gram_f(const RnView vw, const RnFit ft) {
+  const int tid = threadIdx.x;
+  if (ft.ctrl->done) return;
+  constexpr int NOUT = K * K + K;
+  constexpr int PER = (NOUT + 255) / 256;  // outputs per thread (2 for k = 16)
+  __shared__ double rows[256 * K];
+  const int64_t ldx = vw.ldx;
+  const int nchunks = (int)((ldx + 255) / 256);
+  const int c0 = (int)((int64_t)nchunks * blockIdx.x / gridDim.x);
+  const int c1 = (int)((int64_t)nchunks * (blockIdx.x + 1) / gridDim.x);
+  double acc[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) acc[q] = 0.0;
+  for (int ch = c0; ch < c1; ++ch) {
+    const int64_t r = (int64_t)ch * 256 + tid;
+#pragma unroll
+    for (int c = 0; c < K; ++c) rows[tid * K + c] = (r < vw.n) ? vw.F[(int64_t)c * ldx + r] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int o = tid + 256 * q;
+      if (o < K * K) {
+        const int a = o % K, b = o / K;
+        for (int i = 0; i < 256; ++i) acc[q] = fma(rows[i * K + a], rows[i * K + b], acc[q]);
+      } else if (o < NOUT) {
+        const int b = o - K * K;
+        for (int i = 0; i < 256; ++i) acc[q] += rows[i * K + b];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int o = tid + 256 * q;
+    if (o < NOUT) vw.FFpart[(int64_t)blockIdx.x * NOUT + o] = acc[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G stream, CUDA-core path:  T = X'.F.  grid (col_groups32, rs), 256 threads.  Warp w owns data
+// columns j0 + 4w .. +3, lanes own rows 2*lane + {0,1} of every 64-row step; F rows come through L1.
+// ------------------------------------------------------------------------------------------------
+template <int K, int KP>
+__global__ void __launch_bounds__(256) rn_g_stream_dfma(const RnView vw, const RnFit ft) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = blockIdx.x, rs = blockIdx.y, nrs = gridDim.y;
+  if (ft.ctrl->done) return;
+  __shared__ double Ts[RN_COL_GROUP_DFMA * KP];
+  __shared__ int s_last;
+
+  const int64_t ldx = vw.ldx, pp = vw.pp;
+  const int ns = vw.row_tiles;
+  const int s0 = (int)((int64_t)ns * rs / nrs), s1 = (int)((int64_t)ns * (rs + 1) / nrs);
+  const int64_t j0 = (int64_t)grp * RN_COL_GROUP_DFMA;
+  const int64_t jc = j0 + 4 * warp;
+  const int ncols = (int)min((int64_t)RN_COL_GROUP_DFMA, pp - j0);
+  const bool active = jc < pp;
+  const double* __restrict__ F = vw.F;
+
+  double acc[4][K];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+    for (int c = 0; c < K; ++c) acc[jj][c] = 0.0;
+
+  if (active) {
+    for (int s = s0; s < s1; ++s) {
+      const double* xp = vw.X + ((int64_t)s * pp + jc) * RN_ROW_TILE + 2 * lane;
+      const int64_t rr = (int64_t)s * RN_ROW_TILE + 2 * lane;
+      double2 x[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) x[jj] = rn_ld_stream2(xp + jj * RN_ROW_TILE);
+      double2 f2[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) f2[c] = *reinterpret_cast<const double2*>(F + (int64_t)c * ldx + rr);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[jj][c] = fma(x[jj].y, f2[c].y, fma(x[jj].x, f2[c].x, acc[jj][c]));
+    }
+  }
+  for (int i = tid; i < RN_COL_GROUP_DFMA * KP; i += 256) Ts[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const double s = rn_warp_sum(acc[jj][c]);
+      if (lane == 0) Ts[(4 * warp + jj) * KP + c] = s;
+    }
+  __syncthreads();
+
+  if (nrs == 1) {
+    for (int i = tid; i < ncols * KP; i += 256) vw.T[j0 * KP + i] = Ts[i];
+    return;
+  }
+  double* mine = vw.Tpart + ((int64_t)rs * pp + j0) * KP;
+  for (int i = tid; i < ncols * KP; i += 256) mine[i] = Ts[i];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&vw.group_ticket[grp], 1) == nrs - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < ncols * KP; i += 256) {
+    double s = 0.0;
+    for (int r2 = 0; r2 < nrs; ++r2) s += __ldcg(vw.Tpart + ((int64_t)r2 * pp + j0) * KP + i);
+    vw.T[j0 * KP + i] = s;
+  }
+  if (tid == 0) vw.group_ticket[grp] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone G epilogue (CUDA-core path, and the row-sharded path where T / F'F arrive from an
+// all-reduce): update_g from T in HBM, partial G'G | A | colSums(G); the last CTA finishes the view.
+//   grid (gepi_ctas), 256 threads (128 for k > 8), one data column (row of G) per thread.
+// ------------------------------------------------------------------------------------------------
+template <int K, int KP>
+__global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView vw, const RnFit ft, const int v,
+                                                                    const int fuse_finish) {
+  constexpr int NT = RN_GEPI_THREADS(K);
+  constexpr int KK = K * K;
+  constexpr int NOUT = 2 * KK + K;
+  const int tid = threadIdx.x;
+  if (ft.ctrl->done) return;
+
+  __shared__ double Ssm[KK], FtFs[KK + K], Vs[KK], muh[K];
+  __shared__ double Tsm[NT * K], Gsm[NT * K];
+  __shared__ double Us[KK], Sn[KK];
+  __shared__ int s_last;
+  static_assert(NOUT <= NT * K && KK <= NT * K, "last-CTA scratch is aliased onto the row buffers");
+  double* const fin = Tsm;  // only used by the last CTA, after every thread is done with Tsm / Gsm
+  double* const red = Gsm;
+
+  for (int o = tid; o < KK; o += NT) Ssm[o] = vw.S[o];
+  if (tid < K) muh[tid] = 0.5 * vw.mu[tid];
+  for (int o = tid; o < KK + K; o += NT) {  // F'F | colSums(F): fixed-order sum of the partials
+    double s = 0.0;
+    for (int i = 0; i < vw.nff; ++i) s += vw.FFpart[(int64_t)i * (KK + K) + o];
+    FtFs[o] = s;
+  }
+  __syncthreads();
+  for (int o = tid; o < KK; o += NT) {  // V = crossprod(F) %*% S
+    const int a = o % K, c = o / K;
+    double s = 0.0;
+    for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
+    Vs[a + c * K] = s;
+  }
+  __syncthreads();
+
+  const int64_t j = (int64_t)blockIdx.x * NT + tid;
+  {
+    double Tj[K], gn[K];
+    if (j < vw.p) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) Tj[c] = vw.T[j * KP + c];
+      rn_update_g_row<K>(vw, ft, v, j, Tj, Ssm, Vs, muh, gn);
+    } else {
+#pragma unroll
+      for (int c = 0; c < K; ++c) Tj[c] = gn[c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      Tsm[tid * K + c] = Tj[c];
+      Gsm[tid * K + c] = gn[c];
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < NOUT; o += NT) {
+    double s = 0.0;
+    if (o < KK) {
+      const int a = o % K, b = o / K;
+      for (int i = 0; i < NT; ++i) s = fma(Gsm[i * K + a], Gsm[i * K + b], s);
+    } else if (o < 2 * KK) {
+      const int a = (o - KK) % K, b = (o - KK) / K;
+      for (int i = 0; i < NT; ++i) s = fma(Tsm[i * K + a], Gsm[i * K + b], s);
+    } else {
+      const int c = o - 2 * KK;
+      for (int i = 0; i < NT; ++i) s += Gsm[i * K + c];
+    }
+    vw.GGpart[(int64_t)blockIdx.x * NOUT + o] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&vw.misc_ticket[0], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) vw.misc_ticket[0] = 0;
+  for (int o = tid; o < NOUT; o += NT) {
+    double s = 0.0;
+    for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(vw.GGpart + (int64_t)i * NOUT + o);
+    fin[o] = s;
+  }
+  __syncthreads();
+  rn_view_finish<K, NT>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct residual: sum (X - (F S) G')^2, one extra pass over X.  grid (row_tiles, resid_cs), 256 thr.
+// Runs only when flags[0] is set (error mode DIRECT) or when forced (the host's AUTO hand-over).
+// ------------------------------------------------------------------------------------------------
+template <int K, int KP>
+__global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit ft, const int force) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!force && (ft.ctrl->done || !vw.flags[0])) return;
   __shared__ double Ssm[K * K];
   __shared__ double wsum[8];
+  __shared__ double bs[256];
   __shared__ int s_last;
   const int tile = blockIdx.x, cs = blockIdx.y, ncs = gridDim.y;
-  const int64_t ldx = vw.ldx;
+  const int64_t ldx = vw.ldx, pp = vw.pp;
   const int64_t r0 = (int64_t)tile * RN_ROW_TILE + 2 * lane;
-  const int nb = (int)(vw.pp >> 3);
+  const int nb = (int)(pp >> 3);
   const int64_t jbeg = 8 * ((int64_t)nb * cs / ncs), jend = 8 * ((int64_t)nb * (cs + 1) / ncs);
   if (tid < K * K) Ssm[tid] = vw.S[tid];
   __syncthreads();
@@ -783,9 +1022,9 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
     }
   }
   double acc = 0.0;
-  const double* xr = vw.X + r0;
+  const double* xr = vw.X + (int64_t)tile * pp * RN_ROW_TILE + 2 * lane;
   for (int64_t j = jbeg + warp; j < jend; j += 8) {
-    const double2 x = rn_ld_stream2(xr + j * ldx);
+    const double2 x = rn_ld_stream2(xr + j * RN_ROW_TILE);
     const double* gr = vw.G + j * KP;
     double h0 = 0.0, h1 = 0.0;
 #pragma unroll
@@ -815,9 +1054,7 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
   __threadfence();
   double s = 0.0;
   for (int i = tid; i < nblk; i += 256) s += __ldcg(vw.Rpart + i);
-  // fixed-order block sum
-  __shared__ double bs[256];
-  bs[tid] = s;
+  bs[tid] = s;  // fixed-order block sum
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (tid < o) bs[tid] += bs[tid + o];
@@ -836,28 +1073,33 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
   }
 }
 
-// Mean error over the views, history, stop rule (R/main.r:74-80).  <<<1,1>>>.
-__global__ void rn_finish(const RnFit ft) {
-  RnCtrl* c = ft.ctrl;
-  if (c->done) return;
-  double s = 0.0;
-  for (int v = 0; v < ft.n_views; ++v) s += ft.views[v].scal[1];
-  const double mean = s / (double)ft.n_views;
-  if (c->hist_count < ft.hist_cap) ft.hist[c->hist_count] = mean;
-  c->hist_count += 1;
-  c->iters += 1;
-  const double diff = fabs(mean - c->prev_err);
-  c->last_diff = diff;
-  c->prev_err = mean;
-  if (c->conv_mode) {
-    if (isnan(mean)) c->done = 2;
-    else if (!(diff > c->tol)) c->done = 1;
-  }
+// Iteration bookkeeping as its own launch (DIRECT error mode, and the AUTO hand-over).  <<<1,1>>>.
+__global__ void rn_finish(const RnFit ft, const int force) {
+  if (!force && ft.ctrl->done) return;
+  rn_finish_dev(ft);
 }
 
 // ------------------------------------------------------------------------------------------------
 // set-up / tear-down kernels (once per fit, not on the per-iteration path)
 // ------------------------------------------------------------------------------------------------
+
+// Re-tiles `ncols` columns of a column-major source (leading dimension lds, n valid rows) into the
+// panel layout X[tile][col][64] starting at data column col0.  One thread per 16-byte piece; padding rows
+// of the last tile are written as zero.  grid-stride.
+__global__ void __launch_bounds__(256) rn_to_panels(const RnView vw, const double* __restrict__ src, int64_t lds,
+                                                    int64_t col0, int64_t ncols) {
+  const int64_t pieces = (int64_t)vw.row_tiles * ncols * 32;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < pieces; i += (int64_t)gridDim.x * 256) {
+    const int64_t h = i & 31;             // double2 index inside the 64-row column piece
+    const int64_t cj = (i >> 5) % ncols;  // column inside the chunk
+    const int64_t tile = (i >> 5) / ncols;
+    const int64_t r = tile * RN_ROW_TILE + 2 * h;
+    double2 val;
+    val.x = (r < vw.n) ? src[cj * lds + r] : 0.0;
+    val.y = (r + 1 < vw.n) ? src[cj * lds + r + 1] : 0.0;
+    *reinterpret_cast<double2*>(vw.X + (tile * vw.pp + col0 + cj) * RN_ROW_TILE + 2 * h) = val;
+  }
+}
 
 // ||X||_F^2, deterministic two-stage.  grid (nblk), 256 threads.
 __global__ void __launch_bounds__(256) rn_xnorm2(const RnView vw, double* part, int32_t* ticket) {

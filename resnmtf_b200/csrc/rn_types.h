@@ -1,7 +1,10 @@
 // Device-side descriptors shared by the kernels and the host C-ABI (resnmtf_capi.cu).
 // Data layout in HBM (see DESIGN.md "Data layout"):
-//   X   [pp][ldx]  column-major like R, rows padded to a multiple of 64 (ldx), columns to a multiple
-//                  of 8 (pp); all padding is zero so the streaming kernels need no bounds checks.
+//   X   [row_tiles][pp][64]  "panel" layout: 64-row panels, column-major inside a panel, so that both the
+//                  X.G pass (a panel's columns left to right) and the X'.F pass (a column group down the
+//                  panels) read long contiguous runs.  Rows are padded to a multiple of 64 (ldx), columns
+//                  to a multiple of 32 (pp); all padding is zero so the streaming kernels need no bounds
+//                  checks.  Element (r, j) lives at ((r/64)*pp + j)*64 + r%64.
 //   F   [kp][ldx]  column-major, kp = 8 (k<=8) or 16; padding rows/columns zero.
 //   G,T [pp][kp]   row-major (one 64 B / 128 B row per data column) so that a column's k values are one
 //                  uniform / vector load in the X.G pass and one gather in the psi coupling.
@@ -20,7 +23,8 @@
 #define RN_MODE_MAP 2   // int32 gather map, -1 = name not shared
 
 struct RnCtrl {
-  int32_t done;       // 0 running, 1 converged, 2 mean error is NaN (convergence mode only)
+  int32_t done;       // 0 running, 1 converged, 2 mean error is NaN (convergence mode only),
+                      // 3 paused: AUTO error mode wants the direct residual (host takes over)
   int32_t conv_mode;  // 1: apply the stop rule of R/main.r:55
   int64_t iters;      // sweeps since set_factors
   int64_t hist_count; // entries in hist[] since the host last drained it
@@ -28,10 +32,13 @@ struct RnCtrl {
   double tol;
   double last_diff;
   int64_t direct_passes;
+  int32_t want_direct;  // sticky: some view's algebraic error fell below 1e-3 (AUTO mode)
+  int32_t pad_;
 };
 
 struct RnView {
   int64_t n, p, ldx, pp;
+  int64_t n_glob;  // rows of the whole view (== n unless the view is row-sharded over ranks)
   int32_t k, kp;
   double* X;
   double* F;
@@ -46,17 +53,18 @@ struct RnView {
   double* csF;  // k
   double* csG;  // k
   double* scal; // [0] ||X||^2  [1] err  [2] err algebraic  [3] err direct  [4] global F'F etc scratch
-  double* Ppart;   // [cs][ldx][kp]   F-step partial X.G per column split (cs > 1 only)
-  double* Tpart;   // [rs][pp][kp]    G-stream partial X'F per row split
-  double* FFpart;  // [nff][k*k+k]    partial F'F | colSums(F)
-  double* GGpart;  // [gepi_ctas][2*k*k+k]  partial G'G | A | colSums(G)
+  double* Ppart;   // stream-K: [f_ctas][2][64][kp]; CUDA-core path: [cs][row_tiles][64][kp]
+  double* Tpart;   // stream-K: [g_ctas][2][64][kp]; CUDA-core path: [rs][pp][kp]
+  double* FFpart;  // [g_ctas | nff][k*k+k]   partial F'F | colSums(F)
+  double* GGpart;  // [col_groups | gepi_ctas][2*k*k+k]  partial G'G | A | colSums(G)
   double* Rpart;   // [resid ctas]    partial residual sums
   int32_t* tile_ticket;   // [row tiles]
   int32_t* group_ticket;  // [col groups]
-  int32_t* misc_ticket;   // [0] G-epilogue  [1] residual
+  int32_t* misc_ticket;   // [0] G-epilogue  [1] residual  [2] F'F partials published
   int32_t* flags;         // [0] need_direct
-  int32_t row_tiles, cs;       // F-step grid
-  int32_t col_groups, rs;      // G-stream grid
+  int32_t row_tiles, cs;       // F-step grid (CUDA-core path)
+  int32_t col_groups, rs;      // G-stream grid (CUDA-core path); col_groups is also the stream-K group count
+  int32_t f_ctas, g_ctas;      // persistent grids of the stream-K kernels
   int32_t nff;                 // number of FFpart rows
   int32_t gepi_ctas;           // G-epilogue grid
   int32_t resid_cs;            // residual grid y

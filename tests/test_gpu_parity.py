@@ -50,14 +50,16 @@ def test_error_modes(ctx, err_mode):
 
 
 @pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
-def test_forced_splits(ctx, impl, monkeypatch):
-    """Column-split F step and row-split G stream (the cross-CTA partial + last-CTA paths)."""
-    monkeypatch.setenv("RESNMTF_F_CS", "3")
-    monkeypatch.setenv("RESNMTF_G_RS", "5")
+@pytest.mark.parametrize("split", [(3, 5, 7, 5), (1, 1, 1, 1), (2, 7, 23, 41), (4, 2, 1000000, 1000000)])
+def test_forced_splits(ctx, impl, split, monkeypatch):
+    """Work partitions that make tiles / column groups straddle CTAs in every way: column-split F step and
+    row-split G stream on the CUDA-core path, odd persistent grid sizes on the stream-K path (the
+    cross-CTA partial + last-arriver combine)."""
+    monkeypatch.setenv("RESNMTF_F_CS", str(split[0]))
+    monkeypatch.setenv("RESNMTF_G_RS", str(split[1]))
+    monkeypatch.setenv("RESNMTF_F_CTAS", str(split[2]))
+    monkeypatch.setenv("RESNMTF_G_CTAS", str(split[3]))
     prob = single_view_problem(1500, 700, 5, seed=7)
-    compare_trace(prob, ctx, n_iters=5, err_mode=L.ERR_DIRECT, impl=impl)
-    monkeypatch.setenv("RESNMTF_F_CS", "1")
-    monkeypatch.setenv("RESNMTF_G_RS", "1")
     compare_trace(prob, ctx, n_iters=5, err_mode=L.ERR_DIRECT, impl=impl)
 
 
@@ -102,20 +104,41 @@ def test_two_views_coupled(ctx, cfg, impl):
     compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=impl)
 
 
-def test_three_views_mixed_k_and_na_pairs(ctx):
-    """Unequal shapes, unequal k (no xi), one pair sharing nothing (R's NA -> skipped)."""
+def test_four_views_mixed_k_and_na_pairs(ctx):
+    """Unequal shapes; phi/psi between equal-k views, one pair sharing nothing (R's NA -> skipped), and an
+    uncoupled view with another k that still takes the coupled G branch (whole-matrix sum(psi) test)."""
     rng = np.random.default_rng(5)
-    shapes = [(120, 80), (120, 50), (90, 80)]
-    ks = [3, 4, 2]
+    shapes = [(120, 80), (120, 50), (90, 80), (70, 40)]
+    ks = [3, 3, 3, 5]
     data = [synth.prep(synth.planted_view(n, p, 3, rng, 0.3, 0.3)[0]) for n, p in shapes]
     inits = [synth.random_factors(n, p, k, rng) for (n, p), k in zip(shapes, ks)]
-    rn = [[f"r{i}" for i in range(120)], [f"r{i}" for i in range(120)], [f"q{i}" for i in range(90)]]
-    cn = [[f"c{i}" for i in range(80)], [f"d{i}" for i in range(50)], [f"c{i}" for i in range(80)]]
-    phi = np.zeros((3, 3)); phi[0, 1] = 30.0; phi[0, 2] = 7.0   # (0,2) share no row names -> NA
-    psi = np.zeros((3, 3)); psi[0, 2] = 40.0
+    rn = [[f"r{i}" for i in range(120)], [f"r{i}" for i in range(120)], [f"q{i}" for i in range(90)],
+          [f"z{i}" for i in range(70)]]
+    cn = [[f"c{i}" for i in range(80)], [f"d{i}" for i in range(50)], [f"c{i}" for i in range(80)],
+          [f"y{i}" for i in range(40)]]
+    phi = np.zeros((4, 4)); phi[0, 1] = 30.0; phi[0, 2] = 7.0   # (0,2) share no row names -> NA
+    psi = np.zeros((4, 4)); psi[0, 2] = 40.0
     prob = Problem(data, ks, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
-                   phi=O.init_rest_mats(phi, 3), psi=O.init_rest_mats(psi, 3), row_names=rn, col_names=cn)
-    compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT)
+                   phi=O.init_rest_mats(phi, 4), psi=O.init_rest_mats(psi, 4), row_names=rn, col_names=cn)
+    for impl in (L.IMPL_DFMA, L.IMPL_DMMA):
+        compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=impl)
+
+
+def test_coupling_views_of_different_k_is_rejected(ctx):
+    """phi between views with different k is non-conformable in the reference (R/utils.r:72); E_INVALID."""
+    rng = np.random.default_rng(6)
+    data = [synth.prep(synth.planted_view(50, 30, 2, rng, 0.3, 0.3)[0]) for _ in range(2)]
+    inits = [synth.random_factors(50, 30, k, rng) for k in (2, 3)]
+    phi = np.zeros((2, 2)); phi[0, 1] = 5.0
+    prob = Problem(data, [2, 3], [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
+                   phi=O.init_rest_mats(phi, 2), row_names=[[f"r{i}" for i in range(50)]] * 2)
+    fit = prob.device_fit(ctx)
+    try:
+        with pytest.raises(L.ResnmtfError) as e:
+            fit.run(1)
+        assert e.value.code == L.E_INVALID
+    finally:
+        fit.close()
 
 
 def test_convergence_matches_oracle(ctx):
