@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ResNMTF update loop on B200.
+
+Metric (BASELINE.json): update-iterations/s of the F/S/G multiplicative-update sweep, with the achieved
+HBM bandwidth against the measured peak.  Workload at one GPU = BASELINE.json configs[1]: a single view
+20000 x 4000 (FP64, 640 MB, larger than the 126 MB L2) fitted for every k of the sweep 3..8.  One "step" is
+one update-iteration (update_matrices sweep + error, R/main.r:56-80) of each of the six k-fits, so a step is
+6 update-iterations.  All six fits stay resident in HBM.
+
+  value      update-iterations/s with inputs already resident in HBM (device-timed, CUDA events on the
+             library's stream, max over ranks)
+  e2e        the same through the reference-facing call (one res_nmtf_inner-style fit per k through the C
+             ABI with HOST buffers: H2D of X and the initial factors, `steps` sweeps, D2H of the factors
+             and the error history), host-timed around the calls
+  roofline   the dominant kernel (X'.F stream + fused G/S update) against the measured HBM copy peak
+  cpu_baseline / --impl reference: the NumPy restatement of the reference's own operation sequence
+             (3 GEMM passes over X + materialised X_hat, oracle/resnmtf_oracle.py) on the host cores
+
+N > 1 (torchrun, one rank per GPU): the k-sweep / resample fits of the reference are independent, so every
+rank runs its own six fits on its own GPU with no data-path collective (weak scaling); value is the sum
+over ranks divided by the max time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, N_COLS = 20000, 4000
+K_SWEEP = (3, 4, 5, 6, 7, 8)
+METRIC = "resnmtf_update_iterations_per_second"
+UNIT = "update-iterations/s"
+WORKLOAD = "configs[1]: single view 20000x4000 FP64, k sweep 3..8 (one update-iteration of each k per step)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic workload (planted biclusters + |N(0,1)| noise, reference prep)
+# ----------------------------------------------------------------------------------------------------
+
+
+def make_workload(rank=0):
+    from resnmtf_b200 import synth
+
+    rng = np.random.default_rng(synth.config_seed(2, 0) + 1000 * rank)
+    x, _, _ = synth.planted_view(N_ROWS, N_COLS, 5, rng, row_prob=0.2, col_prob=0.2, height=5.0, sigma=1.0)
+    x = synth.prep(x)
+    inits = {k: synth.random_factors(N_ROWS, N_COLS, k, rng) for k in K_SWEEP}
+    return x, inits
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's reference-cost restatement, bounded sample
+# ----------------------------------------------------------------------------------------------------
+
+
+def cpu_reference_rate(x, inits, steps, warmup, budget_s=25.0):
+    """update-iterations/s of the NumPy/BLAS restatement on the host cores.  Each step = one sweep of each
+    k (like the GPU arm); stops early once `budget_s` of timed work has been done."""
+    from oracle import resnmtf_oracle as O
+
+    z = np.zeros((1, 1))
+    names_r, names_c = O.default_names([x])
+    ri, ci = O.shared_names(names_r), O.shared_names(names_c)
+    norms = np.array([np.linalg.norm(x, "fro") ** 2])
+    state = {}
+    for k in K_SWEEP:
+        f, s, g = inits[k]
+        state[k] = ([f.copy()], [s.copy()], [g.copy()], [f.sum(0)], [g.sum(0)])
+
+    def one_step():
+        for k in K_SWEEP:
+            cf, cs, cg, cl, cm = state[k]
+            cf, cs, cg, cl, cm = O.update_matrices([x], cf, cs, cg, cl, cm, z, z, z, ri, ci, names_r, names_c)
+            O.calculate_error([x], cf, cs, cg, norms)
+            state[k] = (cf, cs, cg, cl, cm)
+
+    for _ in range(min(warmup, 1)):
+        one_step()
+    done, t0 = 0, time.perf_counter()
+    while done < steps:
+        one_step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+
+        cores = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    return {
+        "value": done * len(K_SWEEP) / dt, "unit": UNIT, "cores": int(cores), "kind": "port",
+        "sample": f"{done} steps x {len(K_SWEEP)} k-fits of the full 20000x4000 view "
+                  f"(NumPy/OpenBLAS restatement of the R operation sequence incl. X_hat; not R)",
+        "seconds": dt, "steps": done,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if there is one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get("rn_g_step_sk_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from resnmtf_b200 import _lib as L
+    from resnmtf_b200.device import Context, DeviceFit
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L.require_device()
+
+    x, inits = make_workload(rank)
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).pin_memory()  # pinned; memory == column-major n x p
+    x_pinned = xt.numpy().T
+    ctx = Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident fits: one per k -------------------------------------------------------------------
+    fits = {}
+    for k in K_SWEEP:
+        fit = DeviceFit(ctx, [N_ROWS], [N_COLS], [k])
+        fit.set_options(err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO)
+        fit.set_data(0, x_pinned)
+        fit.set_factors(0, *inits[k])
+        fits[k] = fit
+
+    def do_steps(n):
+        launches = 0
+        for k in K_SWEEP:  # each fit advances n sweeps; the fits are independent, so the order is free
+            fits[k].run(n)
+            launches += fits[k].counters()["kernel_launches"]
+        return launches
+
+    do_steps(max(args.warmup, 3))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = do_steps(args.steps)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    iters_rank = args.steps * len(K_SWEEP)
+
+    # ---- roofline of the dominant kernel, measured live (CUDA events between launches) --------------
+    prof_iters = 20
+    bytes_f = bytes_g = ms_f = ms_g = 0.0
+    for k in K_SWEEP:
+        pr = fits[k].profile(prof_iters)
+        ms_f += pr["f_step"]["ms"]
+        ms_g += pr["g_stream"]["ms"]
+        bytes_f += prof_iters * 8.0 * (N_ROWS * N_COLS + 2 * N_ROWS * k + N_COLS * k)
+        bytes_g += prof_iters * 8.0 * (N_ROWS * N_COLS + N_ROWS * k + 2 * N_COLS * k)
+    peak, peak_src = measured_peak()
+    dom = ("rn_g_step_sk", bytes_g, ms_g) if ms_g >= ms_f else ("rn_f_step_sk", bytes_f, ms_f)
+    achieved = dom[1] / dom[2] * 1e-6
+    alg_bytes_step = sum(fits[k].counters()["alg_bytes_per_iter"] for k in K_SWEEP)
+    roofline = {
+        "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
+        "other_kernel": {"name": "rn_f_step_sk" if dom[0] == "rn_g_step_sk" else "rn_g_step_sk",
+                         "achieved": (bytes_f / ms_f if dom[0] == "rn_g_step_sk" else bytes_g / ms_g) * 1e-6},
+        "whole_step_achieved": alg_bytes_step * args.steps / ms * 1e-6,
+        "alg_bytes_per_step": alg_bytes_step,
+    }
+
+    # ---- e2e: reference-facing fit call per k with HOST buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, args.steps)
+        h2d = d2h = 0
+
+        def e2e_once():
+            nonlocal h2d, d2h
+            for k in K_SWEEP:
+                f0, s0, g0 = inits[k]
+                fit = DeviceFit(ctx, [N_ROWS], [N_COLS], [k])
+                fit.set_data(0, x_pinned)
+                fit.set_factors(0, f0, s0, g0)
+                fit.run(e2e_steps)
+                errs = fit.errors()
+                fit.normalise()
+                f, s, g, lam, mu = fit.get_factors(0)
+                fit.close()
+                h2d += x_pinned.nbytes + f0.nbytes + s0.nbytes + g0.nbytes
+                d2h += f.nbytes + s.nbytes + g.nbytes + lam.nbytes + mu.nbytes + errs.nbytes
+
+        e2e_once()  # warm-up
+        h2d = d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        e2e_once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * e2e_steps * len(K_SWEEP) / dt, "unit": UNIT,
+               "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
+               "call": f"one C-ABI fit per k: set_data(host X) + set_factors + run(n_iters={e2e_steps}) + "
+                       "normalise + get_factors/get_errors", "seconds": dt}
+
+    # ---- reduce over ranks -------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+    value = world * iters_rank / (ms * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_rate(x, inits, steps=3, warmup=1)
+
+    for f in fits.values():
+        f.close()
+    ctx.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows": N_ROWS, "cols": N_COLS, "k_sweep": list(K_SWEEP),
+                       "update_iterations_per_step": len(K_SWEEP), "fits_per_gpu": len(K_SWEEP),
+                       "l2": "inputs larger than L2 (640 MB per fit, 6 fits cycled; no flush needed)",
+                       "multi_gpu": "independent k-sweep fits per rank, no data-path collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu, "impl": "b200",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (R is absent from this image,
+    so this is the oracle's NumPy/BLAS restatement of the same operation sequence), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    x, inits = make_workload(0)
+    # bounded sample: each step is ~6 CPU sweeps of the full view; keep the whole run within minutes
+    steps = max(1, min(args.steps, 6))
+    warm = 1 if args.warmup > 0 else 0
+    res = cpu_reference_rate(x, inits, steps=steps, warmup=warm, budget_s=90.0)
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"],
+        "warmup": warm, "ms_per_step": 1e3 * res["seconds"] / max(res["steps"], 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": N_ROWS, "cols": N_COLS, "k_sweep": list(K_SWEEP),
+                   "update_iterations_per_step": len(K_SWEEP)},
+        "impl": "reference",
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

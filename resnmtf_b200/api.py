@@ -1,0 +1,224 @@
+"""``res_nmtf_inner`` and ``apply_resnmtf`` with the reference's exact signatures, argument meaning and
+return structure (R/main.r:32-140, 214-335), with the loop of R/main.r:50-109 replaced by one call into
+the device-resident C-ABI fit (include/resnmtf_b200.h).  This image has no R, so the host side above the C
+ABI is Python; an R package would keep its own R/main.r and call the same C entry points through .Call
+(INTEGRATION.md).
+
+Python-only additions are keyword-only: ``rng`` (a ``numpy.random.Generator`` standing in for R's global
+RNG stream), ``ctx`` (a ``resnmtf_b200.device.Context``; default: one shared context on the current GPU)
+and ``max_iters`` (a safety cap the reference's ``while`` does not have; 0 = none)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from . import prep
+from .bicluster import obtain_biclusters
+from .device import DeviceFit, default_context
+from .prep import NamedMatrix, as_named
+from .stability import stability_check
+
+
+# --------------------------------------------------------------------------------------------------
+# initialisation (R/update_steps.r:36-125) -- host side; the truncated-SVD-on-device row is "next" (N3)
+# --------------------------------------------------------------------------------------------------
+
+
+def _svd_topk(x, k):
+    """|U_k|, d_k, |V_k| of x.  The reference calls LAPACK's full svd(x) (R/update_steps.r:92); only the
+    top-k triplets are used and abs() removes the sign ambiguity.  Small views use the same full SVD; large
+    ones use the Gram matrix of the smaller side (top-k eigenpairs), which is what makes 20000 x 4000
+    tractable on the host."""
+    n, p = x.shape
+    if min(n, p) <= 1536:
+        u, d, vt = np.linalg.svd(x, full_matrices=False)
+        return np.abs(u[:, :k]), d[:k], np.abs(vt[:k, :].T)
+    from scipy.linalg import eigh
+
+    if p <= n:
+        gram = x.T @ x
+        w, v = eigh(gram, subset_by_index=[p - k, p - 1])
+        w, v = w[::-1], v[:, ::-1]
+        d = np.sqrt(np.maximum(w, 0.0))
+        u = (x @ v) / d[None, :]
+    else:
+        gram = x @ x.T
+        w, u = eigh(gram, subset_by_index=[n - k, n - 1])
+        w, u = w[::-1], u[:, ::-1]
+        d = np.sqrt(np.maximum(w, 0.0))
+        v = (x.T @ u) / d[None, :]
+    return np.abs(u), d, np.abs(v)
+
+
+def init_mats_inner(x, k_vec, rng, sigma=0.05):
+    """R/update_steps.r:78-125.  The noise term abs(MASS::mvrnorm(k, 0, sigma I_k)) is drawn from ``rng``."""
+    fs, ss, gs, lams, mus = [], [], [], [], []
+    for i, xi in enumerate(x):
+        k = int(k_vec[i])
+        f, d, g = _svd_topk(xi, k)
+        s = np.abs(np.diag(d)) + np.abs(np.sqrt(sigma) * rng.standard_normal((k, k)))
+        csf, csg = f.sum(axis=0), g.sum(axis=0)
+        s = s * (csf * csg)[None, :]
+        f = f / csf[None, :]
+        g = g / csg[None, :]
+        fs.append(f)
+        ss.append(s)
+        gs.append(g)
+        lams.append(f.sum(axis=0))
+        mus.append(g.sum(axis=0))
+    return fs, ss, gs, lams, mus
+
+
+def init_mats(x, n_v, k_vec, init_f, init_g, init_s, rng):
+    """R/update_steps.r:36-66."""
+    if init_f is None or init_g is None or init_s is None:
+        return init_mats_inner(x, k_vec, rng)
+    cf = [np.asarray(a, dtype=np.float64) for a in init_f]
+    cs = [np.asarray(a, dtype=np.float64) for a in init_s]
+    cg = [np.asarray(a, dtype=np.float64) for a in init_g]
+    return cf, cs, cg, [a.sum(axis=0) for a in cf], [a.sum(axis=0) for a in cg]
+
+
+# --------------------------------------------------------------------------------------------------
+# res_nmtf_inner
+# --------------------------------------------------------------------------------------------------
+
+
+def _names_or_default(data):
+    """Row / column names for the shared-index maps; unnamed views get view-unique placeholders."""
+    rn, cn = [], []
+    for v, m in enumerate(data):
+        rn.append(m.rownames if m.rownames is not None else [f"__v{v}_r{i}" for i in range(m.shape[0])])
+        cn.append(m.colnames if m.colnames is not None else [f"__v{v}_c{i}" for i in range(m.shape[1])])
+    return rn, cn
+
+
+def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, init_g=None, k_vec=None,
+                   phi=None, xi=None, psi=None, n_iters=None, num_repeats=5, spurious=True,
+                   distance="euclidean", no_clusts=False, *, rng=None, ctx=None, max_iters=0,
+                   err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO):
+    """R/main.r:32-140.  ``data``: list of (already prepped) views; ``row_indices`` / ``column_indices``:
+    per view a dict {other view: shared names or None}, as produced by ``prep.reorder_data``."""
+    rng = np.random.default_rng() if rng is None else rng
+    ctx = default_context() if ctx is None else ctx
+    data = [as_named(m) for m in data]
+    n_v = len(data)
+    xs = [np.asfortranarray(m.x, dtype=np.float64) for m in data]
+    phi = np.zeros((n_v, n_v)) if phi is None else np.asarray(phi, dtype=np.float64)
+    xi = np.zeros((n_v, n_v)) if xi is None else np.asarray(xi, dtype=np.float64)
+    psi = np.zeros((n_v, n_v)) if psi is None else np.asarray(psi, dtype=np.float64)
+    cf, cs, cg, clam, cmu = init_mats(xs, n_v, k_vec, init_f, init_g, init_s, rng)
+    k_used = [int(f.shape[1]) for f in cf]
+
+    fit = DeviceFit(ctx, [x.shape[0] for x in xs], [x.shape[1] for x in xs], k_used)
+    try:
+        fit.set_options(err_mode=err_mode, impl=impl)
+        for v in range(n_v):
+            fit.set_data(v, xs[v])  # data_norms (R/main.r:48) are computed on the device
+            fit.set_factors(v, cf[v], cs[v], cg[v], clam[v], cmu[v])
+        fit.set_restrictions(phi, xi, psi)
+        rn, cn = _names_or_default(data)
+        for (v, w), (iv, iw) in prep.shared_maps(row_indices, rn).items():
+            fit.set_shared_map(L.MAP_ROW, v, w, iv, iw)
+        for (v, w), (iv, iw) in prep.shared_maps(column_indices, cn).items():
+            fit.set_shared_map(L.MAP_COL, v, w, iv, iw)
+        fit.run(n_iters, 1.0e-6, max_iters)  # the loop of R/main.r:50-109
+        total_err = fit.errors()
+        lam_mu = [fit.get_factors(v)[3:] for v in range(n_v)]
+        fit.normalise()  # normalisation_check, R/main.r:110
+        outs = [fit.get_factors(v) for v in range(n_v)]
+        counters = fit.counters()
+    finally:
+        fit.close()
+    current_f = [o[0] for o in outs]
+    current_s = [o[1] for o in outs]
+    current_g = [o[2] for o in outs]
+    if no_clusts:
+        return {"output_f": current_f, "output_s": current_s, "output_g": current_g}
+    clusters = obtain_biclusters(data, current_f, current_g, current_s, num_repeats, spurious, distance,
+                                 rng=rng, ctx=ctx)
+    if n_iters is None:
+        error = float(np.mean(total_err[-10:]))
+    else:
+        error = float(total_err[-1])
+    return {
+        "output_f": current_f, "output_s": current_s, "output_g": current_g,
+        "Error": error, "All_Error": total_err, "bisil": clusters["bisil"],
+        "row_clusters": clusters["row_clustering"], "col_clusters": clusters["col_clustering"],
+        "lambda": [lm[0] for lm in lam_mu], "mu": [lm[1] for lm in lam_mu],
+        # not in the reference's list: names (R carries them as dimnames) and device counters
+        "row_names": [m.rownames for m in data], "col_names": [m.colnames for m in data],
+        "counters": counters,
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# apply_resnmtf
+# --------------------------------------------------------------------------------------------------
+
+
+def extract_bisils(res_list, k_vec):
+    """R/utils.r:203-210."""
+    return [res_list[i]["bisil"] for i in range(len(k_vec))]
+
+
+def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=None, xi=None, psi=None,
+                  n_iters=None, k_min=3, k_max=8, distance="euclidean", spurious=True, num_repeats=5,
+                  no_clusts=False, sample_rate=0.9, n_stability=5, stability=True, stab_thres=0.4,
+                  remove_unstable=True, use_parallel=True, *, rng=None, ctx=None, max_iters=0):
+    """R/main.r:214-335."""
+    rng = np.random.default_rng() if rng is None else rng
+    ctx = default_context() if ctx is None else ctx
+    if not isinstance(data, (list, tuple)):
+        # quirk Q1 of the reference (length(data) is taken before the matrix -> list wrap) is not
+        # reproduced: a bare matrix is treated as the single-view list the documentation promises
+        data = [data]
+    n_v = len(data)
+    k_vec = None if k_val is None else [int(np.atleast_1d(k_val)[0])] * n_v
+    phi = None if phi is None else np.asarray(phi, dtype=np.float64)
+    xi = None if xi is None else np.asarray(xi, dtype=np.float64)
+    psi = None if psi is None else np.asarray(psi, dtype=np.float64)
+    named = prep.give_names(data, n_v, phi, psi)
+    reordering = prep.reorder_data(named["data"], n_v, named["row_names"], named["col_names"])
+    phi = prep.init_rest_mats(phi, n_v)
+    psi = prep.init_rest_mats(psi, n_v)
+    xi = prep.init_rest_mats(xi, n_v)
+    data = prep.check_inputs(named["data"], init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_min, k_max,
+                             distance, num_repeats, no_clusts, sample_rate, n_stability, stability, stab_thres,
+                             remove_unstable, spurious)
+    common = dict(rng=rng, ctx=ctx, max_iters=max_iters)
+    if k_vec is not None:
+        results = res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f, init_s,
+                                 init_g, k_vec, phi, xi, psi, n_iters, num_repeats, spurious, distance,
+                                 no_clusts, **common)
+        if stability:
+            results = stability_check(data, results, k_vec, phi, xi, psi, n_iters, spurious, num_repeats,
+                                      no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng, ctx=ctx)
+        return results
+    ks = list(range(int(k_min), int(k_max) + 1))
+    res_list = []
+    for k in ks:  # the reference's %dopar% branch is unreachable (R/main.r:275-299): serial sweep
+        res_list.append(res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f,
+                                       init_s, init_g, [k] * n_v, phi, xi, psi, n_iters, num_repeats,
+                                       spurious, distance, no_clusts, **common))
+    err_list = extract_bisils(res_list, ks)
+    test = ks[int(np.argmax(err_list))]
+    max_k = int(k_max)
+    if k_min != k_max:
+        while test == max_k:
+            max_k += 1
+            ks.append(max_k)
+            # quirk Q3 (R/main.r:312): `reordering$column_indices` does not exist, so the extension fits run
+            # with column_indices = NULL -- nothing is overwritten in the psi coupling.  Reproduced.
+            res_list.append(res_nmtf_inner(data, reordering["row_indices"], None, init_f, init_s, init_g,
+                                           [max_k] * n_v, phi, xi, psi, n_iters, num_repeats, spurious,
+                                           distance, no_clusts, **common))
+            err_list.append(res_list[-1]["bisil"])
+            test = ks[int(np.argmax(err_list))]
+    best = int(np.argmax(err_list))
+    results = res_list[best]
+    if stability:
+        results = stability_check(data, results, ks[best], phi, xi, psi, n_iters, spurious, num_repeats,
+                                  no_clusts, distance, sample_rate, n_stability, stab_thres, remove_unstable,
+                                  rng=rng, ctx=ctx)
+    return results

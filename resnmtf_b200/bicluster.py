@@ -1,0 +1,239 @@
+"""Host post-processing of a fit, mirroring R/obtain_bicl.r (binarisation, S-based row/column pairing,
+spurious-bicluster removal through shuffled refits and JSD thresholds, bisilhouette aggregation).
+
+These run on n x k / p x k outputs, not on the hot path.  Two of the reference's
+dependencies are not in the reference tree and are restated here from their published definitions --
+**parity unpinned**: `bisilhouette::bisilhouette` (Remotes: eso28599/bisilhouette, no version pinned) and
+`philentropy::JSD` on `stats::density` estimates.  In the R drop-in the R host keeps calling the real
+packages on the (bit-identical) binary matrices, so this module only matters for the Python mirror."""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------------
+# stats::density (gaussian kernel, bw.nrd0, linear binning + FFT, as density.default does it)
+# --------------------------------------------------------------------------------------------------
+
+
+def bw_nrd0(x):
+    x = np.asarray(x, dtype=np.float64)
+    hi = np.std(x, ddof=1) if x.size > 1 else 0.0
+    q75, q25 = np.percentile(x, [75, 25])
+    lo = min(hi, (q75 - q25) / 1.34)
+    if not lo:
+        lo = hi or abs(x[0]) or 1.0
+    return 0.9 * lo * x.size ** (-0.2)
+
+
+def r_density(x, from_=None, to=None, n=512, cut=3.0):
+    """(x grid, density) like stats::density(x, from=, to=) with the default gaussian kernel."""
+    x = np.asarray(x, dtype=np.float64)
+    N = x.size
+    bw = bw_nrd0(x)
+    if from_ is None:
+        from_ = x.min() - cut * bw
+    if to is None:
+        to = x.max() + cut * bw
+    n_user = n
+    n = max(n, 512)
+    if n > 512:
+        n = 2 ** int(np.ceil(np.log2(n)))
+    lo, up = from_ - 4 * bw, to + 4 * bw
+    y = np.zeros(2 * n)
+    delta = (up - lo) / (n - 1)
+    xpos = (x - lo) / delta
+    ix = np.floor(xpos).astype(np.int64)
+    fx = xpos - ix
+    w = 1.0 / N
+    inside = (ix >= 0) & (ix <= n - 2)
+    np.add.at(y, ix[inside], w * (1 - fx[inside]))
+    np.add.at(y, ix[inside] + 1, w * fx[inside])
+    left = ix == -1
+    np.add.at(y, np.zeros(left.sum(), dtype=np.int64), w * fx[left])
+    right = ix == n - 1
+    np.add.at(y, ix[right], w * (1 - fx[right]))
+    kords = np.linspace(0, 2 * (up - lo), 2 * n)
+    kords[n + 1:2 * n] = -kords[n - 1:0:-1]
+    kords = np.exp(-0.5 * (kords / bw) ** 2) / (bw * np.sqrt(2 * np.pi))
+    conv = np.fft.ifft(np.fft.fft(y) * np.conj(np.fft.fft(kords))).real  # numpy's ifft divides by len
+    dens = np.maximum(0.0, conv[:n])
+    xords = np.linspace(lo, up, n)
+    xout = np.linspace(from_, to, n_user)
+    return xout, np.interp(xout, xords, dens)
+
+
+def jsd(p, q):
+    """philentropy::JSD(rbind(p, q), unit='log2', est.prob='empirical')."""
+    p = np.asarray(p, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    p = p / p.sum()
+    q = q / q.sum()
+    m = 0.5 * (p + q)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a = np.where(p > 0, p * np.log2(p / m), 0.0)
+        b = np.where(q > 0, q * np.log2(q / m), 0.0)
+    return 0.5 * a.sum() + 0.5 * b.sum()
+
+
+def jsd_calc(x1, x2):
+    """R/utils.r:95-106."""
+    max_val = max(np.max(x1), np.max(x2))
+    gx, d1 = r_density(x1, 0.0, max_val)
+    _, d2 = r_density(x2, 0.0, max_val)
+    d1 = np.where(gx > np.max(x1), 0.0, d1)
+    d2 = np.where(gx > np.max(x2), 0.0, d2)
+    return jsd(d1, d2)
+
+
+# --------------------------------------------------------------------------------------------------
+# bisilhouette (restated; parity unpinned)
+# --------------------------------------------------------------------------------------------------
+
+
+def _pairwise(a, b, method):
+    if method == "euclidean":
+        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * (a @ b.T)
+        return np.sqrt(np.maximum(d2, 0.0))
+    if method == "manhattan":
+        return np.abs(a[:, None, :] - b[None, :, :]).sum(-1)
+    if method == "cosine":
+        na = np.linalg.norm(a, axis=1)[:, None]
+        nb = np.linalg.norm(b, axis=1)[None, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            c = (a @ b.T) / (na * nb)
+        return 1.0 - np.nan_to_num(c)
+    raise ValueError("distance must be one of 'euclidean', 'manhattan' or 'cosine'.")
+
+
+def bisilhouette(data, row_clustering, col_clustering, method="euclidean"):
+    """Bisilhouette score of a biclustering (Orme et al.): for every non-empty bicluster (R_k, C_k) the
+    silhouette of the rows of R_k computed on the columns C_k only, against the other row clusters (or, when
+    there is no other non-empty cluster, against the rows outside R_k); the score is the mean over
+    biclusters of the mean row silhouette.  Returns dict(bisil=..., vals=[per-bicluster])."""
+    x = np.asarray(data, dtype=np.float64)
+    rc = np.asarray(row_clustering) > 0
+    cc = np.asarray(col_clustering) > 0
+    k = rc.shape[1]
+    live = [j for j in range(k) if rc[:, j].any() and cc[:, j].any()]
+    vals = []
+    for j in live:
+        rows = np.flatnonzero(rc[:, j])
+        sub = x[:, cc[:, j]]
+        d_in = _pairwise(sub[rows], sub[rows], method)
+        a = d_in.sum(1) / max(len(rows) - 1, 1) if len(rows) > 1 else np.zeros(len(rows))
+        others = []
+        for l in live:
+            if l == j:
+                continue
+            rl = np.flatnonzero(rc[:, l] & ~rc[:, j])
+            if rl.size:
+                others.append(rl)
+        if not others:
+            rest = np.flatnonzero(~rc[:, j])
+            if rest.size:
+                others.append(rest)
+        if not others:
+            vals.append(0.0)
+            continue
+        b = np.min(np.stack([_pairwise(sub[rows], sub[rl], method).mean(1) for rl in others]), axis=0)
+        den = np.maximum(a, b)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = np.where(den > 0, (b - a) / den, 0.0)
+        vals.append(float(s.mean()))
+    return {"bisil": float(np.mean(vals)) if vals else 0.0, "vals": vals}
+
+
+# --------------------------------------------------------------------------------------------------
+# R/obtain_bicl.r
+# --------------------------------------------------------------------------------------------------
+
+
+def shuffle_view(x_i, rng):
+    """R/obtain_bicl.r:11-22: permute all entries until no row / column is all zero."""
+    x = np.asarray(x_i, dtype=np.float64)
+    while True:
+        m = rng.permutation(x.ravel(order="F")).reshape(x.shape, order="F")
+        if not ((m.sum(0) == 0).any() or (m.sum(1) == 0).any()):
+            return m
+
+
+def obtain_shuffled_f(data, n_views, num_repeats, n_clusts, rng, ctx):
+    """R/obtain_bicl.r:31-42: refit on shuffled data through apply_resnmtf (k_val, no_clusts, no stability)."""
+    from .api import apply_resnmtf
+
+    f_mess = []
+    for _ in range(num_repeats):
+        messed = [shuffle_view(m.x if hasattr(m, "x") else m, rng) for m in data]
+        f_mess.append(apply_resnmtf(messed, k_val=n_clusts, no_clusts=True, stability=False, rng=rng, ctx=ctx)["output_f"])
+    return f_mess
+
+
+def calculate_f_shuffle_jsd(f_mess, i, j, num_repeats, n_clusts):
+    """R/obtain_bicl.r:55-68 (j is 0-based here)."""
+    scores = []
+    for k in range(n_clusts):
+        x1 = f_mess[j][i][:, k]
+        for l in range(j + 1, num_repeats):
+            for m in range(n_clusts):
+                scores.append(jsd_calc(x1, f_mess[l][i][:, m]))
+    return scores
+
+
+def get_thresholds(x, output_f, num_repeats, n_views, n_clusts, rng, ctx):
+    """R/obtain_bicl.r:80-102."""
+    f_mess = obtain_shuffled_f(x, n_views, num_repeats, n_clusts, rng, ctx)
+    avg_score, max_score, shuffled_f = [], [], []
+    for i in range(n_views):
+        scores, cols = [], []
+        for j in range(max(num_repeats - 1, 1)):
+            cols.append(f_mess[j][i])
+            scores += calculate_f_shuffle_jsd(f_mess, i, j, num_repeats, n_clusts)
+        cols.append(f_mess[num_repeats - 1][i])
+        shuffled_f.append(np.concatenate(cols, axis=1))
+        avg_score.append(float(np.mean(scores)))
+        gx, gy = r_density(np.asarray(scores))
+        max_score.append(float(gx[int(np.argmax(gy))]))
+    return {"avg_score": avg_score, "max_score": max_score, "shuffled_f": shuffled_f}
+
+
+def check_biclusters(data, output_f, num_repeats, rng, ctx):
+    """R/obtain_bicl.r:113-133."""
+    n_views = len(data)
+    n_clusts = output_f[0].shape[1]
+    scores = np.zeros((n_views, n_clusts))
+    th = get_thresholds(data, output_f, num_repeats, n_views, n_clusts, rng, ctx)
+    for i in range(n_views):
+        noise = th["shuffled_f"][i]
+        for k in range(n_clusts):
+            xk = output_f[i][:, k]
+            scores[i, k] = np.mean([jsd_calc(xk, noise[:, c]) for c in range(noise.shape[1])])
+    return {"score": scores, "avg_threshold": th["avg_score"], "max_threshold": th["max_score"]}
+
+
+def binarise(output_f, output_g):
+    """R/obtain_bicl.r:162-173: 1[F > 1/n], 1[G > 1/p] as 0/1 float matrices (bit-exact bar of north_star)."""
+    rows = [(f > (1.0 / f.shape[0])).astype(np.float64) for f in output_f]
+    cols = [(g > (1.0 / g.shape[0])).astype(np.float64) for g in output_g]
+    return rows, cols
+
+
+def obtain_biclusters(data, output_f, output_g, output_s, num_repeats, remove_spurious=True,
+                      distance="euclidean", rng=None, ctx=None):
+    """R/obtain_bicl.r:151-204."""
+    n_views = len(output_f)
+    biclusts = check_biclusters(data, output_f, num_repeats, rng, ctx) if remove_spurious else None
+    row_clustering, col_clustering = binarise(output_f, output_g)
+    bisil = []
+    for i in range(n_views):
+        relations = np.argmax(output_s[i], axis=0)  # which.max per column: first maximum
+        row_clustering[i] = row_clustering[i][:, relations]
+        if remove_spurious:
+            indices = (biclusts["score"][i] < biclusts["max_threshold"][i]) | (biclusts["score"][i] == 0)
+            new_indices = indices[relations]
+            row_clustering[i][:, new_indices] = 0.0
+            col_clustering[i][:, new_indices] = 0.0
+        xi = data[i].x if hasattr(data[i], "x") else data[i]
+        bisil.append(bisilhouette(xi, row_clustering[i], col_clustering[i], method=distance)["bisil"])
+    bisil = np.asarray(bisil)
+    overall = 0.0 if bisil.sum() == 0 else float(bisil[bisil != 0].mean())
+    return {"row_clustering": row_clustering, "col_clustering": col_clustering, "bisil": overall}

@@ -6,7 +6,7 @@ out="$here/../libresnmtf_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 -shared)
 if [[ "${RESNMTF_VERBOSE_PTXAS:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
-if [[ "${RESNMTF_WITH_NCCL:-1}" == "1" && -f /usr/include/nccl.h ]]; then
+if [[ "${RESNMTF_WITH_NCCL:-0}" == "1" && -f /usr/include/nccl.h ]]; then
   FLAGS+=(-DRESNMTF_WITH_NCCL -lnccl)
 fi
 "$NVCC" "${FLAGS[@]}" -o "$out" "$here/resnmtf_capi.cu"

@@ -1,0 +1,106 @@
+"""The reference's integration tests (tests/testthat/test-resnmtf.R:53-184) re-expressed against the
+Python mirror of apply_resnmtf / res_nmtf_inner running on the device."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import resnmtf_oracle as O
+from resnmtf_b200 import synth
+from resnmtf_b200.api import apply_resnmtf, res_nmtf_inner
+from resnmtf_b200.prep import NamedMatrix
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def block_data():
+    views, rc = synth.block_views(2, seed=21)
+    return views, rc
+
+
+def sizes_ok(results):
+    for v in range(2):
+        assert sorted(results["row_clusters"][v].sum(0)) == [60, 60, 60]
+        assert sorted(results["col_clusters"][v].sum(0)) == [60, 60, 60]
+
+
+def test_negative_matrix_warns(ctx, block_data):
+    """test-resnmtf.R:53-58."""
+    with pytest.warns(UserWarning, match="Matrix is not non-negative. Has been made non-negative."):
+        apply_resnmtf([-block_data[0][0]], k_max=4, spurious=False, stability=False,
+                      rng=np.random.default_rng(0), ctx=ctx)
+
+
+def test_fixed_k_no_stability_no_spurious(ctx, block_data):
+    """test-resnmtf.R:98-118."""
+    res = apply_resnmtf(block_data[0], k_val=3, spurious=False, stability=False,
+                        rng=np.random.default_rng(1), ctx=ctx)
+    np.testing.assert_allclose(res["output_f"][0].sum(0), np.ones(3), atol=1e-12)
+    np.testing.assert_allclose(res["output_g"][0].sum(0), np.ones(3), atol=1e-12)
+    recon = res["output_f"][0] @ res["output_s"][0] @ res["output_g"][0].T
+    assert np.mean(recon.sum(0) - 1.0) < 1e-3
+    assert len(res["output_f"]) == 2 and res["output_f"][0].shape == (180, 3)
+    sizes_ok(res)
+    assert set(res) >= {"output_f", "output_s", "output_g", "Error", "All_Error", "bisil", "row_clusters",
+                        "col_clusters", "lambda", "mu"}
+
+
+def test_fixed_k_with_spurious_removal(ctx, block_data):
+    """test-resnmtf.R:63-72."""
+    res = apply_resnmtf(block_data[0], k_val=3, stability=False, rng=np.random.default_rng(2), ctx=ctx)
+    sizes_ok(res)
+
+
+def test_fixed_k_with_stability_no_spurious(ctx, block_data):
+    """test-resnmtf.R:86-96."""
+    res = apply_resnmtf(block_data[0], k_val=3, spurious=False, rng=np.random.default_rng(3), ctx=ctx)
+    sizes_ok(res)
+
+
+def test_k_sweep_selects_three(ctx, block_data):
+    """test-resnmtf.R:123-135: the only test that pins the bisilhouette-selected k."""
+    res = apply_resnmtf(block_data[0], k_max=5, spurious=False, stability=False,
+                        rng=np.random.default_rng(4), ctx=ctx)
+    assert res["output_f"][0].shape == (180, 3)
+    sizes_ok(res)
+
+
+def test_restrictions_partial_overlap(ctx, block_data):
+    """test-resnmtf.R:140-184."""
+    rn = [[f"row_{i}" for i in range(1, 181)],
+          [f"row_{i}" for i in range(1, 121)] + [f"row_{i}" for i in range(181, 241)]]
+    cn = [[f"col_{i}" for i in range(1, 181)],
+          [f"col_{i}" for i in range(1, 121)] + [f"col_{i}" for i in range(181, 241)]]
+    data = [NamedMatrix(x, rn[v], cn[v]) for v, x in enumerate(block_data[0])]
+    rest = np.zeros((2, 2))
+    rest[0, 1] = 1000.0
+    res = apply_resnmtf(data, k_val=3, phi=rest, psi=rest, spurious=False, stability=False,
+                        rng=np.random.default_rng(5), ctx=ctx)
+    f, g = res["output_f"], res["output_g"]
+    assert np.mean(np.abs(f[0][120:180] - f[1][120:180])) > np.mean(np.abs(f[0][:120] - f[1][:120]))
+    assert np.mean(np.abs(g[0][120:180] - g[1][120:180])) > np.mean(np.abs(g[0][:120] - g[1][:120]))
+    sizes_ok(res)
+
+
+def test_res_nmtf_inner_matches_oracle_end_to_end(ctx, block_data):
+    """Explicit inits through res_nmtf_inner (the route the reference supports, R/update_steps.r:49-60):
+    identical binary bicluster matrices and All_Error within 1e-9."""
+    data = [synth.prep(x) for x in block_data[0]]
+    rng = np.random.default_rng(6)
+    k = 3
+    noise = [np.abs(np.sqrt(0.05) * rng.standard_normal((k, k))) for _ in range(2)]
+    f0, s0, g0, _, _ = O.init_mats_inner(data, [k, k], noise)
+    rn, cn = O.default_names(data)
+    ri, ci = O.shared_names(rn), O.shared_names(cn)
+    z = np.zeros((2, 2))
+    ref = O.res_nmtf_loop(data, ri, ci, rn, cn, f0, s0, g0, [k, k], z, z, z)
+    named = [NamedMatrix(x, rn[v], cn[v]) for v, x in enumerate(data)]
+    res = res_nmtf_inner(named, ri, ci, f0, s0, g0, [k, k], z, z, z, spurious=False, ctx=ctx)
+    assert len(res["All_Error"]) == len(ref["All_Error"])
+    np.testing.assert_allclose(res["All_Error"], ref["All_Error"], rtol=1e-9)
+    rows_o, cols_o, _ = O.binarise(ref["output_f"], ref["output_g"], ref["output_s"])
+    for v in range(2):
+        assert np.array_equal(res["row_clusters"][v], rows_o[v])
+        assert np.array_equal(res["col_clusters"][v], cols_o[v])
+    assert np.isclose(res["Error"], ref["Error"], rtol=1e-9)
