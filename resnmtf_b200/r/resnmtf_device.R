@@ -1,0 +1,48 @@
+# R side of the drop-in (not run in this repository's image: no R here).
+# In the reference package this replaces lines 50-109 of R/main.r inside res_nmtf_inner(); every other line
+# of R/main.r, R/utils.r, R/obtain_bicl.r and R/stability_analysis.r stays as it is.  NAMESPACE gains
+#   useDynLib(resnmtf, .registration = TRUE)
+# and DESCRIPTION gains  SystemRequirements: CUDA (sm_100a), libresnmtf_b200.
+
+# shared names (the hash objects of produce_indices, R/utils.r:560-601) -> 1-based index pairs
+resnmtf_index_maps <- function(indices, names_list) {
+  if (is.null(indices)) {
+    return(NULL) # the k-extension loop's column_indices = NULL (R/main.r:312)
+  }
+  n_v <- length(names_list)
+  lapply(seq_len(n_v), function(v) {
+    lapply(seq_len(n_v), function(w) {
+      if (w == v) {
+        return(NULL)
+      }
+      shared <- indices[[v]][[as.character(w)]]
+      if (is.null(shared)) {
+        return(NULL)
+      }
+      if (any(is.na(shared))) {
+        return(integer(0)) # NA: the pair shares nothing (skipped, R/utils.r:70)
+      }
+      rbind(match(shared, names_list[[v]]), match(shared, names_list[[w]]))
+    })
+  })
+}
+
+# body of res_nmtf_inner() between init_mats() and obtain_biclusters()
+resnmtf_device_loop <- function(data, current_f, current_s, current_g, current_lam, current_mu,
+                                phi, xi, psi, row_indices, column_indices, n_iters) {
+  row_maps <- resnmtf_index_maps(row_indices, lapply(data, rownames))
+  col_maps <- resnmtf_index_maps(column_indices, lapply(data, colnames))
+  out <- .Call(
+    C_resnmtf_fit, data, current_f, current_s, current_g, current_lam, current_mu,
+    phi, xi, psi, row_maps, col_maps,
+    if (is.null(n_iters)) NA_integer_ else as.integer(n_iters)
+  )
+  for (v in seq_along(data)) { # dimnames the reference carries (R/update_steps.r:61-64)
+    rownames(out$Fn[[v]]) <- rownames(data[[v]])
+    rownames(out$Gn[[v]]) <- colnames(data[[v]])
+  }
+  list(
+    current_f = out$Fn, current_s = out$Sn, current_g = out$Gn, # after normalisation_check()
+    current_lam = out$lam, current_mu = out$mu, total_err = out$total_err
+  )
+}
