@@ -12,7 +12,8 @@ one update-iteration (update_matrices sweep + error, R/main.r:56-80) of each of 
   e2e        the same through the reference-facing call (one res_nmtf_inner-style fit per k through the C
              ABI with HOST buffers: H2D of X and the initial factors, `steps` sweeps, D2H of the factors
              and the error history), host-timed around the calls
-  roofline   the dominant kernel (X'.F stream + fused G/S update) against the measured HBM copy peak
+  roofline   the dominant kernel (rn_g_step_tma: X'.F stream + fused G/S update) against the measured HBM copy
+             peak
   cpu_baseline / --impl reference: the NumPy restatement of the reference's own operation sequence
              (3 GEMM passes over X + materialised X_hat, oracle/resnmtf_oracle.py) on the host cores
 
@@ -187,7 +188,7 @@ def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if there is one."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get("rn_g_step_sk_dram_bytes_per_launch")
+            return json.load(fh).get("rn_g_step_tma_dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -260,14 +261,14 @@ def run_gpu(args):
         bytes_f += prof_iters * 8.0 * (N_ROWS * N_COLS + 2 * N_ROWS * k + N_COLS * k)
         bytes_g += prof_iters * 8.0 * (N_ROWS * N_COLS + N_ROWS * k + 2 * N_COLS * k)
     peak, peak_src = measured_peak()
-    dom = ("rn_g_step_sk", bytes_g, ms_g) if ms_g >= ms_f else ("rn_f_step_sk", bytes_f, ms_f)
+    dom = ("rn_g_step_tma", bytes_g, ms_g) if ms_g >= ms_f else ("rn_f_step_tma", bytes_f, ms_f)
     achieved = dom[1] / dom[2] * 1e-6
     alg_bytes_step = sum(fits[k].counters()["alg_bytes_per_iter"] for k in K_SWEEP)
     roofline = {
         "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
-        "other_kernel": {"name": "rn_f_step_sk" if dom[0] == "rn_g_step_sk" else "rn_g_step_sk",
-                         "achieved": (bytes_f / ms_f if dom[0] == "rn_g_step_sk" else bytes_g / ms_g) * 1e-6},
+        "other_kernel": {"name": "rn_f_step_tma" if dom[0] == "rn_g_step_tma" else "rn_g_step_tma",
+                         "achieved": (bytes_f / ms_f if dom[0] == "rn_g_step_tma" else bytes_g / ms_g) * 1e-6},
         "whole_step_achieved": alg_bytes_step * args.steps / ms * 1e-6,
         "alg_bytes_per_step": alg_bytes_step,
     }

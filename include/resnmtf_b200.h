@@ -52,7 +52,8 @@ extern "C" {
 /* streaming-kernel implementation of the two tall-skinny products */
 #define RESNMTF_IMPL_AUTO 0
 #define RESNMTF_IMPL_DFMA 1 /* CUDA-core FP64 FMA                                    */
-#define RESNMTF_IMPL_DMMA 2 /* FP64 tensor-core mma.sync m8n8k4, k padded to 8 or 16 */
+#define RESNMTF_IMPL_DMMA 2 /* FP64 tensor-core mma.sync m8n8k4 (k <= 8), X loaded straight into fragments */
+#define RESNMTF_IMPL_TMA 3  /* same MMAs, X staged through a shared-memory ring by TMA bulk copies       */
 
 typedef struct resnmtf_ctx resnmtf_ctx;
 typedef struct resnmtf_fit resnmtf_fit;

@@ -83,7 +83,7 @@ struct resnmtf_fit {
   std::vector<double> errors;  // All_Error
   int err_mode = RESNMTF_ERR_AUTO;
   int impl_req = RESNMTF_IMPL_AUTO;
-  int impl = RESNMTF_IMPL_DMMA;
+  int impl = RESNMTF_IMPL_TMA;
   bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
   bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
   bool auto_direct = false; // AUTO error mode has handed over to the direct residual pass
@@ -115,6 +115,12 @@ static int rn_free(resnmtf_fit* f, void* p) {
 
 static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// host twin of rn_fidx (rn_kernels.cuh): position of F[r, c] in the swizzled 64-row panel layout
+static inline int64_t rn_fidx_host(int64_t r, int c, int kp) {
+  const int sigma = ((c & 1) << 2) | (c & 2);
+  return ((r >> 6) * kp + c) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ sigma) + (r & 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch on k
 // ------------------------------------------------------------------------------------------------
@@ -141,12 +147,34 @@ static GStepSkFn g_step_sk_fn(int K) {
   return nullptr;
 }
 
-static inline bool use_mma(const ViewHost& vh, int impl) { return impl == RESNMTF_IMPL_DMMA && vh.d.k <= 8; }
+static FStepSkFn f_step_tma_fn(int K) {
+  switch (K) {
+#define X(KC) case KC: return rn_f_step_tma<KC>;
+    RN_K_CASES_LE8(X)
+#undef X
+  }
+  return nullptr;
+}
+static GStepSkFn g_step_tma_fn(int K) {
+  switch (K) {
+#define X(KC) case KC: return rn_g_step_tma<KC>;
+    RN_K_CASES_LE8(X)
+#undef X
+  }
+  return nullptr;
+}
+
+static inline bool use_mma(const ViewHost& vh, int impl) {
+  return (impl == RESNMTF_IMPL_DMMA || impl == RESNMTF_IMPL_TMA) && vh.d.k <= 8;
+}
 
 static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, cudaStream_t st) {
   const int K = vh.d.k;
   if (use_mma(vh, impl)) {
-    f_step_sk_fn(K)<<<vh.d.f_ctas, 256, 0, st>>>(vh.d, ft, v);
+    if (impl == RESNMTF_IMPL_TMA)
+      f_step_tma_fn(K)<<<vh.d.f_ctas, RN_TMA_THREADS, rn_f_tma_smem(K), st>>>(vh.d, ft, v);
+    else
+      f_step_sk_fn(K)<<<vh.d.f_ctas, 256, 0, st>>>(vh.d, ft, v);
     return;
   }
   dim3 grid(vh.d.row_tiles, vh.d.cs);
@@ -176,7 +204,10 @@ static void launch_g_epilogue(const ViewHost& vh, const RnFit& ft, int v, int fu
 static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, int fuse, cudaStream_t st) {
   const int K = vh.d.k;
   if (use_mma(vh, impl)) {
-    g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, fuse);
+    if (impl == RESNMTF_IMPL_TMA)
+      g_step_tma_fn(K)<<<vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st>>>(vh.d, ft, v, fuse);
+    else
+      g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, fuse);
     return 1;
   }
   dim3 grid(vh.d.col_groups, vh.d.rs);
@@ -425,9 +456,10 @@ extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f,
   cudaStream_t st = fit->ctx->stream;
   const int K = vh.d.k, KP = vh.d.kp;
   const int64_t n = vh.d.n, p = vh.d.p;
-  RN_CUDA(cudaMemsetAsync(vh.d.F, 0, (size_t)vh.d.ldx * KP * sizeof(double), st));
-  RN_CUDA(cudaMemcpy2DAsync(vh.d.F, (size_t)vh.d.ldx * sizeof(double), f, (size_t)n * sizeof(double),
-                            (size_t)n * sizeof(double), (size_t)K, cudaMemcpyHostToDevice, st));
+  std::vector<double> fp((size_t)vh.d.ldx * KP, 0.0);  // F in the device's swizzled 64-row panel layout
+  for (int c = 0; c < K; ++c)
+    for (int64_t r = 0; r < n; ++r) fp[(size_t)rn_fidx_host(r, c, KP)] = f[(size_t)c * n + r];
+  RN_CUDA(cudaMemcpyAsync(vh.d.F, fp.data(), fp.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   std::vector<double> gt((size_t)vh.d.pp * KP, 0.0);  // G is row-major [pp][kp] on the device
   for (int c = 0; c < K; ++c)
     for (int64_t j = 0; j < p; ++j) gt[(size_t)j * KP + c] = g[(size_t)c * p + j];
@@ -522,7 +554,7 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
 
 extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl) {
   RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_options: fit is NULL");
-  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 2, RESNMTF_E_INVALID,
+  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 3, RESNMTF_E_INVALID,
            "resnmtf_fit_set_options: unknown option value");
   if (fit->err_mode != err_mode) {
     fit->meta_dirty = true;
@@ -545,8 +577,8 @@ static int rn_env_int(const char* name, int dflt) {
 static int build_plan(resnmtf_fit* fit) {
   const int sms = fit->ctx->sm_count;
   int impl = fit->impl_req;
-  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_DMMA);
-  if (impl != RESNMTF_IMPL_DFMA && impl != RESNMTF_IMPL_DMMA) impl = RESNMTF_IMPL_DMMA;
+  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_TMA);
+  if (impl != RESNMTF_IMPL_DFMA && impl != RESNMTF_IMPL_DMMA && impl != RESNMTF_IMPL_TMA) impl = RESNMTF_IMPL_TMA;
   fit->impl = impl;
   const int f_target = sms * rn_env_int("RESNMTF_F_CTAS_PER_SM", 2);
   const int g_target_dfma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM_DFMA", 3);
@@ -560,8 +592,20 @@ static int build_plan(resnmtf_fit* fit) {
     if (mma) {
       // persistent stream-K grids: exactly the CTAs that are resident at once (never more than units)
       int occ_f = 1, occ_g = 1;
-      RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, f_step_sk_fn(K), 256, 0));
-      RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, g_step_sk_fn(K), 128, 0));
+      if (impl == RESNMTF_IMPL_TMA) {  // one CTA per SM: the shared-memory ring takes ~200 KB
+        RN_CUDA(cudaFuncSetAttribute(f_step_tma_fn(K), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)rn_f_tma_smem(K)));
+        RN_CUDA(cudaFuncSetAttribute(g_step_tma_fn(K), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)rn_g_tma_smem(K)));
+        RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, f_step_tma_fn(K), RN_TMA_THREADS,
+                                                              rn_f_tma_smem(K)));
+        RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, g_step_tma_fn(K), RN_TMA_THREADS,
+                                                              rn_g_tma_smem(K)));
+        RN_CHECK(occ_f >= 1 && occ_g >= 1, RESNMTF_E_CUDA, "TMA kernels do not fit on this device");
+      } else {
+        RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, f_step_sk_fn(K), 256, 0));
+        RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, g_step_sk_fn(K), 128, 0));
+      }
       occ_f = std::max(1, rn_env_int("RESNMTF_F_OCC", occ_f));
       occ_g = std::max(1, rn_env_int("RESNMTF_G_OCC", occ_g));
       d.col_groups = (int)((d.pp + RN_COL_GROUP - 1) / RN_COL_GROUP);
@@ -930,10 +974,11 @@ extern "C" int resnmtf_fit_get_factors(resnmtf_fit* fit, int v, double* f, doubl
   cudaStream_t st = fit->ctx->stream;
   const int K = vh.d.k, KP = vh.d.kp;
   const int64_t n = vh.d.n, p = vh.d.p;
-  std::vector<double> gt;
-  if (f)
-    RN_CUDA(cudaMemcpy2DAsync(f, (size_t)n * sizeof(double), vh.d.F, (size_t)vh.d.ldx * sizeof(double),
-                              (size_t)n * sizeof(double), (size_t)K, cudaMemcpyDeviceToHost, st));
+  std::vector<double> gt, fp;
+  if (f) {
+    fp.resize((size_t)vh.d.ldx * KP);
+    RN_CUDA(cudaMemcpyAsync(fp.data(), vh.d.F, fp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
   if (g) {
     gt.resize((size_t)vh.d.pp * KP);
     RN_CUDA(cudaMemcpyAsync(gt.data(), vh.d.G, gt.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -942,6 +987,9 @@ extern "C" int resnmtf_fit_get_factors(resnmtf_fit* fit, int v, double* f, doubl
   if (lambda) RN_CUDA(cudaMemcpyAsync(lambda, vh.d.lam, K * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (mu) RN_CUDA(cudaMemcpyAsync(mu, vh.d.mu, K * sizeof(double), cudaMemcpyDeviceToHost, st));
   RN_CUDA(cudaStreamSynchronize(st));
+  if (f)
+    for (int c = 0; c < K; ++c)
+      for (int64_t r = 0; r < n; ++r) f[(size_t)c * n + r] = fp[(size_t)rn_fidx_host(r, c, KP)];
   if (g)
     for (int c = 0; c < K; ++c)
       for (int64_t j = 0; j < p; ++j) g[(size_t)c * p + j] = gt[(size_t)j * KP + c];

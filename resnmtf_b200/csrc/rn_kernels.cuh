@@ -43,10 +43,39 @@ __device__ __forceinline__ void rn_dmma(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
+// In-column swizzle of the X layout: inside a panel, the 16-byte piece (row pair) rp of data column c is
+// stored at piece position rp ^ rn_sigma(c).  With it the MMA fragment reads of BOTH passes hit 8 distinct
+// 16 B bank groups per quarter-warp when a unit is copied verbatim into shared memory (TMA path), and
+// global accesses stay permutations inside 128 B lines.
+__device__ __forceinline__ int rn_sigma(int64_t c) { return (int)(((c & 1) << 2) | (c & 2)); }
+
+// F is stored in 64-row panels like X (F[tile][c][64], pieces swizzled by rn_sigma(c)), so that the 64 rows
+// of F a row step needs are one contiguous kp*512 B run (one TMA copy) with conflict-free fragment reads.
+__device__ __forceinline__ int64_t rn_fidx(int64_t r, int c, int kp) {
+  return ((r >> 6) * kp + c) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ rn_sigma(c)) + (r & 1);
+}
+
 __device__ __forceinline__ double rn_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// sum of p[0], p[stride], ..., p[(n-1)*stride] with 8 interleaved partial sums: the loads of a batch are
+// independent (pipelined L2 reads instead of a serial chain) and the summation order is fixed.
+__device__ __forceinline__ double rn_sum_strided(const double* p, int64_t stride, int64_t n) {
+  double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldcg(p + (i + q) * stride);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] += v[q];
+  }
+  double tail = 0.0;
+  for (; i < n; ++i) tail += __ldcg(p + i * stride);
+  return (((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]))) + tail;
 }
 
 __device__ __forceinline__ int rn_ld_acquire(const int* p) {
@@ -77,11 +106,11 @@ template <int K>
 __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& ft, const int v, const int64_t r,
                                                 const double* P, const double* Ssm, const double* Wsm,
                                                 const double* lamh) {
-  const int64_t ldx = vw.ldx;
+  const int kp = vw.kp;
   const int V = ft.n_views;
   double f[K], N[K], FS[K], D[K];
 #pragma unroll
-  for (int c = 0; c < K; ++c) f[c] = vw.F[(int64_t)c * ldx + r];
+  for (int c = 0; c < K; ++c) f[c] = vw.F[rn_fidx(r, c, kp)];
 #pragma unroll
   for (int c = 0; c < K; ++c) {  // (X G) t(S)
     double s = 0.0;
@@ -110,7 +139,7 @@ __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& f
     for (int c = 0; c < K; ++c) {
       double ratio = N[c] / (D[c] + lamh[c]);
       if (isnan(ratio)) ratio = 1.0;
-      vw.F[(int64_t)c * ldx + r] = fabs(f[c] * ratio);
+      vw.F[rn_fidx(r, c, kp)] = fabs(f[c] * ratio);
     }
   } else {
     double pc[K];
@@ -126,10 +155,10 @@ __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& f
       int64_t src = -1;
       if (mode == RN_MODE_MAP) src = ft.rowmap[w + v * V][r];
       const double* fw = ow->F;
-      const int64_t ldw = ow->ldx;
+      const int kpw = ow->kp;
 #pragma unroll
       for (int c = 0; c < K; ++c) {
-        const double m = (src >= 0) ? fw[(int64_t)c * ldw + src] : f[c];
+        const double m = (src >= 0) ? fw[rn_fidx(src, c, kpw)] : f[c];
         pc[c] += (ph * m) * nw;
       }
     }
@@ -138,7 +167,7 @@ __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& f
     for (int c = 0; c < K; ++c) {
       const double num = N[c] + pc[c] / nv;
       const double den = (D[c] + phisum * f[c]) + lamh[c];
-      vw.F[(int64_t)c * ldx + r] = fabs(f[c] * (num / den));
+      vw.F[rn_fidx(r, c, kp)] = fabs(f[c] * (num / den));
     }
   }
 }
@@ -238,7 +267,7 @@ __device__ __forceinline__ void rn_finish_dev(const RnFit& ft) {
 // Finishes view v once G'G | A | colSums(G) (fin[0..2K^2+K)) and F'F | colSums(F) (FtFs) are complete:
 // update_s (R/update_steps.r:220-240), update_lm (:249-251), algebraic error, and -- when fuse_finish --
 // the iteration bookkeeping.  Called by all NT threads of the last CTA.  Us / Sn / red: K*K scratch.
-template <int K, int NT>
+template <int K, int NT, bool CONSUMER_BAR = false>
 __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft, const int v, const int tid,
                                                const double* fin, const double* FtFs, const double* Ssm,
                                                double* Us, double* Sn, double* red, const int fuse_finish) {
@@ -262,7 +291,8 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
     Us[a + c * K] = s;
   }
-  __syncthreads();
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
   for (int o = tid; o < KK; o += NT) {  // update_s
     const int a = o % K, b = o / K;
     double D = 0.0;
@@ -285,7 +315,8 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     }
     Sn[o] = out;
   }
-  __syncthreads();
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
   for (int o = tid; o < KK; o += NT) vw.S[o] = Sn[o];
   if (tid < K) {  // update_lm
     vw.lam[tid] = FtFs[KK + tid] * vw.lam[tid];
@@ -298,14 +329,16 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Sn[b + c * K], s);
     Us[a + c * K] = s;
   }
-  __syncthreads();
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
   for (int o = tid; o < KK; o += NT) {
     const int a = o % K, b = o / K;
     double q = 0.0;
     for (int c = 0; c < K; ++c) q = fma(Us[a + c * K], GtGn[c + b * K], q);
     red[o] = (q - 2.0 * An[o]) * Sn[o];
   }
-  __syncthreads();
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
   if (tid == 0) {
     double s = 0.0;
     for (int i = 0; i < KK; ++i) s += red[i];
@@ -370,8 +403,11 @@ __global__ void __launch_bounds__(256, 2) rn_f_step_sk(const RnView vw, const Rn
     for (int m = 0; m < 4; ++m)
 #pragma unroll
       for (int h = 0; h < 2; ++h) acc[m][h][0] = acc[m][h][1] = 0.0;
-    const double* xt = vw.X + (tile * pp + 4 * warp + t) * RN_ROW_TILE + 2 * g;
+    const double* xt = vw.X + (tile * pp + 4 * warp + t) * RN_ROW_TILE;
     const double* gt = G + (4 * warp + t) * KP + g;
+    int xo[4];  // swizzled piece offsets of rows 16m + 2g + {0,1} in data column 4w + t (mod 4 == t)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) xo[m] = 2 * ((8 * m + g) ^ rn_sigma(t));
     int64_t cb = cb0;
     for (; cb + 3 < cb1; cb += 4) {
       double2 x[4][4];
@@ -380,7 +416,7 @@ __global__ void __launch_bounds__(256, 2) rn_f_step_sk(const RnView vw, const Rn
       for (int q = 0; q < 4; ++q) {
         const double* xp = xt + (cb + q) * (32 * RN_ROW_TILE);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) x[q][m] = rn_ld_stream2(xp + 16 * m);
+        for (int m = 0; m < 4; ++m) x[q][m] = rn_ld_stream2(xp + xo[m]);
         b[q] = gt[(cb + q) * (32 * KP)];
       }
 #pragma unroll
@@ -395,7 +431,7 @@ __global__ void __launch_bounds__(256, 2) rn_f_step_sk(const RnView vw, const Rn
       const double* xp = xt + cb * (32 * RN_ROW_TILE);
       double2 x[4];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) x[m] = rn_ld_stream2(xp + 16 * m);
+      for (int m = 0; m < 4; ++m) x[m] = rn_ld_stream2(xp + xo[m]);
       const double b = gt[cb * (32 * KP)];
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -477,7 +513,7 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
   __shared__ double fin[NOUT], Us[KK], Sn[KK], red[KK];
   __shared__ int s_flag;
 
-  const int64_t pp = vw.pp, ldx = vw.ldx;
+  const int64_t pp = vw.pp;
   const int64_t NS = vw.row_tiles, NG = vw.col_groups;
   const int64_t U = NS * NG;
   const int64_t C = gridDim.x, cta = blockIdx.x;
@@ -505,14 +541,17 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
     for (int jb = 0; jb < 8; ++jb) acc[jb][0] = acc[jb][1] = 0.0;
     double aff0 = 0.0, aff1 = 0.0, acs0 = 0.0, acs1 = 0.0;
 
+    int xo[8];  // swizzled piece offsets of rows 8i + 2t + {0,1} in data column j0 + 8jb + g (mod 4 == g mod 4)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xo[i] = 2 * ((4 * i + t) ^ rn_sigma(g));
     for (int64_t s = s0 + warp; s < s1; s += 4) {
-      const double* fp = F + (int64_t)g * ldx + s * RN_ROW_TILE + 2 * t;
-      const double* xp = vw.X + (s * pp + j0 + g) * RN_ROW_TILE + 2 * t;
+      const double* fp = F + (s * KP + g) * RN_ROW_TILE;
+      const double* xp = vw.X + (s * pp + j0 + g) * RN_ROW_TILE;
       double2 f2[8], xa[8], xb[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xp + 8 * i);
+      for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xp + xo[i]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f2[i] = *reinterpret_cast<const double2*>(fp + 8 * i);
+      for (int i = 0; i < 8; ++i) f2[i] = *reinterpret_cast<const double2*>(fp + xo[i]);
       if (doFF) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -527,7 +566,7 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
         if (jb + 1 < njb) {
           const double* xq = xp + (8 * (jb + 1)) * RN_ROW_TILE;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xb[i] = rn_ld_stream2(xq + 8 * i);
+          for (int i = 0; i < 8; ++i) xb[i] = rn_ld_stream2(xq + xo[i]);
         }
         if (jb < njb) {
 #pragma unroll
@@ -539,7 +578,7 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
         if (jb + 2 < njb) {
           const double* xq = xp + (8 * (jb + 2)) * RN_ROW_TILE;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xq + 8 * i);
+          for (int i = 0; i < 8; ++i) xa[i] = rn_ld_stream2(xq + xo[i]);
         }
         if (jb + 1 < njb) {
 #pragma unroll
@@ -662,17 +701,468 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
     if (!s_flag) continue;
     __threadfence();
     // ---- last column group done: finish the view --------------------------------------------------
-    for (int o = tid; o < NOUT; o += 128) {
-      double s = 0.0;
-      for (int64_t i = 0; i < NG; ++i) s += __ldcg(vw.GGpart + i * NOUT + o);
-      fin[o] = s;
-    }
+    for (int o = tid; o < NOUT; o += 128) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, NG);
     if (tid == 0) {
       vw.misc_ticket[0] = 0;
       vw.misc_ticket[2] = 0;
     }
     __syncthreads();
     rn_view_finish<K, 128>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA pipeline primitives (sm_90+): mbarrier + 1-D bulk async copy global -> shared.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void rn_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rn_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rn_mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rn_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rn_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void rn_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rn_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void rn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RN_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RN_DONE_%=;\n"
+      "bra RN_WAIT_%=;\n"
+      "RN_DONE_%=:\n"
+      "}\n" ::"r"(rn_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one contiguous run global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void rn_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   rn_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(rn_smem_u32(bar))
+               : "memory");
+}
+// barrier over the 256 consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void rn_consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+#define RN_TMA_THREADS 288  // 8 consumer warps + 1 producer warp
+#define RN_F_STAGES 11
+#define RN_F_STAGE_BYTES (32 * 512 + 32 * 64)  // one 64x32 unit of X (16 KB, verbatim) + its 32 rows of G
+#define RN_G_STAGES 5
+#define RN_G_STAGE_BYTES (64 * 512 + 8 * 512)  // one 64x64 unit of X (32 KB, verbatim) + the step's 64 rows of F
+// dynamic shared memory of the two TMA kernels (stages | 2*NST mbarriers | epilogue scratch)
+static inline size_t rn_f_tma_smem(int k) {
+  return (size_t)RN_F_STAGES * RN_F_STAGE_BYTES + 2 * RN_F_STAGES * 8 + (RN_ROW_TILE * 8 + 2 * k * k + k) * 8 + 16;
+}
+static inline size_t rn_g_tma_smem(int k) {
+  const int nff = k * k + k;
+  return (size_t)RN_G_STAGES * RN_G_STAGE_BYTES + 2 * RN_G_STAGES * 8 +
+         (RN_COL_GROUP * 8 + RN_COL_GROUP * k + 8 * nff + nff + 2 * k * k + k) * 8 + 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F step, tensor-core path fed by a TMA ring (k <= 8), persistent stream-K, 1 CTA per SM.
+//   Same work decomposition and epilogue as rn_f_step_sk; what differs is how X reaches the MMAs: per 64x32
+//   unit one thread issues ONE 16 KB bulk copy (the unit is contiguous in the panel layout) plus a 2 KB copy
+//   of the unit's 32 rows of G into an 11-stage shared-memory ring; the 8 consumer warps wait on the stage's
+//   mbarrier, read their fragments with LDS.128 (conflict-free thanks to the rn_sigma swizzle baked into the
+//   stored layout) and release the stage.  ~200 KB per SM are in flight at all times, independent of
+//   register pressure.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView vw, const RnFit ft, const int v) {
+  constexpr int KP = 8, NST = RN_F_STAGES, XB = 32 * 512, STAGE = RN_F_STAGE_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (ft.ctrl->done) return;
+
+  extern __shared__ __align__(128) unsigned char rn_smem[];
+  unsigned char* stages = rn_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(rn_smem + NST * STAGE);
+  uint64_t* empty = full + NST;
+  double* Ps = reinterpret_cast<double*>(empty + NST);
+  double* Ssm = Ps + RN_ROW_TILE * KP;
+  double* Wsm = Ssm + K * K;
+  double* lamh = Wsm + K * K;
+  int* s_flag = reinterpret_cast<int*>(lamh + K);
+
+  const int64_t pp = vw.pp;
+  const int64_t UPT = pp >> 5;
+  const int64_t U = (int64_t)vw.row_tiles * UPT;
+  const int64_t C = gridDim.x, cta = blockIdx.x;
+  const RnSplit sp(U, C);
+  const int64_t u0 = sp.begin(cta), u1 = sp.begin(cta + 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      rn_mbar_init(&full[i], 1);
+      rn_mbar_init(&empty[i], 8);
+    }
+    rn_mbar_init_fence();
+  }
+  if (tid < K * K) Ssm[tid] = vw.S[tid];
+  if (tid < K) lamh[tid] = 0.5 * vw.lam[tid];
+  __syncthreads();
+
+  if (warp == 8) {  // ---- producer warp ------------------------------------------------------------
+    int64_t it = 0;
+    for (int64_t u = u0; u < u1; ++u, ++it) {
+      const int64_t tile = u / UPT, cb = u - tile * UPT;
+      const int st = (int)(it % NST);
+      const uint32_t ph = (uint32_t)((it / NST) & 1);
+      rn_mbar_wait(&empty[st], ph ^ 1u);
+      unsigned char* sb = stages + st * STAGE;
+      if (lane == 0) {
+        rn_mbar_expect_tx(&full[st], XB + 32 * 64);
+        rn_bulk_g2s(sb, vw.X + (tile * pp + 32 * cb) * RN_ROW_TILE, XB, &full[st]);
+        rn_bulk_g2s(sb + XB, vw.G + (32 * cb) * KP, 32 * 64, &full[st]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ---- consumer warps ----------------------------------------------------------------------------
+  if (tid < K * K) {  // W = crossprod(G) %*% t(S)
+    const int a = tid % K, b = tid / K;
+    double s = 0.0;
+    for (int c = 0; c < K; ++c) s = fma(vw.GtG[a + c * K], Ssm[b + c * K], s);
+    Wsm[a + b * K] = s;
+  }
+  int64_t it = 0;
+  for (int64_t u = u0; u < u1;) {
+    const int64_t tile = u / UPT;
+    const int64_t cb0 = u - tile * UPT;
+    const int64_t cb1 = min(UPT, cb0 + (u1 - u));
+    const bool first_seg = (u == u0);
+    u += cb1 - cb0;
+
+    double acc[4][2][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) acc[m][h][0] = acc[m][h][1] = 0.0;
+    int xo[4];  // swizzled piece offsets (doubles) of rows 16m + 2g + {0,1} in column 4w + t of the unit
+#pragma unroll
+    for (int m = 0; m < 4; ++m) xo[m] = (4 * warp + t) * RN_ROW_TILE + 2 * ((8 * m + g) ^ rn_sigma(t));
+    for (int64_t cb = cb0; cb < cb1; ++cb, ++it) {
+      const int st = (int)(it % NST);
+      const uint32_t ph = (uint32_t)((it / NST) & 1);
+      rn_mbar_wait(&full[st], ph);
+      const unsigned char* sb = stages + st * STAGE;
+      const double* xs = reinterpret_cast<const double*>(sb);
+      const double b = *(reinterpret_cast<const double*>(sb + XB) + (4 * warp + t) * KP + g);
+      double2 x[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) x[m] = *reinterpret_cast<const double2*>(xs + xo[m]);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        rn_dmma(acc[m][0][0], acc[m][0][1], x[m].x, b);
+        rn_dmma(acc[m][1][0], acc[m][1][1], x[m].y, b);
+      }
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&empty[st]);
+    }
+
+    rn_consumer_sync();  // previous segment's epilogue is done with Ps
+    for (int i = tid; i < RN_ROW_TILE * KP; i += 256) Ps[i] = 0.0;
+    rn_consumer_sync();
+    for (int w = 0; w < 8; ++w) {  // fixed warp order
+      if (warp == w) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = 16 * m + 2 * g + h;
+            Ps[row * KP + 2 * t] += acc[m][h][0];
+            Ps[row * KP + 2 * t + 1] += acc[m][h][1];
+          }
+      }
+      rn_consumer_sync();
+    }
+
+    if (!(cb0 == 0 && cb1 == UPT)) {  // the tile straddles CTAs: combine in CTA order
+      double* mine = vw.Ppart + (cta * 2 + (first_seg ? 0 : 1)) * (RN_ROW_TILE * KP);
+      for (int i = tid; i < RN_ROW_TILE * KP; i += 256) mine[i] = Ps[i];
+      __threadfence();
+      rn_consumer_sync();
+      const int64_t c_first = sp.owner(tile * UPT), c_last = sp.owner(tile * UPT + UPT - 1);
+      if (tid == 0) *s_flag = (atomicAdd(&vw.tile_ticket[tile], 1) == (int)(c_last - c_first));
+      rn_consumer_sync();
+      if (!*s_flag) continue;
+      __threadfence();
+      for (int i = tid; i < RN_ROW_TILE * KP; i += 256) {
+        double s = 0.0;
+        for (int64_t c2 = c_first; c2 <= c_last; ++c2) {
+          const int slot = (sp.begin(c2) / UPT == tile) ? 0 : 1;
+          s += __ldcg(vw.Ppart + (c2 * 2 + slot) * (RN_ROW_TILE * KP) + i);
+        }
+        Ps[i] = s;
+      }
+      if (tid == 0) vw.tile_ticket[tile] = 0;
+      rn_consumer_sync();
+    }
+
+    if (tid < RN_ROW_TILE) {
+      const int64_t r = tile * RN_ROW_TILE + tid;
+      if (r < vw.n) {
+        double P[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) P[c] = Ps[tid * KP + c];
+        rn_update_f_row<K>(vw, ft, v, r, P, Ssm, Wsm, lamh);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G step, tensor-core path fed by a TMA ring (k <= 8), persistent stream-K, fused epilogue, 1 CTA per SM.
+//   Unit = 64 data columns x 64 rows of X = one contiguous 32 KB run: ONE bulk copy per unit into a 6-stage
+//   ring (~190 KB in flight per SM).  Consumer warp w owns data columns 8w..8w+7 of the group for every row
+//   step, so there is no cross-warp reduction of T; the F fragment of a step comes straight from global/L1
+//   (all 8 warps read the same 4 KB) and is prefetched one step ahead; F'F / colSums(F) (group 0 only) are
+//   split over the warps by row block.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView vw, const RnFit ft, const int v,
+                                                                   const int fuse_finish) {
+  constexpr int KP = 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
+  constexpr int NST = RN_G_STAGES, STAGE = RN_G_STAGE_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (ft.ctrl->done) return;
+
+  extern __shared__ __align__(128) unsigned char rn_smem[];
+  unsigned char* stages = rn_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(rn_smem + NST * STAGE);
+  uint64_t* empty = full + NST;
+  double* Ts = reinterpret_cast<double*>(empty + NST);  // [64][8]
+  double* Gs = Ts + RN_COL_GROUP * KP;                   // [64][K]
+  double* FFw = Gs + RN_COL_GROUP * K;                   // [8][NFF] per-warp partials; later fin / scratch
+  double* FtFs = FFw + 8 * NFF;                          // [NFF]
+  double* Ssm = FtFs + NFF;
+  double* Vs = Ssm + KK;
+  double* muh = Vs + KK;
+  int* s_flag = reinterpret_cast<int*>(muh + K);
+  static_assert(NOUT + 3 * KK <= 8 * NFF, "last-CTA scratch is aliased onto the per-warp F'F partials");
+  double* fin = FFw;  // used only after the F'F partials have been published
+  double* Us = fin + NOUT;
+  double* Sn = Us + KK;
+  double* red = Sn + KK;
+
+  const int64_t pp = vw.pp;
+  const int64_t NS = vw.row_tiles, NG = vw.col_groups;
+  const int64_t U = NS * NG;
+  const int64_t C = gridDim.x, cta = blockIdx.x;
+  const RnSplit sp(U, C);
+  const int64_t u0 = sp.begin(cta), u1 = sp.begin(cta + 1);
+  const int nffc = (int)sp.owner(NS - 1) + 1;  // CTAs that stream part of column group 0
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      rn_mbar_init(&full[i], 1);
+      rn_mbar_init(&empty[i], 8);
+    }
+    rn_mbar_init_fence();
+  }
+  for (int i = tid; i < KK; i += RN_TMA_THREADS) Ssm[i] = vw.S[i];
+  if (tid < K) muh[tid] = 0.5 * vw.mu[tid];
+  __syncthreads();
+
+  if (warp == 8) {  // ---- producer warp ------------------------------------------------------------
+    int64_t it = 0;
+    for (int64_t u = u0; u < u1; ++u, ++it) {
+      const int64_t grp = u / NS, s = u - grp * NS;
+      const int64_t j0 = grp * RN_COL_GROUP;
+      const int ncol = (int)min((int64_t)RN_COL_GROUP, pp - j0);
+      const int st = (int)(it % NST);
+      const uint32_t ph = (uint32_t)((it / NST) & 1);
+      rn_mbar_wait(&empty[st], ph ^ 1u);
+      unsigned char* sb = stages + st * STAGE;
+      if (lane == 0) {
+        rn_mbar_expect_tx(&full[st], (uint32_t)ncol * 512u + 4096u);
+        rn_bulk_g2s(sb, vw.X + (s * pp + j0) * RN_ROW_TILE, (uint32_t)ncol * 512u, &full[st]);
+        rn_bulk_g2s(sb + 32768, vw.F + s * (KP * RN_ROW_TILE), 4096u, &full[st]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ---- consumer warps ----------------------------------------------------------------------------
+  bool ff_ready = false;
+  int64_t it = 0;
+  for (int64_t u = u0; u < u1;) {
+    const int64_t grp = u / NS;
+    const int64_t s0 = u - grp * NS;
+    const int64_t s1 = min(NS, s0 + (u1 - u));
+    const bool first_seg = (u == u0);
+    u += s1 - s0;
+    const int64_t j0 = grp * RN_COL_GROUP;
+    const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
+    const bool doFF = (grp == 0);
+    const bool have_cols = warp < njb;
+
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;  // two MMA chains (even / odd i)
+    double aff0 = 0.0, aff1 = 0.0, acs0 = 0.0, acs1 = 0.0;
+    int xo[8];  // swizzled piece offsets (doubles) of rows 8i + 2t + {0,1} in column 8w + g of the unit
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xo[i] = (8 * warp + g) * RN_ROW_TILE + 2 * ((4 * i + t) ^ rn_sigma(g));
+    int fo[8];  // F fragment (column c = g, same rows) inside the stage's F block
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fo[i] = 4096 + g * RN_ROW_TILE + 2 * ((4 * i + t) ^ rn_sigma(g));
+    for (int64_t s = s0; s < s1; ++s, ++it) {
+      const int st = (int)(it % NST);
+      const uint32_t ph = (uint32_t)((it / NST) & 1);
+      rn_mbar_wait(&full[st], ph);
+      const double* xs = reinterpret_cast<const double*>(stages + st * STAGE);
+      double2 fw = make_double2(0.0, 0.0);
+      if (doFF) fw = *reinterpret_cast<const double2*>(xs + 4096 + g * RN_ROW_TILE + 2 * ((4 * warp + t) ^ rn_sigma(g)));
+      if (have_cols) {
+        double2 x2[8], f2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x2[i] = *reinterpret_cast<const double2*>(xs + xo[i]);
+          f2[i] = *reinterpret_cast<const double2*>(xs + fo[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          rn_dmma(a0, a1, x2[i].x, f2[i].x);
+          rn_dmma(b0, b1, x2[i + 1].x, f2[i + 1].x);
+          rn_dmma(a0, a1, x2[i].y, f2[i].y);
+          rn_dmma(b0, b1, x2[i + 1].y, f2[i + 1].y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&empty[st]);
+      if (doFF) {  // warp w covers rows 8w + 2t + {0,1} of the step
+        rn_dmma(aff0, aff1, fw.x, fw.x);
+        rn_dmma(aff0, aff1, fw.y, fw.y);
+        rn_dmma(acs0, acs1, 1.0, fw.x);
+        rn_dmma(acs0, acs1, 1.0, fw.y);
+      }
+    }
+
+    rn_consumer_sync();  // previous segment's epilogue is done with Ts / Gs / FFw
+    Ts[(8 * warp + g) * KP + 2 * t] = a0 + b0;
+    Ts[(8 * warp + g) * KP + 2 * t + 1] = a1 + b1;
+    if (doFF) {
+      double* mine = FFw + warp * NFF;
+      if (g < K) {
+        if (2 * t < K) mine[g + (2 * t) * K] = aff0;
+        if (2 * t + 1 < K) mine[g + (2 * t + 1) * K] = aff1;
+      }
+      if (g == 0) {
+        if (2 * t < K) mine[KK + 2 * t] = acs0;
+        if (2 * t + 1 < K) mine[KK + 2 * t + 1] = acs1;
+      }
+    }
+    rn_consumer_sync();
+    if (doFF) {  // publish this CTA's F'F | colSums(F) partial (warps summed in order)
+      if (tid < NFF) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += FFw[w * NFF + tid];
+        vw.FFpart[cta * NFF + tid] = s;
+      }
+      __threadfence();
+      rn_consumer_sync();
+      if (tid == 0) atomicAdd(&vw.misc_ticket[2], 1);
+    }
+
+    if (!(s0 == 0 && s1 == NS)) {  // the column group straddles CTAs: combine in CTA order
+      double* mine = vw.Tpart + (cta * 2 + (first_seg ? 0 : 1)) * (RN_COL_GROUP * KP);
+      for (int i = tid; i < RN_COL_GROUP * KP; i += 256) mine[i] = Ts[i];
+      __threadfence();
+      rn_consumer_sync();
+      const int64_t c_first = sp.owner(grp * NS), c_last = sp.owner(grp * NS + NS - 1);
+      if (tid == 0) *s_flag = (atomicAdd(&vw.group_ticket[grp], 1) == (int)(c_last - c_first));
+      rn_consumer_sync();
+      if (!*s_flag) continue;
+      __threadfence();
+      for (int i = tid; i < RN_COL_GROUP * KP; i += 256) {
+        double s = 0.0;
+        for (int64_t c2 = c_first; c2 <= c_last; ++c2) {
+          const int slot = (sp.begin(c2) / NS == grp) ? 0 : 1;
+          s += __ldcg(vw.Tpart + (c2 * 2 + slot) * (RN_COL_GROUP * KP) + i);
+        }
+        Ts[i] = s;
+      }
+      if (tid == 0) vw.group_ticket[grp] = 0;
+      rn_consumer_sync();
+    }
+
+    // ---- epilogue of this column group: update_g, then the group's G'G | A | colSums(G) partial ----
+    if (!ff_ready) {
+      if (tid == 0) {
+        while (rn_ld_acquire(&vw.misc_ticket[2]) < nffc) __nanosleep(64);
+      }
+      rn_consumer_sync();
+      if (tid < NFF) {
+        double s = 0.0;
+        for (int i = 0; i < nffc; ++i) s += __ldcg(vw.FFpart + (int64_t)i * NFF + tid);
+        FtFs[tid] = s;
+      }
+      rn_consumer_sync();
+      for (int o = tid; o < KK; o += 256) {  // V = crossprod(F) %*% S
+        const int a = o % K, c = o / K;
+        double s = 0.0;
+        for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
+        Vs[a + c * K] = s;
+      }
+      rn_consumer_sync();
+      ff_ready = true;
+    }
+    if (tid < RN_COL_GROUP) {
+      const int64_t j = j0 + tid;
+      double gn[K];
+      if (j < vw.p) {
+        double Tj[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) Tj[c] = Ts[tid * KP + c];
+        rn_update_g_row<K>(vw, ft, v, j, Tj, Ssm, Vs, muh, gn);
+      } else {
+#pragma unroll
+        for (int c = 0; c < K; ++c) gn[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < K; ++c) Gs[tid * K + c] = gn[c];
+    }
+    rn_consumer_sync();
+    for (int o = tid; o < NOUT; o += 256) {
+      double s = 0.0;
+      if (o < KK) {
+        const int a = o % K, b = o / K;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
+      } else if (o < 2 * KK) {
+        const int a = (o - KK) % K, b = (o - KK) / K;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
+      } else {
+        const int c = o - 2 * KK;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s += Gs[i * K + c];
+      }
+      vw.GGpart[grp * NOUT + o] = s;
+    }
+    __threadfence();
+    rn_consumer_sync();
+    if (tid == 0) *s_flag = (atomicAdd(&vw.misc_ticket[0], 1) == (int)NG - 1);
+    rn_consumer_sync();
+    if (!*s_flag) continue;
+    __threadfence();
+    // ---- last column group done: finish the view --------------------------------------------------
+    for (int o = tid; o < NOUT; o += 256) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, NG);
+    if (tid == 0) {
+      vw.misc_ticket[0] = 0;
+      vw.misc_ticket[2] = 0;
+    }
+    rn_consumer_sync();
+    rn_view_finish<K, 256, true>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
   }
 }
 
@@ -702,13 +1192,14 @@ __global__ void __launch_bounds__(256) rn_f_step_dfma(const RnView vw, const RnF
   double a0[K], a1[K];
 #pragma unroll
   for (int c = 0; c < K; ++c) a0[c] = a1[c] = 0.0;
-  const double* xr = vw.X + (int64_t)tile * pp * RN_ROW_TILE + 2 * lane;
+  const double* xr = vw.X + (int64_t)tile * pp * RN_ROW_TILE;
   constexpr int U = 4;
   int64_t j = jbeg + warp;
+  const int xo = 2 * (lane ^ rn_sigma(j));  // j advances in steps of 8: j mod 4 (hence the swizzle) is fixed
   for (; j + 8 * (U - 1) < jend; j += 8 * U) {
     double2 x[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) x[u] = rn_ld_stream2(xr + (j + 8 * u) * RN_ROW_TILE);
+    for (int u = 0; u < U; ++u) x[u] = rn_ld_stream2(xr + (j + 8 * u) * RN_ROW_TILE + xo);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double* gr = G + (j + 8 * u) * KP;
@@ -721,7 +1212,7 @@ __global__ void __launch_bounds__(256) rn_f_step_dfma(const RnView vw, const RnF
     }
   }
   for (; j < jend; j += 8) {
-    const double2 x = rn_ld_stream2(xr + j * RN_ROW_TILE);
+    const double2 x = rn_ld_stream2(xr + j * RN_ROW_TILE + xo);
     const double* gr = G + j * KP;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
@@ -799,7 +1290,7 @@ __global__ void __launch_bounds__(256) rn_gram_f(const RnView vw, const RnFit ft
   for (int ch = c0; ch < c1; ++ch) {
     const int64_t r = (int64_t)ch * 256 + tid;
 #pragma unroll
-    for (int c = 0; c < K; ++c) rows[tid * K + c] = (r < vw.n) ? vw.F[(int64_t)c * ldx + r] : 0.0;
+    for (int c = 0; c < K; ++c) rows[tid * K + c] = (r < vw.n) ? vw.F[rn_fidx(r, c, vw.kp)] : 0.0;
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
@@ -833,7 +1324,7 @@ __global__ void __launch_bounds__(256) rn_g_stream_dfma(const RnView vw, const R
   __shared__ double Ts[RN_COL_GROUP_DFMA * KP];
   __shared__ int s_last;
 
-  const int64_t ldx = vw.ldx, pp = vw.pp;
+  const int64_t pp = vw.pp;
   const int ns = vw.row_tiles;
   const int s0 = (int)((int64_t)ns * rs / nrs), s1 = (int)((int64_t)ns * (rs + 1) / nrs);
   const int64_t j0 = (int64_t)grp * RN_COL_GROUP_DFMA;
@@ -850,14 +1341,15 @@ __global__ void __launch_bounds__(256) rn_g_stream_dfma(const RnView vw, const R
 
   if (active) {
     for (int s = s0; s < s1; ++s) {
-      const double* xp = vw.X + ((int64_t)s * pp + jc) * RN_ROW_TILE + 2 * lane;
-      const int64_t rr = (int64_t)s * RN_ROW_TILE + 2 * lane;
+      const double* xp = vw.X + ((int64_t)s * pp + jc) * RN_ROW_TILE;
       double2 x[4];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) x[jj] = rn_ld_stream2(xp + jj * RN_ROW_TILE);
+      for (int jj = 0; jj < 4; ++jj)  // jc is a multiple of 4: the swizzle of column jc + jj is sigma(jj)
+        x[jj] = rn_ld_stream2(xp + jj * RN_ROW_TILE + 2 * (lane ^ rn_sigma(jj)));
       double2 f2[K];
 #pragma unroll
-      for (int c = 0; c < K; ++c) f2[c] = *reinterpret_cast<const double2*>(F + (int64_t)c * ldx + rr);
+      for (int c = 0; c < K; ++c)
+        f2[c] = *reinterpret_cast<const double2*>(F + ((int64_t)s * KP + c) * RN_ROW_TILE + 2 * (lane ^ rn_sigma(c)));
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
@@ -972,11 +1464,7 @@ __global__ void __launch_bounds__(RN_GEPI_THREADS(K)) rn_g_epilogue(const RnView
   if (!s_last) return;
   __threadfence();
   if (tid == 0) vw.misc_ticket[0] = 0;
-  for (int o = tid; o < NOUT; o += NT) {
-    double s = 0.0;
-    for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(vw.GGpart + (int64_t)i * NOUT + o);
-    fin[o] = s;
-  }
+  for (int o = tid; o < NOUT; o += NT) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, (int64_t)gridDim.x);
   __syncthreads();
   rn_view_finish<K, NT>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
 }
@@ -994,8 +1482,7 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
   __shared__ double bs[256];
   __shared__ int s_last;
   const int tile = blockIdx.x, cs = blockIdx.y, ncs = gridDim.y;
-  const int64_t ldx = vw.ldx, pp = vw.pp;
-  const int64_t r0 = (int64_t)tile * RN_ROW_TILE + 2 * lane;
+  const int64_t pp = vw.pp;
   const int nb = (int)(pp >> 3);
   const int64_t jbeg = 8 * ((int64_t)nb * cs / ncs), jend = 8 * ((int64_t)nb * (cs + 1) / ncs);
   if (tid < K * K) Ssm[tid] = vw.S[tid];
@@ -1005,7 +1492,8 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
     double f0[K], f1[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      const double2 f = *reinterpret_cast<const double2*>(vw.F + (int64_t)c * ldx + r0);
+      const double2 f = *reinterpret_cast<const double2*>(vw.F + ((int64_t)tile * KP + c) * RN_ROW_TILE +
+                                                          2 * (lane ^ rn_sigma(c)));
       f0[c] = f.x;
       f1[c] = f.y;
     }
@@ -1022,9 +1510,9 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
     }
   }
   double acc = 0.0;
-  const double* xr = vw.X + (int64_t)tile * pp * RN_ROW_TILE + 2 * lane;
+  const double* xr = vw.X + (int64_t)tile * pp * RN_ROW_TILE;
   for (int64_t j = jbeg + warp; j < jend; j += 8) {
-    const double2 x = rn_ld_stream2(xr + j * RN_ROW_TILE);
+    const double2 x = rn_ld_stream2(xr + j * RN_ROW_TILE + 2 * (lane ^ rn_sigma(j)));
     const double* gr = vw.G + j * KP;
     double h0 = 0.0, h1 = 0.0;
 #pragma unroll
@@ -1084,8 +1572,8 @@ __global__ void rn_finish(const RnFit ft, const int force) {
 // ------------------------------------------------------------------------------------------------
 
 // Re-tiles `ncols` columns of a column-major source (leading dimension lds, n valid rows) into the
-// panel layout X[tile][col][64] starting at data column col0.  One thread per 16-byte piece; padding rows
-// of the last tile are written as zero.  grid-stride.
+// panel layout X[tile][col][64] (16-byte pieces swizzled by rn_sigma) starting at data column col0.  One
+// thread per 16-byte piece; padding rows of the last tile are written as zero.  grid-stride.
 __global__ void __launch_bounds__(256) rn_to_panels(const RnView vw, const double* __restrict__ src, int64_t lds,
                                                     int64_t col0, int64_t ncols) {
   const int64_t pieces = (int64_t)vw.row_tiles * ncols * 32;
@@ -1097,7 +1585,8 @@ __global__ void __launch_bounds__(256) rn_to_panels(const RnView vw, const doubl
     double2 val;
     val.x = (r < vw.n) ? src[cj * lds + r] : 0.0;
     val.y = (r + 1 < vw.n) ? src[cj * lds + r + 1] : 0.0;
-    *reinterpret_cast<double2*>(vw.X + (tile * vw.pp + col0 + cj) * RN_ROW_TILE + 2 * h) = val;
+    *reinterpret_cast<double2*>(vw.X + (tile * vw.pp + col0 + cj) * RN_ROW_TILE +
+                                2 * (h ^ rn_sigma(col0 + cj))) = val;
   }
 }
 
@@ -1149,7 +1638,7 @@ __global__ void __launch_bounds__(1024) rn_factor_sums(const RnView vw) {
   __shared__ double bs[1024];
   for (int c = 0; c < K; ++c) {
     double s = 0.0;
-    for (int64_t r = tid; r < vw.n; r += 1024) s += vw.F[(int64_t)c * vw.ldx + r];
+    for (int64_t r = tid; r < vw.n; r += 1024) s += vw.F[rn_fidx(r, c, KP)];
     bs[tid] = s;
     __syncthreads();
     for (int o = 512; o > 0; o >>= 1) {
@@ -1201,7 +1690,7 @@ __global__ void __launch_bounds__(256) rn_normalise(const RnView vw) {
   const int K = vw.k, KP = vw.kp;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < vw.n)
-    for (int c = 0; c < K; ++c) vw.F[(int64_t)c * vw.ldx + i] /= vw.csF[c];
+    for (int c = 0; c < K; ++c) vw.F[rn_fidx(i, c, KP)] /= vw.csF[c];
   if (i < vw.p)
     for (int c = 0; c < K; ++c) vw.G[i * KP + c] /= vw.csG[c];
   if (blockIdx.x == 0 && threadIdx.x < K * K) {

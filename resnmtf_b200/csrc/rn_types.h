@@ -5,7 +5,8 @@
 //                  panels) read long contiguous runs.  Rows are padded to a multiple of 64 (ldx), columns
 //                  to a multiple of 32 (pp); all padding is zero so the streaming kernels need no bounds
 //                  checks.  Element (r, j) lives at ((r/64)*pp + j)*64 + r%64.
-//   F   [kp][ldx]  column-major, kp = 8 (k<=8) or 16; padding rows/columns zero.
+//   F   [row_tiles][kp][64]  the same 64-row panels (and the same piece swizzle) as X, kp = 8 (k<=8) or 16;
+//                  padding rows/columns zero.  The 64 rows of F a row step needs are one kp*512 B run.
 //   G,T [pp][kp]   row-major (one 64 B / 128 B row per data column) so that a column's k values are one
 //                  uniform / vector load in the X.G pass and one gather in the psi coupling.
 //   S, F'F, G'G, A  k x k column-major compact, lambda/mu/colsums length k.

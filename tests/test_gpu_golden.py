@@ -11,7 +11,7 @@ from resnmtf_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
 @pytest.mark.parametrize("name", CASES)
 def test_fixed_sweeps_match_golden(ctx, name, impl):
     prob, z, V = load(name)

@@ -21,7 +21,7 @@ def single_view_problem(n, p, k, seed, n_planted=4, sigma=1.0):
     return Problem([x], [k], [f], [s], [g])
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_single_view_every_k(ctx, k, impl):
     prob = single_view_problem(300, 200, k, seed=100 + k)
@@ -34,7 +34,7 @@ def test_single_view_k_above_8(ctx, k):
     compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT)
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
 @pytest.mark.parametrize("shape", [(1, 1), (2, 3), (63, 7), (64, 8), (65, 9), (129, 65), (257, 93), (1000, 37)])
 def test_ragged_shapes(ctx, shape, impl):
     n, p = shape
@@ -49,7 +49,7 @@ def test_error_modes(ctx, err_mode):
     compare_trace(prob, ctx, n_iters=8, err_mode=err_mode)
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
 @pytest.mark.parametrize("split", [(3, 5, 7, 5), (1, 1, 1, 1), (2, 7, 23, 41), (4, 2, 1000000, 1000000)])
 def test_forced_splits(ctx, impl, split, monkeypatch):
     """Work partitions that make tiles / column groups straddle CTAs in every way: column-split F step and
@@ -94,7 +94,7 @@ def two_view_problem(seed, k=3, phi=0.0, psi=0.0, xi=0.0, partial=False):
                    phi=rest(phi), xi=rest(xi), psi=rest(psi), row_names=rn, col_names=cn)
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
 @pytest.mark.parametrize("cfg", [
     dict(phi=200.0), dict(psi=200.0), dict(xi=50.0), dict(phi=200.0, psi=100.0, xi=50.0),
     dict(phi=1000.0, psi=1000.0, partial=True), dict(phi=5.0, partial=True),
@@ -120,7 +120,7 @@ def test_four_views_mixed_k_and_na_pairs(ctx):
     psi = np.zeros((4, 4)); psi[0, 2] = 40.0
     prob = Problem(data, ks, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
                    phi=O.init_rest_mats(phi, 4), psi=O.init_rest_mats(psi, 4), row_names=rn, col_names=cn)
-    for impl in (L.IMPL_DFMA, L.IMPL_DMMA):
+    for impl in (L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA):
         compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=impl)
 
 

@@ -42,7 +42,7 @@ def main():
             fit.set_factors(0, f, s, g)
             fit.run(args.iters)
             c = fit.counters()
-            line = f"k={k} impl={'DFMA' if impl == 1 else 'DMMA'}"
+            line = f"k={k} impl={ {1: 'DFMA', 2: 'DMMA', 3: 'TMA'}.get(c['impl'], c['impl']) }"
             for name in ("f_step", "g_stream", "g_epilogue", "residual", "finish"):
                 ms = prof[name]["ms"] / max(1, args.iters)
                 line += f" | {name} {ms * 1e3:8.1f} us"
