@@ -152,9 +152,12 @@ int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[5], int64_t
 /* Size of the opaque NCCL unique id and its creation on rank 0 (to be broadcast by the host). */
 int resnmtf_comm_id_size(void);
 int resnmtf_comm_id_create(void* id_out);
-/* Joins the communicator.  After this, every view of every fit created on ctx is treated as
- * ROW-SHARDED: n[v] passed to fit_create is the local row count, F rows are local, G/S/lambda/mu are
- * replicated and X'F, F'F, colSums(F), ||X||^2 and the residual are all-reduced each sweep. */
+/* Joins the communicator (NCCL is resolved with dlopen at this point; RESNMTF_E_COMM when it is missing).
+ * After this, every view of every fit created on ctx is treated as ROW-SHARDED: n[v] passed to fit_create
+ * is the local row count (whole 64-row panels except on the last rank), F rows are local, G/S/lambda/mu
+ * are replicated; per sweep [X'F | F'F | colSums(F)] is all-reduced once (p*k + k*k + k doubles) and the
+ * G/S/lambda/mu updates are computed redundantly on every rank; ||X||^2 and the direct residual are
+ * all-reduced scalars.  phi/psi gather maps then refer to LOCAL rows of equally sharded views. */
 int resnmtf_ctx_join(resnmtf_ctx* ctx, const void* id, int rank, int n_ranks);
 
 #ifdef __cplusplus

@@ -14,9 +14,44 @@
 #include "../../include/resnmtf_b200.h"
 #include "rn_kernels.cuh"
 
-#ifdef RESNMTF_WITH_NCCL
-#include <nccl.h>
-#endif
+#include <dlfcn.h>
+
+// NCCL is only needed by the row-sharded path, so it is resolved lazily with dlopen (no link-time
+// dependency): the handful of types / enum values used here are ABI-stable across NCCL 2.x.
+typedef struct rn_nccl_comm* rn_ncclComm_t;
+typedef struct { char internal[128]; } rn_ncclUniqueId;
+enum { RN_NCCL_SUCCESS = 0, RN_NCCL_SUM = 0, RN_NCCL_INT64 = 4, RN_NCCL_FLOAT64 = 8 };
+struct RnNccl {
+  void* handle = nullptr;
+  int (*GetUniqueId)(rn_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(rn_ncclComm_t*, int, rn_ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(rn_ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, rn_ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static RnNccl& rn_nccl() {
+  static RnNccl api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.GetUniqueId = (int (*)(rn_ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(rn_ncclComm_t*, int, rn_ncclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(rn_ncclComm_t))dlsym(api.handle, "ncclCommDestroy");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, rn_ncclComm_t, cudaStream_t))dlsym(
+          api.handle, "ncclAllReduce");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    }
+  }
+  return api;
+}
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -36,6 +71,13 @@ static int rn_fail(int code, const std::string& msg) {
                      std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
   } while (0)
 
+#define RN_NCCL(expr)                                                                                   \
+  do {                                                                                                  \
+    int r__ = (expr);                                                                                   \
+    if (r__ != RN_NCCL_SUCCESS)                                                                         \
+      return rn_fail(RESNMTF_E_COMM, std::string(#expr) + ": " + rn_nccl().GetErrorString(r__));        \
+  } while (0)
+
 #define RN_CHECK(cond, code, msg) \
   do {                            \
     if (!(cond)) return rn_fail(code, msg); \
@@ -50,9 +92,7 @@ struct resnmtf_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int rank = 0, n_ranks = 1;
-#ifdef RESNMTF_WITH_NCCL
-  ncclComm_t comm = nullptr;
-#endif
+  rn_ncclComm_t comm = nullptr;
 };
 
 struct ViewHost {
@@ -87,6 +127,7 @@ struct resnmtf_fit {
   bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
   bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
   bool auto_direct = false; // AUTO error mode has handed over to the direct residual pass
+  int comm_rc = 0;          // first NCCL failure seen while enqueueing (row-sharded path)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int64_t launches_per_iter = 0;
@@ -114,6 +155,14 @@ static int rn_free(resnmtf_fit* f, void* p) {
 }
 
 static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// in-place sum over the ranks of a row-sharded context, on the context's stream (graph-capturable)
+static int rn_allreduce(resnmtf_ctx* ctx, void* buf, size_t count, bool is_int64 = false) {
+  if (ctx->n_ranks <= 1) return RESNMTF_OK;
+  RN_NCCL(rn_nccl().AllReduce(buf, buf, count, is_int64 ? RN_NCCL_INT64 : RN_NCCL_FLOAT64, RN_NCCL_SUM, ctx->comm,
+                              ctx->stream));
+  return RESNMTF_OK;
+}
 
 // host twin of rn_fidx (rn_kernels.cuh): position of F[r, c] in the swizzled 64-row panel layout
 static inline int64_t rn_fidx_host(int64_t r, int c, int kp) {
@@ -200,15 +249,59 @@ static void launch_g_epilogue(const ViewHost& vh, const RnFit& ft, int v, int fu
   }
 }
 
-// G step of one view: returns the number of kernels launched.
-static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, int fuse, cudaStream_t st) {
+// number of stream-K CTAs that stream part of column group 0 (the F'F contributors) -- host twin of the
+// `nffc` the G-step kernels compute from RnSplit
+static int ff_contributors(const RnView& d) {
+  const int64_t NS = d.row_tiles, U = NS * d.col_groups, C = d.g_ctas;
+  const int64_t q = U / C, rem = U % C, u = NS - 1, cut = rem * (q + 1);
+  return (int)(u < cut ? u / (q + 1) : rem + (u - cut) / q) + 1;
+}
+
+// G step of one view: returns the number of kernels launched.  `ctx` is non-null with n_ranks > 1 for a
+// row-sharded view: the stream kernel then stops after T, [T | F'F | colSums(F)] is all-reduced over the ranks
+// and the stand-alone epilogue finishes the view on every rank redundantly (no broadcast needed).
+static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, int fuse, cudaStream_t st,
+                         resnmtf_ctx* ctx, int* comm_rc) {
   const int K = vh.d.k;
-  if (use_mma(vh, impl)) {
+  const bool sharded = ctx && ctx->n_ranks > 1;
+  if (use_mma(vh, impl) && !sharded) {
     if (impl == RESNMTF_IMPL_TMA)
       g_step_tma_fn(K)<<<vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st>>>(vh.d, ft, v, fuse);
     else
       g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, fuse);
     return 1;
+  }
+  if (sharded) {
+    int n = 0, count;
+    if (use_mma(vh, impl)) {
+      if (impl == RESNMTF_IMPL_TMA)
+        g_step_tma_fn(K)<<<vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st>>>(vh.d, ft, v, -1);
+      else
+        g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, -1);
+      count = ff_contributors(vh.d);
+      n = 1;
+    } else {
+      dim3 grid(vh.d.col_groups, vh.d.rs);
+      switch (K) {
+#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 8><<<grid, 256, 0, st>>>(vh.d, ft); break;
+        RN_K_CASES_LE8(X)
+#undef X
+#define X(KC) case KC: rn_gram_f<KC><<<vh.d.nff, 256, 0, st>>>(vh.d, ft); rn_g_stream_dfma<KC, 16><<<grid, 256, 0, st>>>(vh.d, ft); break;
+        RN_K_CASES_GT8(X)
+#undef X
+      }
+      count = vh.d.nff;
+      n = 2;
+    }
+    rn_pack_ff<<<1, 128, 0, st>>>(vh.d, ft, count);
+    const size_t words = (size_t)vh.d.pp * vh.d.kp + (size_t)K * K + K;
+    const int rc = rn_allreduce(ctx, vh.d.T, words);
+    if (rc && comm_rc) *comm_rc = rc;
+    ViewHost tmp = vh;  // the epilogue reads the reduced F'F | colSums(F) as a single "partial"
+    tmp.d.FFpart = vh.d.T + (size_t)vh.d.pp * vh.d.kp;
+    tmp.d.nff = 1;
+    launch_g_epilogue(tmp, ft, v, fuse, st);
+    return n + 3;
   }
   dim3 grid(vh.d.col_groups, vh.d.rs);
   switch (K) {
@@ -223,7 +316,7 @@ static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, i
   return 3;
 }
 
-static void launch_residual(const ViewHost& vh, const RnFit& ft, int force, cudaStream_t st) {
+static void launch_residual_kernel(const ViewHost& vh, const RnFit& ft, int force, cudaStream_t st) {
   dim3 grid(vh.d.row_tiles, vh.d.resid_cs);
   const int K = vh.d.k;
   switch (K) {
@@ -234,6 +327,17 @@ static void launch_residual(const ViewHost& vh, const RnFit& ft, int force, cuda
     RN_K_CASES_GT8(X)
 #undef X
   }
+}
+
+// direct error of one view; row-sharded: local sum of squares -> all-reduce -> scale.  Returns launches.
+static int launch_residual(const ViewHost& vh, const RnFit& ft, int force, cudaStream_t st, resnmtf_ctx* ctx,
+                           int* comm_rc) {
+  launch_residual_kernel(vh, ft, force, st);
+  if (!(ctx && ctx->n_ranks > 1)) return 1;
+  const int rc = rn_allreduce(ctx, vh.d.scal + 3, 1);
+  if (rc && comm_rc) *comm_rc = rc;
+  rn_residual_scale<<<1, 1, 0, st>>>(vh.d, ft, force);
+  return 3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,9 +383,7 @@ extern "C" int resnmtf_ctx_create(int device, resnmtf_ctx** out) {
 extern "C" int resnmtf_ctx_destroy(resnmtf_ctx* ctx) {
   if (!ctx) return RESNMTF_OK;
   cudaSetDevice(ctx->device);
-#ifdef RESNMTF_WITH_NCCL
-  if (ctx->comm) ncclCommDestroy(ctx->comm);
-#endif
+  if (ctx->comm) rn_nccl().CommDestroy(ctx->comm);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -379,6 +481,20 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
   f->h_psi.assign((size_t)V * V, 0.0);
   std::memset(&f->d, 0, sizeof(RnFit));
   std::memset(&f->h_ctrl, 0, sizeof(RnCtrl));
+  if (ctx->n_ranks > 1) {  // row-sharded views: n is local, the coupling weights need the global row count
+    int64_t* d_n = nullptr;
+    if ((rc = rn_alloc(f, &d_n, (size_t)V))) return fail(rc);
+    std::vector<int64_t> hn(n, n + V);
+    cudaError_t e = cudaMemcpyAsync(d_n, hn.data(), V * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && (rc = rn_allreduce(ctx, d_n, (size_t)V, true))) return fail(rc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hn.data(), d_n, V * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      rn_fail(RESNMTF_E_CUDA, std::string("resnmtf_fit_create: ") + cudaGetErrorString(e));
+      return fail(RESNMTF_E_CUDA);
+    }
+    for (int v = 0; v < V; ++v) f->views[v].d.n_glob = hn[v];
+  }
   *out = f;
   return RESNMTF_OK;
 }
@@ -435,6 +551,10 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
   }
   rn_xnorm2<<<1024, 256, 0, st>>>(vh.d, vh.xpart, vh.xticket);
   RN_CUDA(cudaGetLastError());
+  {
+    int rc2 = rn_allreduce(fit->ctx, vh.d.scal, 1);  // data_norms of the whole view when row-sharded
+    if (rc2) return rc2;
+  }
   RN_CUDA(cudaStreamSynchronize(st));  // the caller's buffer is only borrowed for the call
   vh.has_data = true;
   return RESNMTF_OK;
@@ -468,6 +588,10 @@ extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f,
   if (lambda) RN_CUDA(cudaMemcpyAsync(vh.d.lam, lambda, K * sizeof(double), cudaMemcpyHostToDevice, st));
   if (mu) RN_CUDA(cudaMemcpyAsync(vh.d.mu, mu, K * sizeof(double), cudaMemcpyHostToDevice, st));
   rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);
+  {
+    int rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)K);  // F rows are sharded, G is replicated
+    if (rc2) return rc2;
+  }
   rn_default_lm<<<1, 32, 0, st>>>(vh.d, lambda ? 0 : 1, mu ? 0 : 1);
   RN_CUDA(cudaGetLastError());
   RN_CUDA(cudaStreamSynchronize(st));
@@ -617,11 +741,11 @@ static int build_plan(resnmtf_fit* fit) {
       d.g_ctas = std::max(1, std::min<int>(rn_env_int("RESNMTF_G_CTAS", d.g_ctas), (int)g_units));
       d.cs = d.rs = 1;
       d.nff = 0;
-      d.gepi_ctas = 0;
+      d.gepi_ctas = (int)((d.p + RN_GEPI_THREADS(K) - 1) / RN_GEPI_THREADS(K));  // row-sharded path only
       n_ppart = (size_t)d.f_ctas * 2 * RN_ROW_TILE * KP;
       n_tpart = (size_t)d.g_ctas * 2 * RN_COL_GROUP * KP;
       n_ffpart = (size_t)d.g_ctas * (K * K + K);
-      n_ggpart = (size_t)d.col_groups * (2 * K * K + K);
+      n_ggpart = (size_t)std::max(d.col_groups, d.gepi_ctas) * (2 * K * K + K);
     } else {
       // F step: one CTA per 64-row tile; split the columns only when there are too few tiles to fill
       // the machine (each split keeps >= 64 data columns)
@@ -749,11 +873,10 @@ static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<
     launches += 1;
     mark(1);
     const int fuse = (!direct && v == fit->V - 1) ? 1 : 0;
-    launches += launch_g_step(vh, fit->d, v, fit->impl, fuse, st);
+    launches += launch_g_step(vh, fit->d, v, fit->impl, fuse, st, fit->ctx, &fit->comm_rc);
     if (direct) {
       mark(3);
-      launch_residual(vh, fit->d, 0, st);
-      launches += 1;
+      launches += launch_residual(vh, fit->d, 0, st, fit->ctx, &fit->comm_rc);
     }
   }
   if (direct) {
@@ -832,6 +955,7 @@ static int run_batch(resnmtf_fit* fit, int64_t iters) {
     }
   }
   fit->counters.kernel_launches += iters * fit->launches_per_iter;
+  if (fit->comm_rc) return fit->comm_rc;
   return RESNMTF_OK;
 }
 
@@ -861,10 +985,11 @@ static int handle_pause(resnmtf_fit* fit) {
   fit->h_ctrl.want_direct = 0;
   int rc;
   if ((rc = push_ctrl(fit))) return rc;
-  for (int v = 0; v < fit->V; ++v) launch_residual(fit->views[v], fit->d, 1, st);
+  int nl = 1;
+  for (int v = 0; v < fit->V; ++v) nl += launch_residual(fit->views[v], fit->d, 1, st, fit->ctx, &fit->comm_rc);
   rn_finish<<<1, 1, 0, st>>>(fit->d, 0);
   RN_CUDA(cudaGetLastError());
-  fit->counters.kernel_launches += fit->V + 1;
+  fit->counters.kernel_launches += nl;
   fit->auto_direct = true;
   fit->meta_dirty = true;
   if ((rc = pull_ctrl(fit))) return rc;
@@ -1004,9 +1129,12 @@ extern "C" int resnmtf_fit_normalise(resnmtf_fit* fit) {
     const ViewHost& vh = fit->views[v];
     RN_CHECK(vh.has_factors, RESNMTF_E_STATE, "resnmtf_fit_normalise: factors were never set");
     rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);
+    int rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)vh.d.k);
+    if (rc2) return rc2;
     const int64_t m = std::max(vh.d.n, vh.d.p);
     rn_normalise<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(vh.d);
     rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);  // keep G'G / colsums consistent with the scaled factors
+    if ((rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)vh.d.k))) return rc2;
   }
   RN_CUDA(cudaGetLastError());
   RN_CUDA(cudaStreamSynchronize(st));
@@ -1043,29 +1171,27 @@ extern "C" int resnmtf_fit_get_counters(resnmtf_fit* fit, resnmtf_counters* out)
 // ------------------------------------------------------------------------------------------------
 // row-sharded path (NCCL) -- see DESIGN.md "Multi-GPU"
 // ------------------------------------------------------------------------------------------------
-extern "C" int resnmtf_comm_id_size(void) {
-#ifdef RESNMTF_WITH_NCCL
-  return (int)sizeof(ncclUniqueId);
-#else
-  return 0;
-#endif
-}
+extern "C" int resnmtf_comm_id_size(void) { return (int)sizeof(rn_ncclUniqueId); }
 
 extern "C" int resnmtf_comm_id_create(void* id_out) {
-#ifdef RESNMTF_WITH_NCCL
   RN_CHECK(id_out != nullptr, RESNMTF_E_INVALID, "resnmtf_comm_id_create: NULL argument");
-  ncclUniqueId id;
-  ncclResult_t r = ncclGetUniqueId(&id);
-  if (r != ncclSuccess) return rn_fail(RESNMTF_E_COMM, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+  RN_CHECK(rn_nccl().ok, RESNMTF_E_COMM, "libnccl.so.2 could not be loaded");
+  rn_ncclUniqueId id;
+  RN_NCCL(rn_nccl().GetUniqueId(&id));
   std::memcpy(id_out, &id, sizeof(id));
   return RESNMTF_OK;
-#else
-  (void)id_out;
-  return rn_fail(RESNMTF_E_UNSUPPORTED, "library was built without NCCL");
-#endif
 }
 
 extern "C" int resnmtf_ctx_join(resnmtf_ctx* ctx, const void* id, int rank, int n_ranks) {
-  (void)ctx; (void)id; (void)rank; (void)n_ranks;
-  return rn_fail(RESNMTF_E_UNSUPPORTED, "row-sharded views are not implemented yet");
+  RN_CHECK(ctx && id, RESNMTF_E_INVALID, "resnmtf_ctx_join: NULL argument");
+  RN_CHECK(n_ranks >= 1 && rank >= 0 && rank < n_ranks, RESNMTF_E_INVALID, "resnmtf_ctx_join: bad rank");
+  RN_CHECK(ctx->comm == nullptr, RESNMTF_E_STATE, "resnmtf_ctx_join: the context already joined a communicator");
+  RN_CHECK(rn_nccl().ok, RESNMTF_E_COMM, "libnccl.so.2 could not be loaded");
+  RN_CUDA(cudaSetDevice(ctx->device));
+  rn_ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  RN_NCCL(rn_nccl().CommInitRank(&ctx->comm, n_ranks, uid, rank));
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  return RESNMTF_OK;
 }

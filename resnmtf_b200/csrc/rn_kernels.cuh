@@ -643,6 +643,10 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
       __syncthreads();
     }
 
+    if (fuse_finish < 0) {  // row-sharded view: T goes to HBM for the all-reduce, the epilogue is its own launch
+      for (int i = tid; i < 8 * njb * KP; i += 128) vw.T[j0 * KP + i] = Ts[i];
+      continue;
+    }
     // ---- epilogue of this column group: update_g, then the group's G'G | A | colSums(G) partial ----
     if (!ff_ready) {
       if (tid == 0) {
@@ -1098,6 +1102,10 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView 
       rn_consumer_sync();
     }
 
+    if (fuse_finish < 0) {  // row-sharded view: T goes to HBM for the all-reduce, the epilogue is its own launch
+      for (int i = tid; i < 8 * njb * KP; i += 256) vw.T[j0 * KP + i] = Ts[i];
+      continue;
+    }
     // ---- epilogue of this column group: update_g, then the group's G'G | A | colSums(G) partial ----
     if (!ff_ready) {
       if (tid == 0) {
@@ -1559,6 +1567,28 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
     }
     ft.ctrl->direct_passes += 1;
   }
+}
+
+// Row-sharded path: sums the `count` F'F | colSums(F) partials in order into the tail of the T buffer
+// (T | F'F | colSums(F) is then one contiguous all-reduce) and re-arms the F'F publication counter.
+__global__ void rn_pack_ff(const RnView vw, const RnFit ft, const int count) {
+  if (ft.ctrl->done) return;
+  const int nff = vw.k * vw.k + vw.k;
+  double* tail = vw.T + vw.pp * vw.kp;
+  for (int o = threadIdx.x; o < nff; o += blockDim.x) {
+    double s = 0.0;
+    for (int i = 0; i < count; ++i) s += vw.FFpart[(int64_t)i * nff + o];
+    tail[o] = s;
+  }
+  if (threadIdx.x == 0) vw.misc_ticket[2] = 0;
+}
+
+// Row-sharded path: the residual kernel left the all-reduced sum of squares in scal[3]; turn it into the error.
+__global__ void rn_residual_scale(const RnView vw, const RnFit ft, const int force) {
+  if (!force && (ft.ctrl->done || !vw.flags[0])) return;
+  const double e = vw.scal[3] / vw.scal[0];
+  vw.scal[1] = e;
+  vw.scal[3] = e;
 }
 
 // Iteration bookkeeping as its own launch (DIRECT error mode, and the AUTO hand-over).  <<<1,1>>>.

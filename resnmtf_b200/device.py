@@ -34,6 +34,21 @@ class Context:
     def synchronize(self):
         L.check(self._lib.resnmtf_ctx_synchronize(self._h))
 
+    # ---- row-sharded views over ranks (one process per GPU) ---------------------------------------
+    @staticmethod
+    def comm_id_create():
+        """Opaque NCCL unique id (bytes) created on one rank; broadcast it to the others by any means."""
+        lib = L.require_device()
+        buf = C.create_string_buffer(lib.resnmtf_comm_id_size())
+        L.check(lib.resnmtf_comm_id_create(buf))
+        return buf.raw
+
+    def join(self, comm_id, rank, n_ranks):
+        """After this, every fit created on the context is row-sharded: n[v] is the local row count, F rows
+        are local, G / S / lambda / mu are replicated and [X'F | F'F | colSums(F)] is all-reduced per sweep."""
+        buf = C.create_string_buffer(bytes(comm_id), len(comm_id))
+        L.check(self._lib.resnmtf_ctx_join(self._h, buf, int(rank), int(n_ranks)))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.resnmtf_ctx_destroy(self._h)

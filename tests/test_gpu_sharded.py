@@ -1,0 +1,93 @@
+"""Row-sharded view over 2 GPUs (NCCL all-reduce of [X'F | F'F | colSums(F)] per sweep) against the unsharded
+oracle.  Needs >= 2 visible GPUs: run with  gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from resnmtf_b200 import _lib as L  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+WORLD = 2
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def problem(k):
+    from resnmtf_b200 import synth
+
+    rng = np.random.default_rng(23)
+    n, p = 1000, 300  # 16 panels -> 8 + 8, ragged last panel
+    x = synth.prep(synth.planted_view(n, p, 4, rng, 0.3, 0.3)[0])
+    f, s, g = synth.random_factors(n, p, k, rng)
+    return x, f, s, g
+
+
+def worker(rank, world, port, out_dir, impl, err_mode, k):
+    import torch
+    import torch.distributed as dist
+
+    from helpers import rel_err
+    from oracle import resnmtf_oracle as O
+    from resnmtf_b200 import sharding
+    from resnmtf_b200.device import Context, DeviceFit
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = Context(rank)
+    ids = [Context.comm_id_create() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.join(ids[0], rank, world)
+    x, f, s, g = problem(k)
+    b, e = sharding.row_shards(x.shape[0], world)[rank]
+    z = np.zeros((1, 1))
+    states = []
+    ref = O.res_nmtf_loop([x], None, None, [None], [None], [f], [s], [g], [k], z, z, z, n_iters=6,
+                          trace=lambda t, cf, cs, cg, cl, cm, er: states.append(
+                              (cf[0].copy(), cs[0].copy(), cg[0].copy(), cl[0].copy(), cm[0].copy(), er.copy())))
+    fit = DeviceFit(ctx, [e - b], [x.shape[1]], [k])
+    fit.set_options(err_mode=err_mode, impl=impl)
+    fit.set_data(0, x[b:e])
+    fit.set_factors(0, f[b:e], s, g)  # lambda/mu default to the GLOBAL colSums (all-reduced)
+    worst = 0.0
+    for t in range(6):
+        fit.step()
+        fl, sl, gl, lam, mu = fit.get_factors(0)
+        errs, _ = fit.view_errors()
+        cf, cs, cg, cl, cm, oerr = states[t]
+        for a, r in ((fl, cf[b:e]), (sl, cs), (gl, cg), (lam, cl), (mu, cm), (errs, oerr)):
+            worst = max(worst, rel_err(a, r))
+    fit.normalise()
+    fn, sn, gn, _, _ = fit.get_factors(0)
+    worst_n = max(rel_err(fn, ref["output_f"][0][b:e]), rel_err(sn, ref["output_s"][0]),
+                  rel_err(gn, ref["output_g"][0]))
+    fit.close()
+    ctx.close()
+    np.save(os.path.join(out_dir, f"worst{rank}.npy"), np.array([worst, worst_n]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(L.device_count() < WORLD, reason="needs 2 GPUs")
+@pytest.mark.parametrize("impl,err_mode,k", [(L.IMPL_TMA, L.ERR_AUTO, 5), (L.IMPL_DMMA, L.ERR_DIRECT, 3),
+                                             (L.IMPL_DFMA, L.ERR_DIRECT, 9)])
+def test_row_sharded_view_matches_oracle(tmp_path, impl, err_mode, k):
+    import torch.multiprocessing as mp
+
+    mp.spawn(worker, args=(WORLD, free_port(), str(tmp_path), impl, err_mode, k), nprocs=WORLD, join=True)
+    for r in range(WORLD):
+        worst = np.load(os.path.join(tmp_path, f"worst{r}.npy"))
+        assert worst[0] <= 1e-9 and worst[1] <= 1e-9, (r, worst)
