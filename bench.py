@@ -198,7 +198,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from resnmtf_b200 import _lib as L
-    from resnmtf_b200.device import Context, DeviceFit
+    from resnmtf_b200.device import Context, DeviceData, DeviceFit
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,19 +280,24 @@ def run_gpu(args):
         h2d = d2h = 0
 
         def e2e_once():
+            # what apply_resnmtf's k-sweep does (R/main.r:279-287): the same host data for every k -- uploaded
+            # once into a shared handle -- then one fit per k with its own host inits and host results
             nonlocal h2d, d2h
+            data = DeviceData(ctx, x_pinned)
+            h2d += x_pinned.nbytes
             for k in K_SWEEP:
                 f0, s0, g0 = inits[k]
                 fit = DeviceFit(ctx, [N_ROWS], [N_COLS], [k])
-                fit.set_data(0, x_pinned)
+                fit.attach_data(0, data)
                 fit.set_factors(0, f0, s0, g0)
                 fit.run(e2e_steps)
                 errs = fit.errors()
                 fit.normalise()
                 f, s, g, lam, mu = fit.get_factors(0)
                 fit.close()
-                h2d += x_pinned.nbytes + f0.nbytes + s0.nbytes + g0.nbytes
+                h2d += f0.nbytes + s0.nbytes + g0.nbytes
                 d2h += f.nbytes + s.nbytes + g.nbytes + lam.nbytes + mu.nbytes + errs.nbytes
+            data.close()
 
         e2e_once()  # warm-up
         h2d = d2h = 0
@@ -307,7 +312,8 @@ def run_gpu(args):
             dt = float(t.item())
         e2e = {"value": world * e2e_steps * len(K_SWEEP) / dt, "unit": UNIT,
                "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-               "call": f"one C-ABI fit per k: set_data(host X) + set_factors + run(n_iters={e2e_steps}) + "
+               "call": f"k-sweep through the C ABI: data_create(host X) once, then per k fit_create + attach_data + "
+                       f"set_factors(host) + run(n_iters={e2e_steps}) + "
                        "normalise + get_factors/get_errors", "seconds": dt}
 
     # ---- reduce over ranks -------------------------------------------------------------------------------

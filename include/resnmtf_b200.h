@@ -96,6 +96,16 @@ int resnmtf_fit_set_data(resnmtf_fit* fit, int v, const double* x, int64_t ld);
 /* Same, but x is a DEVICE pointer on the fit's device (no host round trip). */
 int resnmtf_fit_set_data_device(resnmtf_fit* fit, int v, const double* x_dev, int64_t ld);
 
+/* A view's data uploaded ONCE and shared by several fits: apply_resnmtf() fits the same `data` for every k
+ * of its sweep (R/main.r:279-287) and again in the k-extension loop (:306-320).  The handle is reference
+ * counted: it may be destroyed while fits are still attached.  resnmtf_fit_attach_data replaces set_data
+ * for that view (data_norms comes with the handle). */
+typedef struct resnmtf_data resnmtf_data;
+int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
+                        resnmtf_data** out);
+int resnmtf_data_destroy(resnmtf_data* data);
+int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* data);
+
 /* Initial factors of view v: F n x k, S k x k, G p x k, lambda k, mu k (what init_mats(),
  * R/update_steps.r:36-66, hands to the loop).  lambda / mu may be NULL: they are then set to
  * colSums(F) / colSums(G) as R/update_steps.r:53-54 does.  Resets the iteration counter. */

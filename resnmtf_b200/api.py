@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib as L
 from . import prep
 from .bicluster import obtain_biclusters
-from .device import DeviceFit, default_context
+from .device import DeviceData, DeviceFit, default_context
 from .prep import NamedMatrix, as_named
 from .stability import stability_check
 
@@ -96,9 +96,11 @@ def _names_or_default(data):
 def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, init_g=None, k_vec=None,
                    phi=None, xi=None, psi=None, n_iters=None, num_repeats=5, spurious=True,
                    distance="euclidean", no_clusts=False, *, rng=None, ctx=None, max_iters=0,
-                   err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO):
+                   err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO, device_data=None):
     """R/main.r:32-140.  ``data``: list of (already prepped) views; ``row_indices`` / ``column_indices``:
-    per view a dict {other view: shared names or None}, as produced by ``prep.reorder_data``."""
+    per view a dict {other view: shared names or None}, as produced by ``prep.reorder_data``.
+    ``device_data``: optional list of ``DeviceData`` (the views already uploaded, shared between the fits of
+    one apply_resnmtf call)."""
     rng = np.random.default_rng() if rng is None else rng
     ctx = default_context() if ctx is None else ctx
     data = [as_named(m) for m in data]
@@ -114,7 +116,10 @@ def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, 
     try:
         fit.set_options(err_mode=err_mode, impl=impl)
         for v in range(n_v):
-            fit.set_data(v, xs[v])  # data_norms (R/main.r:48) are computed on the device
+            if device_data is not None:
+                fit.attach_data(v, device_data[v])
+            else:
+                fit.set_data(v, xs[v])  # data_norms (R/main.r:48) are computed on the device
             fit.set_factors(v, cf[v], cs[v], cg[v], clam[v], cmu[v])
         fit.set_restrictions(phi, xi, psi)
         rn, cn = _names_or_default(data)
@@ -196,6 +201,8 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
                                       no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng, ctx=ctx)
         return results
     ks = list(range(int(k_min), int(k_max) + 1))
+    # every fit of the sweep (and of the k-extension loop) uses the same data: upload the views once
+    common["device_data"] = [DeviceData(ctx, m.x) for m in data]
     res_list = []
     for k in ks:  # the reference's %dopar% branch is unreachable (R/main.r:275-299): serial sweep
         res_list.append(res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f,

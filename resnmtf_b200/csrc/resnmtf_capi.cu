@@ -95,8 +95,26 @@ struct resnmtf_ctx {
   rn_ncclComm_t comm = nullptr;
 };
 
+// A view's X in the device layout, shareable between fits (the k-sweep of apply_resnmtf fits the same
+// data for every k, R/main.r:279-287): reference-counted, freed when the last holder lets go.
+struct resnmtf_data {
+  resnmtf_ctx* ctx = nullptr;
+  int64_t n = 0, p = 0, ldx = 0, pp = 0;
+  double* X = nullptr;
+  double xnorm2 = 0.0;
+  int refs = 1;
+};
+
+static void rn_data_release(resnmtf_data* d) {
+  if (d && --d->refs == 0) {
+    if (d->X) cudaFree(d->X);
+    delete d;
+  }
+}
+
 struct ViewHost {
   RnView d;  // device pointers + geometry (passed by value to the kernels)
+  resnmtf_data* shared = nullptr;  // non-null: X belongs to a shared data handle
   bool has_data = false, has_factors = false;
   std::vector<int32_t*> rowmaps, colmaps;  // [V] device maps of this view into view w (or null)
   double* xpart = nullptr;                 // ||X||^2 partials
@@ -441,7 +459,7 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
     vh.rowmaps.assign(V, nullptr);
     vh.colmaps.assign(V, nullptr);
     const int K = k[v], KP = vh.d.kp;
-    if ((rc = rn_alloc(f, &vh.d.X, (size_t)vh.d.ldx * vh.d.pp))) break;
+    // X is allocated by set_data (or borrowed from a shared resnmtf_data handle by attach_data)
     if ((rc = rn_alloc(f, &vh.d.F, (size_t)vh.d.ldx * KP))) break;
     if ((rc = rn_alloc(f, &vh.d.G, (size_t)vh.d.pp * KP))) break;
     if ((rc = rn_alloc(f, &vh.d.T, (size_t)vh.d.pp * KP + K * K + K))) break;
@@ -506,7 +524,70 @@ extern "C" int resnmtf_fit_destroy(resnmtf_fit* fit) {
   if (fit->graph_exec) cudaGraphExecDestroy(fit->graph_exec);
   if (fit->graph) cudaGraphDestroy(fit->graph);
   for (void* p : fit->allocs) cudaFree(p);
+  for (ViewHost& vh : fit->views) rn_data_release(vh.shared);
   delete fit;
+  return RESNMTF_OK;
+}
+
+// Copies a column-major matrix (host or device) into the swizzled panel layout at g.X (already zeroed) and
+// leaves ||X||_F^2 (all-reduced when the context is row-sharded) in g.scal[0].  `g` needs n, p, pp, ldx,
+// row_tiles, X, scal.  Host sources go through two <= 128 MB device staging buffers so that the H2D copy of
+// chunk c+1 overlaps the re-tiling of chunk c.
+static int upload_panels(resnmtf_ctx* ctx, const RnView& g, const double* x, int64_t ld, bool on_device,
+                         double* xpart, int32_t* xticket, const char* who) {
+  cudaStream_t st = ctx->stream;
+  const int64_t n = g.n, p = g.p;
+  if (on_device) {
+    const int blocks = (int)std::min<int64_t>(((int64_t)g.row_tiles * p * 32 + 255) / 256, 1 << 20);
+    rn_to_panels<<<blocks, 256, 0, st>>>(g, x, ld, 0, p);
+    RN_CUDA(cudaGetLastError());
+  } else {
+    const int64_t max_cols = std::max<int64_t>(1, ((int64_t)128 << 20) / (n * (int64_t)sizeof(double)));
+    const int64_t chunk = std::min<int64_t>(p, max_cols);
+    const int nbuf = chunk < p ? 2 : 1;
+    double* stage[2] = {nullptr, nullptr};
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, tiled[2] = {nullptr, nullptr};
+    cudaError_t e = cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking);
+    for (int b = 0; b < nbuf && e == cudaSuccess; ++b) {
+      e = cudaMalloc(&stage[b], (size_t)chunk * n * sizeof(double));
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&tiled[b], cudaEventDisableTiming);
+    }
+    int64_t ci = 0;
+    for (int64_t c0 = 0; c0 < p && e == cudaSuccess; c0 += chunk, ++ci) {
+      const int b = (int)(ci % nbuf);
+      const int64_t nc = std::min(chunk, p - c0);
+      if (ci >= nbuf) e = cudaStreamWaitEvent(copy_st, tiled[b], 0);  // the buffer's previous chunk is re-tiled
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(stage[b], (size_t)n * sizeof(double), x + c0 * ld, (size_t)ld * sizeof(double),
+                              (size_t)n * sizeof(double), (size_t)nc, cudaMemcpyHostToDevice, copy_st);
+      if (e == cudaSuccess) e = cudaEventRecord(copied[b], copy_st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
+      if (e == cudaSuccess) {
+        const int blocks = (int)std::min<int64_t>(((int64_t)g.row_tiles * nc * 32 + 255) / 256, 1 << 20);
+        rn_to_panels<<<blocks, 256, 0, st>>>(g, stage[b], n, c0, nc);
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(tiled[b], st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(copy_st);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    for (int b = 0; b < 2; ++b) {
+      if (stage[b]) cudaFree(stage[b]);
+      if (copied[b]) cudaEventDestroy(copied[b]);
+      if (tiled[b]) cudaEventDestroy(tiled[b]);
+    }
+    if (copy_st) cudaStreamDestroy(copy_st);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = e3;
+    if (e != cudaSuccess) return rn_fail(RESNMTF_E_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  }
+  rn_xnorm2<<<1024, 256, 0, st>>>(g, xpart, xticket);
+  RN_CUDA(cudaGetLastError());
+  int rc = rn_allreduce(ctx, g.scal, 1);  // data_norms of the whole view when row-sharded
+  if (rc) return rc;
+  RN_CUDA(cudaStreamSynchronize(st));  // the caller's buffer is only borrowed for the call
   return RESNMTF_OK;
 }
 
@@ -517,46 +598,96 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
   ViewHost& vh = fit->views[v];
   RN_CHECK(ld >= vh.d.n, RESNMTF_E_INVALID, std::string(who) + ": ld < n");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
-  cudaStream_t st = fit->ctx->stream;
-  const int64_t n = vh.d.n, p = vh.d.p;
-  // padding columns / rows were zeroed at allocation; rn_to_panels rewrites the padding rows as zero
-  if (on_device) {
-    const int blocks = (int)std::min<int64_t>(((int64_t)vh.d.row_tiles * p * 32 + 255) / 256, 1 << 20);
-    rn_to_panels<<<blocks, 256, 0, st>>>(vh.d, x, ld, 0, p);
-    RN_CUDA(cudaGetLastError());
-  } else {
-    // stage column chunks (<= 256 MB) in device memory, re-tile each into the panel layout
-    const int64_t max_cols = std::max<int64_t>(1, ((int64_t)256 << 20) / (n * (int64_t)sizeof(double)));
-    const int64_t chunk = std::min<int64_t>(p, max_cols);
-    double* stage = nullptr;
-    RN_CUDA(cudaMalloc(&stage, (size_t)chunk * n * sizeof(double)));
-    for (int64_t c0 = 0; c0 < p; c0 += chunk) {
-      const int64_t nc = std::min(chunk, p - c0);
-      cudaError_t e = cudaMemcpy2DAsync(stage, (size_t)n * sizeof(double), x + c0 * ld, (size_t)ld * sizeof(double),
-                                        (size_t)n * sizeof(double), (size_t)nc, cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) {
-        const int blocks = (int)std::min<int64_t>(((int64_t)vh.d.row_tiles * nc * 32 + 255) / 256, 1 << 20);
-        rn_to_panels<<<blocks, 256, 0, st>>>(vh.d, stage, n, c0, nc);
-        e = cudaGetLastError();
-      }
-      if (e != cudaSuccess) {
-        cudaStreamSynchronize(st);
-        cudaFree(stage);
-        return rn_fail(RESNMTF_E_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
-      }
-    }
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(stage);
-    if (e != cudaSuccess) return rn_fail(RESNMTF_E_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  if (vh.shared) {  // the view was attached to a shared handle: give it its own buffer again
+    rn_data_release(vh.shared);
+    vh.shared = nullptr;
+    vh.d.X = nullptr;
   }
-  rn_xnorm2<<<1024, 256, 0, st>>>(vh.d, vh.xpart, vh.xticket);
-  RN_CUDA(cudaGetLastError());
-  {
-    int rc2 = rn_allreduce(fit->ctx, vh.d.scal, 1);  // data_norms of the whole view when row-sharded
-    if (rc2) return rc2;
+  if (!vh.d.X) {
+    int rc = rn_alloc(fit, &vh.d.X, (size_t)vh.d.ldx * vh.d.pp);  // zeroed: padding rows / columns stay zero
+    if (rc) return rc;
+    fit->meta_dirty = true;  // X is a by-value kernel parameter: the iteration graph must be rebuilt
   }
-  RN_CUDA(cudaStreamSynchronize(st));  // the caller's buffer is only borrowed for the call
+  int rc = upload_panels(fit->ctx, vh.d, x, ld, on_device, vh.xpart, vh.xticket, who);
+  if (rc) return rc;
   vh.has_data = true;
+  return RESNMTF_OK;
+}
+
+// ---- shared device data -------------------------------------------------------------------------
+extern "C" int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
+                                   resnmtf_data** out) {
+  RN_CHECK(ctx && x && out, RESNMTF_E_INVALID, "resnmtf_data_create: NULL argument");
+  RN_CHECK(n >= 1 && p >= 1 && ld >= n, RESNMTF_E_INVALID, "resnmtf_data_create: bad shape");
+  RN_CUDA(cudaSetDevice(ctx->device));
+  resnmtf_data* d = new (std::nothrow) resnmtf_data();
+  RN_CHECK(d != nullptr, RESNMTF_E_NOMEM, "resnmtf_data_create: out of host memory");
+  d->ctx = ctx;
+  d->n = n;
+  d->p = p;
+  d->ldx = rn_round_up(n, RN_ROW_TILE);
+  d->pp = rn_round_up(p, 32);
+  double* scratch = nullptr;  // [0..7] scal, then 1024 partials, then the ticket
+  const size_t xbytes = (size_t)d->ldx * d->pp * sizeof(double);
+  cudaError_t e = cudaMalloc(&d->X, xbytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d->X, 0, xbytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&scratch, (8 + 1024 + 2) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemsetAsync(scratch, 0, (8 + 1024 + 2) * sizeof(double), ctx->stream);
+  int rc = RESNMTF_OK;
+  if (e != cudaSuccess) {
+    rc = rn_fail(e == cudaErrorMemoryAllocation ? RESNMTF_E_NOMEM : RESNMTF_E_CUDA,
+                 std::string("resnmtf_data_create: ") + cudaGetErrorString(e));
+  } else {
+    RnView g;
+    std::memset(&g, 0, sizeof(g));
+    g.n = n;
+    g.p = p;
+    g.ldx = d->ldx;
+    g.pp = d->pp;
+    g.row_tiles = (int)(d->ldx / RN_ROW_TILE);
+    g.X = d->X;
+    g.scal = scratch;
+    rc = upload_panels(ctx, g, x, ld, false, scratch + 8, reinterpret_cast<int32_t*>(scratch + 8 + 1024),
+                       "resnmtf_data_create");
+    if (rc == RESNMTF_OK && cudaMemcpy(&d->xnorm2, scratch, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = rn_fail(RESNMTF_E_CUDA, "resnmtf_data_create: reading back ||X||^2 failed");
+  }
+  if (scratch) cudaFree(scratch);
+  if (rc) {
+    rn_data_release(d);
+    return rc;
+  }
+  *out = d;
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_data_destroy(resnmtf_data* data) {
+  if (data) {
+    cudaSetDevice(data->ctx->device);
+    rn_data_release(data);
+  }
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* data) {
+  RN_CHECK(fit && data, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: NULL argument");
+  RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: view index out of range");
+  RN_CHECK(data->ctx == fit->ctx, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: data lives on another context");
+  ViewHost& vh = fit->views[v];
+  RN_CHECK(data->n == vh.d.n && data->p == vh.d.p, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: shape mismatch");
+  RN_CUDA(cudaSetDevice(fit->ctx->device));
+  RN_CUDA(cudaStreamSynchronize(fit->ctx->stream));
+  if (vh.shared) rn_data_release(vh.shared);
+  else if (vh.d.X) {
+    int rc = rn_free(fit, vh.d.X);
+    if (rc) return rc;
+  }
+  vh.shared = data;
+  data->refs += 1;
+  vh.d.X = data->X;
+  RN_CUDA(cudaMemcpy(vh.d.scal, &data->xnorm2, sizeof(double), cudaMemcpyHostToDevice));
+  vh.has_data = true;
+  fit->meta_dirty = true;
   return RESNMTF_OK;
 }
 

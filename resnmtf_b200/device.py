@@ -77,6 +77,31 @@ def default_context():
     return _default_ctx
 
 
+class DeviceData:
+    """One view uploaded once into the device layout and shared by several fits (the k-sweep of
+    apply_resnmtf fits the same data for every k).  Reference counted on the C side."""
+
+    def __init__(self, ctx, x):
+        self._lib = L.require_device()
+        self.ctx = ctx
+        x = _f64(x)
+        self.shape = x.shape
+        h = C.c_void_p()
+        L.check(self._lib.resnmtf_data_create(ctx._h, x.shape[0], x.shape[1], _ptr(x), x.shape[0], C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.resnmtf_data_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceFit:
     """Device-resident state of one fit.  Shapes: view v is n[v] x p[v] with k[v] clusters."""
 
@@ -104,6 +129,12 @@ class DeviceFit:
         if x.shape != (self.n[v], self.p[v]):
             raise ValueError(f"view {v}: expected shape {(self.n[v], self.p[v])}, got {x.shape}")
         L.check(self._lib.resnmtf_fit_set_data(self._h, v, _ptr(x), x.shape[0]))
+
+    def attach_data(self, v, data):
+        """Use a shared DeviceData as view v (no copy)."""
+        if tuple(data.shape) != (self.n[v], self.p[v]):
+            raise ValueError(f"view {v}: expected shape {(self.n[v], self.p[v])}, got {tuple(data.shape)}")
+        L.check(self._lib.resnmtf_fit_attach_data(self._h, v, data._h))
 
     def set_data_device(self, v, dev_ptr, ld):
         """Column-major float64 matrix already resident on this context's GPU."""

@@ -215,3 +215,33 @@ def test_state_errors(ctx):
     with pytest.raises(L.ResnmtfError) as e:
         DeviceFit(ctx, [10], [5], [17])
     assert e.value.code == L.E_UNSUPPORTED
+
+
+def test_shared_data_handle_matches_private_copy(ctx):
+    """resnmtf_data: one upload shared by the fits of a k-sweep gives bit-identical results to set_data, and
+    survives being destroyed while fits are still attached (reference counting)."""
+    from resnmtf_b200.device import DeviceData, DeviceFit
+
+    prob = single_view_problem(700, 333, 4, seed=55)
+    x = prob.data[0]
+    data = DeviceData(ctx, x)
+    outs = []
+    for shared in (False, True, True):
+        fit = DeviceFit(ctx, [x.shape[0]], [x.shape[1]], [4])
+        if shared:
+            fit.attach_data(0, data)
+        else:
+            fit.set_data(0, x)
+        fit.set_factors(0, prob.init_f[0], prob.init_s[0], prob.init_g[0])
+        if len(outs) == 1:
+            data.close()  # the second fit keeps the buffer alive on its own
+        fit.run(12)
+        outs.append((fit.get_factors(0), fit.errors(), fit.view_errors()[1]))
+        if len(outs) == 2:
+            data = DeviceData(ctx, x)  # a fresh handle for the third fit
+        fit.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0][0], o[0]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
+    data.close()
