@@ -55,6 +55,13 @@ __device__ __forceinline__ int64_t rn_fidx(int64_t r, int c, int kp) {
   return ((r >> 6) * kp + c) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ rn_sigma(c)) + (r & 1);
 }
 
+// Position of (row, col) of a 64 x 8 tile in the fragment-major order the MMA F-step kernels accumulate in:
+// lane (g,t) of a warp holds rows 16m + 2g + h, columns 2t + j in register (m, h, j).
+__device__ __forceinline__ int rn_ps_index(int row, int col) {
+  const int m = row >> 4, g = (row & 15) >> 1, h = row & 1, t = col >> 1, j = col & 1;
+  return ((m * 2 + h) * 2 + j) * 32 + 4 * g + t;
+}
+
 __device__ __forceinline__ double rn_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -449,9 +456,9 @@ __global__ void __launch_bounds__(256, 2) rn_f_step_sk(const RnView vw, const Rn
         for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int row = 16 * m + 2 * g + h;
-            Ps[row * KP + 2 * t] += acc[m][h][0];
-            Ps[row * KP + 2 * t + 1] += acc[m][h][1];
+            // fragment-major layout: (register, lane) -> conflict-free; rn_ps_index maps (row, col) back
+            Ps[((m * 2 + h) * 2 + 0) * 32 + lane] += acc[m][h][0];
+            Ps[((m * 2 + h) * 2 + 1) * 32 + lane] += acc[m][h][1];
           }
       }
       __syncthreads();
@@ -484,7 +491,7 @@ __global__ void __launch_bounds__(256, 2) rn_f_step_sk(const RnView vw, const Rn
       if (r < vw.n) {
         double P[K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) P[c] = Ps[tid * KP + c];
+        for (int c = 0; c < K; ++c) P[c] = Ps[rn_ps_index(tid, c)];
         rn_update_f_row<K>(vw, ft, v, r, P, Ssm, Wsm, lamh);
       }
     }
@@ -884,9 +891,9 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
         for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int row = 16 * m + 2 * g + h;
-            Ps[row * KP + 2 * t] += acc[m][h][0];
-            Ps[row * KP + 2 * t + 1] += acc[m][h][1];
+            // fragment-major layout: (register, lane) -> conflict-free; rn_ps_index maps (row, col) back
+            Ps[((m * 2 + h) * 2 + 0) * 32 + lane] += acc[m][h][0];
+            Ps[((m * 2 + h) * 2 + 1) * 32 + lane] += acc[m][h][1];
           }
       }
       rn_consumer_sync();
@@ -919,7 +926,7 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
       if (r < vw.n) {
         double P[K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) P[c] = Ps[tid * KP + c];
+        for (int c = 0; c < K; ++c) P[c] = Ps[rn_ps_index(tid, c)];
         rn_update_f_row<K>(vw, ft, v, r, P, Ssm, Wsm, lamh);
       }
     }

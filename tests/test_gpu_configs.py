@@ -1,0 +1,84 @@
+"""The BASELINE.json configurations as parity cases: C2 at full size (20000 x 4000), C3 / C4 with the exact
+restriction structure of SURVEY 8(d) at reduced size (the oracle materialises X_hat, so full size would not
+fit the time budget), plus size-independent properties at full size (two independently written kernel paths
+agree; unit column sums after normalisation_check; the algebraic and the direct error agree)."""
+import numpy as np
+import pytest
+
+from helpers import RTOL, Problem, compare_trace, rel_err
+from oracle import resnmtf_oracle as O
+from resnmtf_b200 import _lib as L
+from resnmtf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def planted(n, p, n_planted, seed, rows=None, cols=None, sigma=1.0):
+    rng = np.random.default_rng(seed)
+    return synth.planted_view(n, p, n_planted, rng, 0.2, 0.2, 5.0, sigma, rows=rows, cols=cols)
+
+
+def test_c2_full_size_two_sweeps_vs_oracle_and_paths_agree(ctx):
+    n, p, k = 20000, 4000, 5
+    x, _, _ = planted(n, p, 5, synth.config_seed(2, 0))
+    x = synth.prep(x)
+    f, s, g = synth.random_factors(n, p, k, np.random.default_rng(1))
+    prob = Problem([x], [k], [f], [s], [g])
+    compare_trace(prob, ctx, n_iters=2, err_mode=L.ERR_AUTO, impl=L.IMPL_TMA)
+    outs = {}
+    for impl, mode in ((L.IMPL_TMA, L.ERR_ALGEBRAIC), (L.IMPL_DMMA, L.ERR_DIRECT), (L.IMPL_DFMA, L.ERR_DIRECT)):
+        fit = prob.device_fit(ctx, err_mode=mode, impl=impl)
+        fit.run(5)
+        errs = fit.errors()
+        fit.normalise()
+        outs[impl] = (fit.get_factors(0), errs)
+        fit.close()
+    ref = outs[L.IMPL_TMA]
+    for impl in (L.IMPL_DMMA, L.IMPL_DFMA):
+        for a, b in zip(outs[impl][0][:3], ref[0][:3]):
+            assert rel_err(a, b) <= RTOL
+        assert rel_err(outs[impl][1], ref[1]) <= RTOL  # direct vs algebraic error
+    np.testing.assert_allclose(ref[0][0].sum(0), np.ones(k), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ref[0][2].sum(0), np.ones(k), rtol=0, atol=1e-12)
+
+
+def test_c3_structure_four_views_phi_psi(ctx):
+    """4 views; 1-2 and 3-4 share rows (phi = 200), 1&3 and 2&4 share columns (psi = 200); k = 5."""
+    n, p, k = 12500, 1250, 5
+    _, r12, _ = planted(8, 8, 5, 1)  # placeholders replaced below
+    rng = np.random.default_rng(synth.config_seed(3, 0))
+    rows_a = (rng.random((n, 5)) < 0.2).astype(float)
+    rows_b = (rng.random((n, 5)) < 0.2).astype(float)
+    cols_a = (rng.random((p, 5)) < 0.2).astype(float)
+    cols_b = (rng.random((p, 5)) < 0.2).astype(float)
+    layout = [(rows_a, cols_a), (rows_a, cols_b), (rows_b, cols_a), (rows_b, cols_b)]
+    data = [synth.prep(planted(n, p, 5, synth.config_seed(3, v), rows=r, cols=c)[0]) for v, (r, c) in enumerate(layout)]
+    rn = [[f"a{i}" for i in range(n)], [f"a{i}" for i in range(n)], [f"b{i}" for i in range(n)],
+          [f"b{i}" for i in range(n)]]
+    cn = [[f"u{i}" for i in range(p)], [f"w{i}" for i in range(p)], [f"u{i}" for i in range(p)],
+          [f"w{i}" for i in range(p)]]
+    phi = np.zeros((4, 4)); phi[0, 1] = 200.0; phi[2, 3] = 200.0
+    psi = np.zeros((4, 4)); psi[0, 2] = 200.0; psi[1, 3] = 200.0
+    irng = np.random.default_rng(7)
+    inits = [synth.random_factors(n, p, k, irng) for _ in range(4)]
+    prob = Problem(data, [k] * 4, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
+                   phi=O.init_rest_mats(phi, 4), psi=O.init_rest_mats(psi, 4), row_names=rn, col_names=cn)
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_AUTO)
+
+
+def test_c4_structure_eight_views_phi_xi_psi(ctx):
+    """8 views, all sharing rows and columns, phi = psi = 200 and xi = 50 on every pair; k = 8."""
+    n, p, k, V = 6250, 500, 8, 8
+    rng = np.random.default_rng(synth.config_seed(4, 0))
+    rows = (rng.random((n, 8)) < 0.2).astype(float)
+    cols = (rng.random((p, 8)) < 0.2).astype(float)
+    data = [synth.prep(planted(n, p, 8, synth.config_seed(4, v), rows=rows, cols=cols)[0]) for v in range(V)]
+    rn = [[f"r{i}" for i in range(n)]] * V
+    cn = [[f"c{i}" for i in range(p)]] * V
+    up = np.triu(np.ones((V, V)), 1)
+    irng = np.random.default_rng(8)
+    inits = [synth.random_factors(n, p, k, irng) for _ in range(V)]
+    prob = Problem(data, [k] * V, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
+                   phi=O.init_rest_mats(200.0 * up, V), xi=O.init_rest_mats(50.0 * up, V),
+                   psi=O.init_rest_mats(200.0 * up, V), row_names=rn, col_names=cn)
+    compare_trace(prob, ctx, n_iters=3, err_mode=L.ERR_AUTO)
