@@ -77,6 +77,8 @@ int resnmtf_ctx_destroy(resnmtf_ctx* ctx);
 /* cudaStream_t the context launches on, as an opaque pointer (for CUDA-event timing by the caller). */
 void* resnmtf_ctx_stream(resnmtf_ctx* ctx);
 int resnmtf_ctx_synchronize(resnmtf_ctx* ctx);
+/* CUDA device index of the context (-1 for NULL). */
+int resnmtf_ctx_device(resnmtf_ctx* ctx);
 /* Thread-local message of the last failure on the calling thread (never NULL). */
 const char* resnmtf_last_error(void);
 /* Library version string, and the number of CUDA devices visible (0 when none / no driver). */

@@ -22,6 +22,7 @@ IMPL_AUTO, IMPL_DFMA, IMPL_DMMA, IMPL_TMA = 0, 1, 2, 3
 # every symbol include/resnmtf_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "resnmtf_ctx_create", "resnmtf_ctx_destroy", "resnmtf_ctx_stream", "resnmtf_ctx_synchronize",
+    "resnmtf_ctx_device",
     "resnmtf_last_error", "resnmtf_version", "resnmtf_device_count",
     "resnmtf_fit_create", "resnmtf_fit_destroy", "resnmtf_fit_set_data", "resnmtf_fit_set_data_device",
     "resnmtf_data_create", "resnmtf_data_destroy", "resnmtf_fit_attach_data",
@@ -78,6 +79,7 @@ def load():
         "resnmtf_ctx_destroy": (C.c_int, [vp]),
         "resnmtf_ctx_stream": (vp, [vp]),
         "resnmtf_ctx_synchronize": (C.c_int, [vp]),
+        "resnmtf_ctx_device": (C.c_int, [vp]),
         "resnmtf_last_error": (C.c_char_p, []),
         "resnmtf_version": (C.c_char_p, []),
         "resnmtf_device_count": (C.c_int, []),

@@ -12,9 +12,9 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
-from . import prep
+from . import prep, sharding
 from .bicluster import obtain_biclusters
-from .device import DeviceData, DeviceFit, default_context
+from .device import DeviceData, DeviceFit, default_context, device_contexts
 from .prep import NamedMatrix, as_named
 from .stability import stability_check
 
@@ -201,13 +201,46 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
                                       no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng, ctx=ctx)
         return results
     ks = list(range(int(k_min), int(k_max) + 1))
-    # every fit of the sweep (and of the k-extension loop) uses the same data: upload the views once
-    common["device_data"] = [DeviceData(ctx, m.x) for m in data]
-    res_list = []
-    for k in ks:  # the reference's %dopar% branch is unreachable (R/main.r:275-299): serial sweep
-        res_list.append(res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f,
-                                       init_s, init_g, [k] * n_v, phi, xi, psi, n_iters, num_repeats,
-                                       spurious, distance, no_clusts, **common))
+    if no_clusts:
+        # the reference fails here too: results carry no bisil, which.max(NULL) is integer(0) and the
+        # `while (test == max_k)` at R/main.r:307 stops with "argument is of length zero"
+        raise ValueError("argument is of length zero")
+    # The fits of the sweep are independent: every k gets its own child generator -- so the result
+    # does not depend on how many GPUs run the sweep -- and, with use_parallel and more than one visible
+    # GPU, the fits are placed longest-first on one context per GPU (the reference's %dopar% intent,
+    # R/main.r:288-299, which is unreachable there).  Each device uploads the views once and shares them.
+    child_rngs = rng.spawn(len(ks))
+    contexts = [ctx]
+    if use_parallel:
+        contexts = device_contexts(ctx)
+    shapes = [m.shape for m in data]
+    where, _ = sharding.assign_fits([sharding.fit_cost(shapes, k) for k in ks], len(contexts))
+    dev_data = {}
+
+    def fit_k(i):
+        c = contexts[where[i]]
+        if where[i] not in dev_data:
+            dev_data[where[i]] = [DeviceData(c, m.x) for m in data]
+        return res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f, init_s,
+                              init_g, [ks[i]] * n_v, phi, xi, psi, n_iters, num_repeats, spurious, distance,
+                              no_clusts, rng=child_rngs[i], ctx=c, max_iters=max_iters,
+                              device_data=dev_data[where[i]])
+
+    if len(contexts) == 1:
+        res_list = [fit_k(i) for i in range(len(ks))]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        res_list = [None] * len(ks)
+
+        def run_rank(r):  # one host thread per GPU; ctypes releases the GIL inside the library
+            for i in range(len(ks)):
+                if where[i] == r:
+                    res_list[i] = fit_k(i)
+
+        with ThreadPoolExecutor(max_workers=len(contexts)) as pool:
+            list(pool.map(run_rank, range(len(contexts))))
+    common["device_data"] = dev_data.get(0) or [DeviceData(ctx, m.x) for m in data]
     err_list = extract_bisils(res_list, ks)
     test = ks[int(np.argmax(err_list))]
     max_k = int(k_max)

@@ -411,6 +411,8 @@ extern "C" int resnmtf_ctx_destroy(resnmtf_ctx* ctx) {
 
 extern "C" void* resnmtf_ctx_stream(resnmtf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+extern "C" int resnmtf_ctx_device(resnmtf_ctx* ctx) { return ctx ? ctx->device : -1; }
+
 extern "C" int resnmtf_ctx_synchronize(resnmtf_ctx* ctx) {
   RN_CHECK(ctx != nullptr, RESNMTF_E_INVALID, "resnmtf_ctx_synchronize: ctx is NULL");
   RN_CUDA(cudaSetDevice(ctx->device));

@@ -25,6 +25,7 @@ class Context:
         h = C.c_void_p()
         L.check(lib.resnmtf_ctx_create(int(device), C.byref(h)))
         self._h = h
+        self.device = int(lib.resnmtf_ctx_device(h))
 
     @property
     def stream(self):
@@ -75,6 +76,23 @@ def default_context():
     if _default_ctx is None:
         _default_ctx = Context()
     return _default_ctx
+
+
+_device_ctx = {}
+
+
+def device_contexts(first):
+    """One context per visible GPU, ``first`` (and its device) leading: the placement targets of the
+    independent fits of an apply_resnmtf call."""
+    n = L.device_count()
+    out = [first]
+    for dev in range(n):
+        if dev == first.device:
+            continue
+        if dev not in _device_ctx:
+            _device_ctx[dev] = Context(dev)
+        out.append(_device_ctx[dev])
+    return out
 
 
 class DeviceData:

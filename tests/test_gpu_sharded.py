@@ -91,3 +91,23 @@ def test_row_sharded_view_matches_oracle(tmp_path, impl, err_mode, k):
     for r in range(WORLD):
         worst = np.load(os.path.join(tmp_path, f"worst{r}.npy"))
         assert worst[0] <= 1e-9 and worst[1] <= 1e-9, (r, worst)
+
+
+@pytest.mark.skipif(L.device_count() < WORLD, reason="needs 2 GPUs")
+def test_k_sweep_placed_on_two_gpus_equals_serial_sweep():
+    """apply_resnmtf's k-sweep with use_parallel on >= 2 GPUs (one host thread and one context per GPU, fits
+    placed longest-first) returns exactly what the single-GPU sweep returns: same selected k, same factors."""
+    from resnmtf_b200 import synth
+    from resnmtf_b200.api import apply_resnmtf
+    from resnmtf_b200.device import Context
+
+    views, _ = synth.block_views(2, seed=31)
+    ctx = Context(0)
+    kw = dict(k_max=5, spurious=False, stability=False, ctx=ctx)
+    par = apply_resnmtf(views, use_parallel=True, rng=np.random.default_rng(9), **kw)
+    ser = apply_resnmtf(views, use_parallel=False, rng=np.random.default_rng(9), **kw)
+    assert par["output_f"][0].shape == ser["output_f"][0].shape == (180, 3)
+    for key in ("output_f", "output_s", "output_g", "row_clusters", "col_clusters"):
+        for a, b in zip(par[key], ser[key]):
+            assert np.array_equal(a, b), key
+    assert par["bisil"] == ser["bisil"]
