@@ -89,6 +89,7 @@ static int rn_fail(int code, const std::string& msg) {
 struct resnmtf_ctx {
   int device = 0;
   int sm_count = 148;
+  size_t l2_persist_bytes = 0;  // persisting-L2 carve-out granted to this device (0: unavailable / disabled)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int rank = 0, n_ranks = 1;
@@ -115,6 +116,7 @@ static void rn_data_release(resnmtf_data* d) {
 struct ViewHost {
   RnView d;  // device pointers + geometry (passed by value to the kernels)
   resnmtf_data* shared = nullptr;  // non-null: X belongs to a shared data handle
+  size_t l2_window = 0;            // bytes at the head of X pinned in L2 (persisting access-policy window)
   bool has_data = false, has_factors = false;
   std::vector<int32_t*> rowmaps, colmaps;  // [V] device maps of this view into view w (or null)
   double* xpart = nullptr;                 // ||X||^2 partials
@@ -174,6 +176,11 @@ static int rn_free(resnmtf_fit* f, void* p) {
 
 static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+static int rn_env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : dflt;
+}
+
 // in-place sum over the ranks of a row-sharded context, on the context's stream (graph-capturable)
 static int rn_allreduce(resnmtf_ctx* ctx, void* buf, size_t count, bool is_int64 = false) {
   if (ctx->n_ranks <= 1) return RESNMTF_OK;
@@ -231,6 +238,30 @@ static GStepSkFn g_step_tma_fn(int K) {
   return nullptr;
 }
 
+// Launch of a streaming kernel with (optionally) a persisting-L2 access-policy window over the head of X.
+template <typename... Args>
+static void launch_windowed(void (*fn)(Args...), int grid, int block, size_t smem, cudaStream_t st, const void* win_ptr,
+                            size_t win_bytes, Args... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (win_bytes > 0) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(win_ptr);
+    attr[0].val.accessPolicyWindow.num_bytes = win_bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, fn, args...);
+}
+
 static inline bool use_mma(const ViewHost& vh, int impl) {
   return (impl == RESNMTF_IMPL_DMMA || impl == RESNMTF_IMPL_TMA) && vh.d.k <= 8;
 }
@@ -239,7 +270,8 @@ static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, 
   const int K = vh.d.k;
   if (use_mma(vh, impl)) {
     if (impl == RESNMTF_IMPL_TMA)
-      f_step_tma_fn(K)<<<vh.d.f_ctas, RN_TMA_THREADS, rn_f_tma_smem(K), st>>>(vh.d, ft, v);
+      launch_windowed(f_step_tma_fn(K), vh.d.f_ctas, RN_TMA_THREADS, rn_f_tma_smem(K), st, vh.d.X, vh.l2_window,
+                      vh.d, ft, v);
     else
       f_step_sk_fn(K)<<<vh.d.f_ctas, 256, 0, st>>>(vh.d, ft, v);
     return;
@@ -284,7 +316,8 @@ static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, i
   const bool sharded = ctx && ctx->n_ranks > 1;
   if (use_mma(vh, impl) && !sharded) {
     if (impl == RESNMTF_IMPL_TMA)
-      g_step_tma_fn(K)<<<vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st>>>(vh.d, ft, v, fuse);
+      launch_windowed(g_step_tma_fn(K), vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st, vh.d.X, vh.l2_window,
+                      vh.d, ft, v, fuse);
     else
       g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, fuse);
     return 1;
@@ -293,7 +326,8 @@ static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, i
     int n = 0, count;
     if (use_mma(vh, impl)) {
       if (impl == RESNMTF_IMPL_TMA)
-        g_step_tma_fn(K)<<<vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st>>>(vh.d, ft, v, -1);
+        launch_windowed(g_step_tma_fn(K), vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st, vh.d.X, vh.l2_window,
+                        vh.d, ft, v, -1);
       else
         g_step_sk_fn(K)<<<vh.d.g_ctas, 128, 0, st>>>(vh.d, ft, v, -1);
       count = ff_contributors(vh.d);
@@ -391,6 +425,15 @@ extern "C" int resnmtf_ctx_create(int device, resnmtf_ctx** out) {
   cudaDeviceProp prop;
   RN_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  // Persisting L2 (experiment knob, OFF by default): pin the head of every view's X in L2 across the two
+  // passes of an iteration with an access-policy window on the streaming kernels.  Measured on B200: no gain
+  // for the TMA bulk loads, and the 79 MB set-aside alone slows the G step by 6 % (116 -> 123 us at C2, k=8).
+  if (rn_env_int("RESNMTF_L2_PERSIST", 0) && prop.persistingL2CacheMaxSize > 0 &&
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+    c->l2_persist_bytes = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)prop.accessPolicyMaxWindowSize);
+  } else {
+    cudaGetLastError();
+  }
   RN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   RN_CUDA(cudaEventCreate(&c->ev0));
   RN_CUDA(cudaEventCreate(&c->ev1));
@@ -826,10 +869,6 @@ extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl)
 // ------------------------------------------------------------------------------------------------
 // plan: grids, workspaces, device metadata, per-iteration graph
 // ------------------------------------------------------------------------------------------------
-static int rn_env_int(const char* name, int dflt) {
-  const char* s = std::getenv(name);
-  return (s && *s) ? std::atoi(s) : dflt;
-}
 
 static int build_plan(resnmtf_fit* fit) {
   const int sms = fit->ctx->sm_count;
@@ -920,6 +959,17 @@ static int build_plan(resnmtf_fit* fit) {
     if ((rc = rn_alloc(fit, &d.tile_ticket, (size_t)d.row_tiles))) return rc;
     if ((rc = rn_alloc(fit, &d.group_ticket, (size_t)d.col_groups))) return rc;
     RN_CUDA(cudaMemsetAsync(d.misc_ticket, 0, 4 * sizeof(int32_t), fit->ctx->stream));
+  }
+  {  // persisting-L2 budget: 90 % of the carve-out, split over the views in proportion to their size
+    double total = 0.0;
+    for (int v = 0; v < fit->V; ++v) total += (double)fit->views[v].d.ldx * fit->views[v].d.pp;
+    const double budget = 0.9 * (double)fit->ctx->l2_persist_bytes * rn_env_int("RESNMTF_L2_PERSIST_PCT", 100) / 100.0;
+    for (int v = 0; v < fit->V; ++v) {
+      ViewHost& vh = fit->views[v];
+      const double xbytes = (double)vh.d.ldx * vh.d.pp * sizeof(double);
+      double w = std::min(xbytes, budget * ((double)vh.d.ldx * vh.d.pp / total));
+      vh.l2_window = (size_t)(w / 32768.0) * 32768;  // whole 32 KB units
+    }
   }
   fit->plan_dirty = false;
   fit->meta_dirty = true;
