@@ -13,6 +13,7 @@
 
 #include "../../include/resnmtf_b200.h"
 #include "rn_kernels.cuh"
+#include "rn_fused.cuh"
 
 #include <dlfcn.h>
 
@@ -102,6 +103,8 @@ struct resnmtf_data {
   resnmtf_ctx* ctx = nullptr;
   int64_t n = 0, p = 0, ldx = 0, pp = 0;
   double* X = nullptr;
+  double* X8 = nullptr;  // 8-row-group copy for the one-pass fused kernel (built on demand by the first plan)
+  int64_t pp8 = 0;
   double xnorm2 = 0.0;
   int refs = 1;
 };
@@ -109,6 +112,7 @@ struct resnmtf_data {
 static void rn_data_release(resnmtf_data* d) {
   if (d && --d->refs == 0) {
     if (d->X) cudaFree(d->X);
+    if (d->X8) cudaFree(d->X8);
     delete d;
   }
 }
@@ -117,6 +121,8 @@ struct ViewHost {
   RnView d;  // device pointers + geometry (passed by value to the kernels)
   resnmtf_data* shared = nullptr;  // non-null: X belongs to a shared data handle
   size_t l2_window = 0;            // bytes at the head of X pinned in L2 (persisting access-policy window)
+  int impl = RESNMTF_IMPL_TMA;     // kernel family this view runs (a fit may mix FUSED and TMA views)
+  double* x8_own = nullptr;        // X8 owned by the fit (views without a shared data handle)
   bool has_data = false, has_factors = false;
   std::vector<int32_t*> rowmaps, colmaps;  // [V] device maps of this view into view w (or null)
   double* xpart = nullptr;                 // ||X||^2 partials
@@ -238,6 +244,43 @@ static GStepSkFn g_step_tma_fn(int K) {
   return nullptr;
 }
 
+static GStepSkFn fused_step_fn(int K) {
+  switch (K) {
+#define X(KC) case KC: return rn_fused_step<KC>;
+    RN_K_CASES_LE8(X)
+#undef X
+  }
+  return nullptr;
+}
+
+// One-pass fused update of a view: cluster launch (fu_csize CTAs per cluster, fu_clusters clusters).
+static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(vh.d.fu_clusters * vh.d.fu_csize));
+  cfg.blockDim = dim3(RN_FU_THREADS);
+  cfg.dynamicSmemBytes = rn_fused_smem();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)vh.d.fu_csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, fused_step_fn(vh.d.k), vh.d, ft, v, fuse);
+}
+
+// Cluster size of the fused path for a view, 0 when it does not qualify: k <= 8, not row-sharded, p within
+// 4 x 1024 columns and not padded by more than RESNMTF_FUSED_MAX_PAD percent (default 130).
+static int fused_csize(const RnView& d, int n_ranks) {
+  if (d.k > 8 || n_ranks > 1) return 0;
+  const double max_pad = rn_env_int("RESNMTF_FUSED_MAX_PAD", 130) / 100.0;
+  for (int c = 1; c <= RN_FU_MAXC; c *= 2)
+    if ((int64_t)c * RN_FU_CCOLS >= d.p) return ((double)c * RN_FU_CCOLS <= max_pad * (double)d.p) ? c : 0;
+  return 0;
+}
+
 // Launch of a streaming kernel with (optionally) a persisting-L2 access-policy window over the head of X.
 template <typename... Args>
 static void launch_windowed(void (*fn)(Args...), int grid, int block, size_t smem, cudaStream_t st, const void* win_ptr,
@@ -263,13 +306,13 @@ static void launch_windowed(void (*fn)(Args...), int grid, int block, size_t sme
 }
 
 static inline bool use_mma(const ViewHost& vh, int impl) {
-  return (impl == RESNMTF_IMPL_DMMA || impl == RESNMTF_IMPL_TMA) && vh.d.k <= 8;
+  return (impl == RESNMTF_IMPL_DMMA || impl == RESNMTF_IMPL_TMA || impl == RESNMTF_IMPL_FUSED) && vh.d.k <= 8;
 }
 
 static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, cudaStream_t st) {
   const int K = vh.d.k;
   if (use_mma(vh, impl)) {
-    if (impl == RESNMTF_IMPL_TMA)
+    if (impl != RESNMTF_IMPL_DMMA)
       launch_windowed(f_step_tma_fn(K), vh.d.f_ctas, RN_TMA_THREADS, rn_f_tma_smem(K), st, vh.d.X, vh.l2_window,
                       vh.d, ft, v);
     else
@@ -315,7 +358,7 @@ static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, i
   const int K = vh.d.k;
   const bool sharded = ctx && ctx->n_ranks > 1;
   if (use_mma(vh, impl) && !sharded) {
-    if (impl == RESNMTF_IMPL_TMA)
+    if (impl != RESNMTF_IMPL_DMMA)
       launch_windowed(g_step_tma_fn(K), vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st, vh.d.X, vh.l2_window,
                       vh.d, ft, v, fuse);
     else
@@ -325,7 +368,7 @@ static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, i
   if (sharded) {
     int n = 0, count;
     if (use_mma(vh, impl)) {
-      if (impl == RESNMTF_IMPL_TMA)
+      if (impl != RESNMTF_IMPL_DMMA)
         launch_windowed(g_step_tma_fn(K), vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st, vh.d.X, vh.l2_window,
                         vh.d, ft, v, -1);
       else
@@ -647,6 +690,8 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
     rn_data_release(vh.shared);
     vh.shared = nullptr;
     vh.d.X = nullptr;
+    if (vh.d.X8) fit->plan_dirty = true;
+    vh.d.X8 = nullptr;
   }
   if (!vh.d.X) {
     int rc = rn_alloc(fit, &vh.d.X, (size_t)vh.d.ldx * vh.d.pp);  // zeroed: padding rows / columns stay zero
@@ -656,6 +701,10 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
   int rc = upload_panels(fit->ctx, vh.d, x, ld, on_device, vh.xpart, vh.xticket, who);
   if (rc) return rc;
   vh.has_data = true;
+  if (vh.d.X8) {  // the fused path's copy of X is stale: the next plan rebuilds it
+    vh.d.X8 = nullptr;
+    fit->plan_dirty = true;
+  }
   return RESNMTF_OK;
 }
 
@@ -730,6 +779,8 @@ extern "C" int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* da
   vh.shared = data;
   data->refs += 1;
   vh.d.X = data->X;
+  if (vh.d.X8) fit->plan_dirty = true;
+  vh.d.X8 = nullptr;
   RN_CUDA(cudaMemcpy(vh.d.scal, &data->xnorm2, sizeof(double), cudaMemcpyHostToDevice));
   vh.has_data = true;
   fit->meta_dirty = true;
@@ -854,7 +905,7 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
 
 extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl) {
   RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_options: fit is NULL");
-  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 3, RESNMTF_E_INVALID,
+  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 4, RESNMTF_E_INVALID,
            "resnmtf_fit_set_options: unknown option value");
   if (fit->err_mode != err_mode) {
     fit->meta_dirty = true;
@@ -873,19 +924,84 @@ extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl)
 static int build_plan(resnmtf_fit* fit) {
   const int sms = fit->ctx->sm_count;
   int impl = fit->impl_req;
-  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_TMA);
-  if (impl != RESNMTF_IMPL_DFMA && impl != RESNMTF_IMPL_DMMA && impl != RESNMTF_IMPL_TMA) impl = RESNMTF_IMPL_TMA;
-  fit->impl = impl;
+  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_FUSED);
+  if (impl < RESNMTF_IMPL_DFMA || impl > RESNMTF_IMPL_FUSED) impl = RESNMTF_IMPL_FUSED;
+  const int impl_fit = impl;
+  bool any_fused = false;
   const int f_target = sms * rn_env_int("RESNMTF_F_CTAS_PER_SM", 2);
   const int g_target_dfma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM_DFMA", 3);
   int rc;
   for (int v = 0; v < fit->V; ++v) {
     ViewHost& vh = fit->views[v];
     RnView& d = vh.d;
+    // the one-pass fused kernel serves the views that qualify (fused_csize); the others of the fit run the
+    // two-pass TMA kernels
+    const int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->n_ranks) : 0;
+    const int impl = (impl_fit == RESNMTF_IMPL_FUSED && !csz) ? RESNMTF_IMPL_TMA : impl_fit;
+    vh.impl = impl;
     const bool mma = use_mma(vh, impl);
     const int K = d.k, KP = d.kp;
     size_t n_ppart, n_tpart, n_ffpart, n_ggpart;
-    if (mma) {
+    d.fu_csize = d.fu_clusters = 0;
+    if (csz) {
+      any_fused = true;
+      GStepSkFn fn = fused_step_fn(K);
+      RN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rn_fused_smem()));
+      int max_clusters = 0;
+      {
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(csz * sms));
+        cfg.blockDim = dim3(RN_FU_THREADS);
+        cfg.dynamicSmemBytes = rn_fused_smem();
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csz;
+        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
+      }
+      RN_CHECK(max_clusters >= 1, RESNMTF_E_CUDA, "the fused kernel's cluster does not fit on this device");
+      const int64_t groups = (d.n + 7) / 8;
+      int nc = (int)std::min<int64_t>(max_clusters, groups);
+      nc = std::max(1, std::min(nc, rn_env_int("RESNMTF_FU_CLUSTERS", nc)));
+      d.fu_csize = csz;
+      d.fu_clusters = nc;
+      d.pp8 = (int64_t)csz * RN_FU_CCOLS;
+      d.col_groups = (int)((d.pp + RN_COL_GROUP - 1) / RN_COL_GROUP);
+      d.cs = d.rs = 1;
+      d.nff = 0;
+      d.f_ctas = d.g_ctas = 0;
+      d.gepi_ctas = (int)((d.p + RN_GEPI_THREADS(K) - 1) / RN_GEPI_THREADS(K));
+      n_ppart = 0;
+      n_tpart = (size_t)nc * d.pp8 * KP;
+      n_ffpart = (size_t)nc * (K * K + K);
+      n_ggpart = (size_t)std::max(d.col_groups, d.gepi_ctas) * (2 * K * K + K);
+      if (!d.X8) {  // second copy of X in the 8-row-group layout (shared by every fit attached to the same data)
+        const size_t x8_count = (size_t)d.ldx * d.pp8;
+        bool convert = true;
+        if (vh.shared) {
+          if (vh.shared->X8 && vh.shared->pp8 == d.pp8) {
+            convert = false;
+          } else {
+            if (vh.shared->X8) cudaFree(vh.shared->X8);
+            vh.shared->X8 = nullptr;
+            RN_CUDA(cudaMalloc(&vh.shared->X8, x8_count * sizeof(double)));
+            vh.shared->pp8 = d.pp8;
+          }
+          d.X8 = vh.shared->X8;
+        } else {
+          if (!vh.x8_own && (rc = rn_alloc(fit, &vh.x8_own, x8_count, false))) return rc;
+          d.X8 = vh.x8_own;
+        }
+        if (convert) {
+          const int blocks = (int)std::min<int64_t>(((int64_t)x8_count / 2 + 255) / 256, 1 << 20);
+          rn_panels_to_x8<<<blocks, 256, 0, fit->ctx->stream>>>(d);
+          RN_CUDA(cudaGetLastError());
+        }
+      }
+    } else if (mma) {
       // persistent stream-K grids: exactly the CTAs that are resident at once (never more than units)
       int occ_f = 1, occ_g = 1;
       if (impl == RESNMTF_IMPL_TMA) {  // one CTA per SM: the shared-memory ring takes ~200 KB
@@ -971,6 +1087,7 @@ static int build_plan(resnmtf_fit* fit) {
       vh.l2_window = (size_t)(w / 32768.0) * 32768;  // whole 32 KB units
     }
   }
+  fit->impl = (impl_fit == RESNMTF_IMPL_FUSED && !any_fused) ? RESNMTF_IMPL_TMA : impl_fit;
   fit->plan_dirty = false;
   fit->meta_dirty = true;
   if (fit->graph_exec) {
@@ -1051,12 +1168,18 @@ static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<
   const bool direct = fit->d.err_mode == RESNMTF_ERR_DIRECT;
   for (int v = 0; v < fit->V; ++v) {
     const ViewHost& vh = fit->views[v];
-    mark(0);
-    launch_f_step(vh, fit->d, v, fit->impl, st);
-    launches += 1;
-    mark(1);
     const int fuse = (!direct && v == fit->V - 1) ? 1 : 0;
-    launches += launch_g_step(vh, fit->d, v, fit->impl, fuse, st, fit->ctx, &fit->comm_rc);
+    if (vh.d.fu_csize) {  // one pass over X: F step and G step in one launch
+      mark(2);
+      launch_fused(vh, fit->d, v, fuse, st);
+      launches += 1;
+    } else {
+      mark(0);
+      launch_f_step(vh, fit->d, v, vh.impl, st);
+      launches += 1;
+      mark(1);
+      launches += launch_g_step(vh, fit->d, v, vh.impl, fuse, st, fit->ctx, &fit->comm_rc);
+    }
     if (direct) {
       mark(3);
       launches += launch_residual(vh, fit->d, 0, st, fit->ctx, &fit->comm_rc);
@@ -1154,7 +1277,8 @@ static double alg_bytes_per_iter(const resnmtf_fit* fit) {
       if (fit->h_phi[w + (size_t)v * V] != 0.0 && fit->h_rowmode[w + (size_t)v * V] != RN_MODE_NA) cv += (double)d.n * d.k;
       if (fit->h_psi[w + (size_t)v * V] != 0.0 && fit->h_colmode[w + (size_t)v * V] != RN_MODE_NA) cv += (double)d.p * d.k;
     }
-    b += 8.0 * (2.0 * d.n * d.p + 4.0 * d.n * d.k + 4.0 * d.p * d.k + cv);
+    // the one-pass fused kernel reads X once: B_min = B_alg - 8 n p
+    b += 8.0 * ((d.fu_csize ? 1.0 : 2.0) * d.n * d.p + 4.0 * d.n * d.k + 4.0 * d.p * d.k + cv);
   }
   return b;
 }

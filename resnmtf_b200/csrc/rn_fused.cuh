@@ -1,0 +1,525 @@
+// One-pass fused update of one view: F step AND G step with a SINGLE read of X per update-iteration.
+//
+// Why: the two streaming kernels of rn_kernels.cuh each read X once (B_alg = 16 n p bytes per iteration) and run
+// at 0.85-0.92 of the HBM roofline, so the only way left to go faster is to move fewer bytes.  The G step needs
+// T = X' F_new, and F_new[r,] depends on the WHOLE row r of X (P = X G) -- but only on that row.  So a group of
+// 8 rows that is resident on chip can do both: P for its rows, the F update (update_f, R/update_steps.r:141-165),
+// and then its contribution X[rows,]' F_new[rows,] to T (update_g, :180-207), before the rows are dropped.
+// 8 rows x p columns of FP64 do not fit one SM (256 KB at p = 4000), so a CLUSTER of C = 1/2/4 CTAs splits the
+// columns (1024 per CTA) and exchanges the 8 x 8 partial of P through distributed shared memory.
+//
+//   X8 layout (HBM): X8[row group (8 rows)][column pair q][8 x 16 B]; the 16 B piece of row r holds
+//   (X[r][2q], X[r][2q+1]) and sits at piece position r ^ 2(q & 3).  A warp's share of a group (64 column pairs =
+//   8 KB) is one contiguous run = one bulk copy, and a verbatim copy in shared memory is bank-conflict-free for the
+//   LDS.128 fragment reads of both phases (each LDS.128 feeds two m8n8k4 MMAs).
+//   Roles per CTA (320 threads): 8 consumer warps (warp w owns data columns 128w..128w+127 of the CTA's 1024 for
+//   every row group: G fragments and the T accumulators of those columns live in registers for the whole kernel),
+//   1 producer warp (bulk copies into a 24-slot x 8 KB ring: a slot is read twice -- F phase, G phase -- and then
+//   released), 1 epilogue warp (sums the 8 warp partials of P, exchanges the CTA partial with the cluster peers by
+//   st.async + mbarrier complete_tx, runs the F update for the 8 rows redundantly in every CTA, writes F_new to
+//   shared memory for the G phase and -- rank 0 -- to HBM, accumulates F'F and colSums(F)).
+//   Software pipeline of a consumer warp: F phase of group i+1, then G phase of group i, so the exchange and the
+//   F update of group i+1 overlap the G phase MMAs of group i.
+//   Tail: every cluster publishes its T partial [pp8][8]; after a grid-wide arrival counter the 64-column groups
+//   are dealt round-robin to the CTAs, each sums the cluster partials in cluster order and runs the same G-update
+//   epilogue as rn_g_step_tma (update_g, G'G, A = T'G, colSums(G); last CTA: update_s, update_lm, error,
+//   bookkeeping).  All summation orders are fixed: results are bit-reproducible run to run.
+#pragma once
+#include "rn_kernels.cuh"
+
+#define RN_FU_THREADS 320
+#define RN_FU_NB 8                                        // 16-column blocks per consumer warp and row group
+#define RN_FU_WCOLS (16 * RN_FU_NB)                       // data columns per consumer warp
+#define RN_FU_CCOLS (8 * RN_FU_WCOLS)                     // data columns per CTA (1024)
+#define RN_FU_SLOT_BYTES (RN_FU_NB * 1024)                // one warp's share of one row group
+#define RN_FU_NSLOT 24                                    // ring slots = 3 row groups
+#define RN_FU_RING_BYTES (RN_FU_NSLOT * RN_FU_SLOT_BYTES) // 192 KB
+#define RN_FU_MAXC 4                                      // largest cluster (columns <= 4096)
+
+// doubles of shared memory behind the ring (see the carve-up in the kernel)
+#define RN_FU_AUX_DOUBLES (2 * 8 * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8)
+static inline size_t rn_fused_smem() {
+  return (size_t)RN_FU_RING_BYTES + (size_t)RN_FU_AUX_DOUBLES * 8 + (2 * RN_FU_NSLOT + 6) * 8 + 16;
+}
+
+// position (in doubles) of X[r][j] in the X8 layout with pp8 (even) columns
+__device__ __forceinline__ int64_t rn_x8idx(int64_t r, int64_t j, int64_t pp8) {
+  const int64_t q = j >> 1;
+  return (((r >> 3) * (pp8 >> 1) + q) << 4) + 2 * ((int)(r & 7) ^ (2 * (int)(q & 3))) + (j & 1);
+}
+
+// panel layout -> X8 layout (once per plan; one thread per 16-byte piece, grid-stride)
+__global__ void __launch_bounds__(256) rn_panels_to_x8(const RnView vw) {
+  const int64_t qrow = vw.pp8 >> 1;
+  const int64_t pieces = (vw.ldx >> 3) * qrow * 8;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < pieces; i += (int64_t)gridDim.x * 256) {
+    const int pos = (int)(i & 7);
+    const int64_t q = (i >> 3) % qrow;
+    const int64_t grp = (i >> 3) / qrow;
+    const int64_t r = grp * 8 + (pos ^ (2 * (int)(q & 3)));
+    double2 val = make_double2(0.0, 0.0);
+    const int64_t j = 2 * q;
+    if (j < vw.pp)
+      val.x = vw.X[((r >> 6) * vw.pp + j) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ rn_sigma(j)) + (r & 1)];
+    if (j + 1 < vw.pp)
+      val.y = vw.X[((r >> 6) * vw.pp + j + 1) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ rn_sigma(j + 1)) + (r & 1)];
+    *reinterpret_cast<double2*>(vw.X8 + (i << 1)) = val;
+  }
+}
+
+// ---- cluster / DSMEM primitives ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t rn_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void rn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t rn_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 16-byte store into a peer CTA's shared memory; completion is counted (in bytes) on the peer's mbarrier
+__device__ __forceinline__ void rn_st_async2(uint32_t raddr, double a, double b, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+               "d"(a), "d"(b), "r"(rbar)
+               : "memory");
+}
+// wait on a local mbarrier whose phase is completed by peer CTAs (cluster-scope acquire)
+__device__ __forceinline__ void rn_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RN_WAITC_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RN_DONEC_%=;\n"
+      "bra RN_WAITC_%=;\n"
+      "RN_DONEC_%=:\n"
+      "}\n" ::"r"(rn_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void rn_cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rn_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void rn_cp_async_wait2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+
+template <int K>
+__global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView vw, const RnFit ft, const int v,
+                                                                  const int fuse_finish) {
+  constexpr int KP = 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
+  constexpr int NB = RN_FU_NB, NSLOT = RN_FU_NSLOT, SLOT = RN_FU_SLOT_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (ft.ctrl->done) return;  // uniform over the grid
+
+  extern __shared__ __align__(128) unsigned char rn_smem[];
+  unsigned char* ring = rn_smem;
+  double* Pw = reinterpret_cast<double*>(rn_smem + RN_FU_RING_BYTES);  // [2][8 warps][64]  warp partials of P
+  double* Pex = Pw + 2 * 8 * 64;                                        // [2][MAXC][64]     CTA partials (peers write)
+  double* Fp = Pex + 2 * RN_FU_MAXC * 64;                               // [2][8 rows][8]    F_new of a group
+  double* Ps = Fp + 2 * 64;                                             // [8][8]            P of the current group
+  double* Fo = Ps + 64;                                                 // [4][8][8]         old F rows (cp.async)
+  double* FSs = Fo + 4 * 64;                                            // [8][8]            F S of the current group
+  double* Ssm = FSs + 64;                                               // [K*K] (64 reserved)
+  double* Wsm = Ssm + 64;
+  double* lamh = Wsm + 64;
+  double* muh = lamh + 8;
+  uint64_t* full = reinterpret_cast<uint64_t*>(muh + 8);
+  uint64_t* empty = full + NSLOT;
+  uint64_t* pw_full = empty + NSLOT;
+  uint64_t* pex_full = pw_full + 2;
+  uint64_t* fp_full = pex_full + 2;
+  int* s_flag = reinterpret_cast<int*>(fp_full + 2);
+
+  const uint32_t rank = rn_cluster_rank(), csize = rn_cluster_size();
+  const int64_t n_clusters = gridDim.x / csize, cid = blockIdx.x / csize;
+  const int64_t NGT = (vw.n + 7) >> 3;  // row groups that hold data
+  const RnSplit gsp(NGT, n_clusters);
+  const int64_t g0 = gsp.begin(cid);
+  const int NGL = (int)(gsp.begin(cid + 1) - g0);
+  const int64_t qrow = vw.pp8 >> 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      rn_mbar_init(&full[i], 1);
+      rn_mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      rn_mbar_init(&pw_full[i], 8);
+      rn_mbar_init(&pex_full[i], 1);
+      rn_mbar_init(&fp_full[i], 1);
+    }
+    rn_mbar_init_fence();
+  }
+  if (tid < 64) {
+    Ssm[tid] = (tid < KK) ? vw.S[tid] : 0.0;
+    Wsm[tid] = 0.0;
+  }
+  if (tid < 8) {
+    lamh[tid] = (tid < K) ? 0.5 * vw.lam[tid] : 0.0;
+    muh[tid] = (tid < K) ? 0.5 * vw.mu[tid] : 0.0;
+  }
+  __syncthreads();
+  if (tid < KK) {  // W = crossprod(G) %*% t(S)
+    const int a = tid % K, b = tid / K;
+    double s = 0.0;
+    for (int c = 0; c < K; ++c) s = fma(vw.GtG[a + c * K], Ssm[b + c * K], s);
+    Wsm[a + b * K] = s;
+  }
+  __syncthreads();
+  rn_cluster_sync();  // peers' mbarriers are initialised before anyone stores into them
+
+  double tacc[2 * NB][2];  // consumer warps: T accumulators of the warp's 128 columns (tile 2b+e: columns 16b+2g+e)
+#pragma unroll
+  for (int s = 0; s < 2 * NB; ++s) tacc[s][0] = tacc[s][1] = 0.0;
+  const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + (int64_t)(warp & 7) * RN_FU_WCOLS;
+
+  if (warp == 8) {
+    // ---- producer warp -------------------------------------------------------------------------------
+    for (int i = 0; i < NGL; ++i) {
+      const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
+      for (int w = 0; w < 8; ++w) {
+        const int cnt = i * 8 + w;
+        const int st = cnt % NSLOT;
+        const uint32_t ph = (uint32_t)((cnt / NSLOT) & 1);
+        rn_mbar_wait(&empty[st], ph ^ 1u);
+        if (lane == 0) {
+          rn_mbar_expect_tx(&full[st], SLOT);
+          rn_bulk_g2s(ring + st * SLOT, src + w * (SLOT / 8), SLOT, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 9) {
+    // ---- epilogue warp: lane (g,t) owns row g, factor columns 2t and 2t+1 of every row group ------------
+    const int V = ft.n_views;
+    const int kp = vw.kp;
+    const int c0 = 2 * t, c1 = 2 * t + 1;
+    double Sa0[8], Sa1[8], Sn0[8], Sn1[8], Wd0[8], Wd1[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool in = b < K;
+      Sa0[b] = (in && c0 < K) ? Ssm[b + c0 * K] : 0.0;  // (F S)[c0] = sum_b f[b] S[b, c0]
+      Sa1[b] = (in && c1 < K) ? Ssm[b + c1 * K] : 0.0;
+      Sn0[b] = (in && c0 < K) ? Ssm[c0 + b * K] : 0.0;  // ((X G) t(S))[c0] = sum_a P[a] S[c0, a]
+      Sn1[b] = (in && c1 < K) ? Ssm[c1 + b * K] : 0.0;
+      Wd0[b] = (in && c0 < K) ? Wsm[b + c0 * K] : 0.0;  // ((F S) W)[c0] = sum_a FS[a] W[a, c0]
+      Wd1[b] = (in && c1 < K) ? Wsm[b + c1 * K] : 0.0;
+    }
+    const double lam0 = lamh[c0], lam1 = lamh[c1];
+    double phisum = 0.0;
+    for (int w = 0; w < V; ++w) phisum += ft.phi[w + v * V];
+    const double nv = (double)vw.n_glob;
+    double ff0 = 0.0, ff1 = 0.0, cs0 = 0.0, cs1 = 0.0;
+    const uint32_t my_pex = rn_smem_u32(Pex + rank * 64 + 2 * lane);
+    auto prefetch_f = [&](int i) {  // old F rows of local group i -> Fo[i & 3]
+      if (i < NGL) {
+        const int64_t r = (g0 + i) * 8 + g;
+        rn_cp_async8(Fo + (i & 3) * 64 + g * 8 + c0, vw.F + rn_fidx(r, c0, kp));
+        rn_cp_async8(Fo + (i & 3) * 64 + g * 8 + c1, vw.F + rn_fidx(r, c1, kp));
+      }
+      rn_cp_async_commit();
+    };
+    prefetch_f(0);
+    prefetch_f(1);
+    for (int i = 0; i < NGL; ++i) {
+      const int sl = i & 1;
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      prefetch_f(i + 2);
+      if (lane == 0) rn_mbar_expect_tx(&pex_full[sl], csize * 512u);
+      rn_mbar_wait(&pw_full[sl], ph);
+      double2 acc = *reinterpret_cast<const double2*>(Pw + (sl * 8) * 64 + 2 * lane);
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        const double2 x = *reinterpret_cast<const double2*>(Pw + (sl * 8 + w) * 64 + 2 * lane);
+        acc.x += x.x;
+        acc.y += x.y;
+      }
+      // the old F rows of this group are on chip before any peer can be released to overwrite them in HBM
+      rn_cp_async_wait2();
+      __syncwarp();
+      for (uint32_t rr = 0; rr < csize; ++rr)
+        rn_st_async2(rn_mapa(my_pex + sl * (RN_FU_MAXC * 64 * 8), rr), acc.x, acc.y,
+                     rn_mapa(rn_smem_u32(&pex_full[sl]), rr));
+      rn_mbar_wait_cluster(&pex_full[sl], ph);
+      double2 tot = *reinterpret_cast<const double2*>(Pex + (sl * RN_FU_MAXC) * 64 + 2 * lane);
+      for (uint32_t rr = 1; rr < csize; ++rr) {
+        const double2 x = *reinterpret_cast<const double2*>(Pex + (sl * RN_FU_MAXC + rr) * 64 + 2 * lane);
+        tot.x += x.x;
+        tot.y += x.y;
+      }
+      *reinterpret_cast<double2*>(Ps + 2 * lane) = tot;
+      __syncwarp();
+      const double* fo = Fo + (i & 3) * 64 + g * 8;
+      double fr[8], pr[8];
+#pragma unroll
+      for (int b = 0; b < 8; b += 2) {
+        const double2 x = *reinterpret_cast<const double2*>(fo + b);
+        fr[b] = x.x;
+        fr[b + 1] = x.y;
+        const double2 y = *reinterpret_cast<const double2*>(Ps + g * 8 + b);
+        pr[b] = y.x;
+        pr[b + 1] = y.y;
+      }
+      double fs0 = 0.0, fs1 = 0.0, N0 = 0.0, N1 = 0.0;
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        fs0 = fma(fr[b], Sa0[b], fs0);
+        fs1 = fma(fr[b], Sa1[b], fs1);
+        N0 = fma(pr[b], Sn0[b], N0);
+        N1 = fma(pr[b], Sn1[b], N1);
+      }
+      *reinterpret_cast<double2*>(FSs + g * 8 + c0) = make_double2(fs0, fs1);
+      __syncwarp();
+      double D0 = 0.0, D1 = 0.0;
+#pragma unroll
+      for (int a = 0; a < K; a += 2) {
+        const double2 x = *reinterpret_cast<const double2*>(FSs + g * 8 + a);
+        D0 = fma(x.x, Wd0[a], D0);
+        D1 = fma(x.x, Wd1[a], D1);
+        if (a + 1 < K) {
+          D0 = fma(x.y, Wd0[a + 1], D0);
+          D1 = fma(x.y, Wd1[a + 1], D1);
+        }
+      }
+      const int64_t r = (g0 + i) * 8 + g;
+      const double2 fmine = *reinterpret_cast<const double2*>(fo + c0);
+      const double f0 = fmine.x, f1 = fmine.y;
+      double o0 = 0.0, o1 = 0.0;
+      if (r < vw.n) {
+        if (phisum == 0.0) {  // update_steps.r:152-155
+          double q0 = N0 / (D0 + lam0), q1 = N1 / (D1 + lam1);
+          if (isnan(q0)) q0 = 1.0;
+          if (isnan(q1)) q1 = 1.0;
+          o0 = fabs(f0 * q0);
+          o1 = fabs(f1 * q1);
+        } else {  // update_steps.r:156-163 with star_prod_relevant (utils.r:63-78)
+          double pc0 = 0.0, pc1 = 0.0;
+          for (int w = 0; w < V; ++w) {
+            const double phw = ft.phi[w + v * V];
+            if (phw == 0.0) continue;
+            const int mode = ft.rowmode[w + v * V];
+            if (mode == RN_MODE_NA) continue;
+            const RnView* ow = ft.views + w;
+            const double nw = (double)ow->n_glob;
+            int64_t src = -1;
+            if (mode == RN_MODE_MAP) src = ft.rowmap[w + v * V][r];
+            const double m0 = (src >= 0) ? ow->F[rn_fidx(src, c0, ow->kp)] : f0;
+            const double m1 = (src >= 0) ? ow->F[rn_fidx(src, c1, ow->kp)] : f1;
+            pc0 += (phw * m0) * nw;
+            pc1 += (phw * m1) * nw;
+          }
+          o0 = fabs(f0 * ((N0 + pc0 / nv) / ((D0 + phisum * f0) + lam0)));
+          o1 = fabs(f1 * ((N1 + pc1 / nv) / ((D1 + phisum * f1) + lam1)));
+        }
+        if (c0 >= K) o0 = 0.0;
+        if (c1 >= K) o1 = 0.0;
+        if (rank == 0) {
+          if (c0 < K) vw.F[rn_fidx(r, c0, kp)] = o0;
+          if (c1 < K) vw.F[rn_fidx(r, c1, kp)] = o1;
+        }
+      }
+      *reinterpret_cast<double2*>(Fp + sl * 64 + g * 8 + c0) = make_double2(o0, o1);
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&fp_full[sl]);
+      if (rank == 0) {  // F'F and colSums(F) of this cluster's rows, off the critical path
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const double a = Fp[sl * 64 + rr * 8 + g];
+          const double2 b = *reinterpret_cast<const double2*>(Fp + sl * 64 + rr * 8 + c0);
+          ff0 = fma(a, b.x, ff0);
+          ff1 = fma(a, b.y, ff1);
+          cs0 += b.x;
+          cs1 += b.y;
+        }
+      }
+    }
+    if (rank == 0) {
+      double* mine = vw.FFpart + cid * NFF;
+      if (g < K) {
+        if (c0 < K) mine[g + c0 * K] = ff0;
+        if (c1 < K) mine[g + c1 * K] = ff1;
+      }
+      if (g == 0) {
+        if (c0 < K) mine[KK + c0] = cs0;
+        if (c1 < K) mine[KK + c1] = cs1;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(&vw.misc_ticket[2], 1);
+    }
+  } else {
+    // ---- consumer warps --------------------------------------------------------------------------------
+    double gfr[2 * NB][2];  // G fragments of the warp's columns: B operand of the F phase
+#pragma unroll
+    for (int s = 0; s < 2 * NB; ++s)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t col = colbase + 8 * s + 2 * t + e;
+        gfr[s][e] = (col < vw.pp) ? vw.G[col * KP + g] : 0.0;
+      }
+    const int ra = (t & 1) + 4 * (t >> 1);  // G-phase K slot t <-> rows {0,1,4,5} (first MMA), {2,3,6,7} (second)
+    const int rb = ra + 2;
+    const uint32_t off1 = (uint32_t)(t * 128 + ((g ^ (2 * t)) * 16));
+    const uint32_t off2a = (uint32_t)(g * 128 + ((ra ^ (2 * (g & 3))) * 16));
+    const uint32_t off2b = (uint32_t)(g * 128 + ((rb ^ (2 * (g & 3))) * 16));
+
+    auto f_phase = [&](int i) {
+      const int cnt = i * 8 + warp;
+      const int st = cnt % NSLOT;
+      rn_mbar_wait(&full[st], (uint32_t)((cnt / NSLOT) & 1));
+      const unsigned char* xs = ring + st * SLOT + off1;
+      double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;
+#pragma unroll
+      for (int s = 0; s < 2 * NB; ++s) {
+        const double2 x = *reinterpret_cast<const double2*>(xs + s * 512);
+        rn_dmma(pe0, pe1, x.x, gfr[s][0]);
+        rn_dmma(po0, po1, x.y, gfr[s][1]);
+      }
+      *reinterpret_cast<double2*>(Pw + ((i & 1) * 8 + warp) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&pw_full[i & 1]);
+    };
+    auto g_phase = [&](int i) {
+      const int cnt = i * 8 + warp;
+      const int st = cnt % NSLOT;
+      rn_mbar_wait(&fp_full[i & 1], (uint32_t)((i >> 1) & 1));
+      const double fa = Fp[(i & 1) * 64 + ra * 8 + g];
+      const double fb = Fp[(i & 1) * 64 + rb * 8 + g];
+      const unsigned char* xs = ring + st * SLOT;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const double2 xa = *reinterpret_cast<const double2*>(xs + off2a + b * 1024);
+        const double2 xb = *reinterpret_cast<const double2*>(xs + off2b + b * 1024);
+        rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xa.x, fa);
+        rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xa.y, fa);
+        rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
+        rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
+      }
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&empty[st]);
+    };
+    if (NGL > 0) f_phase(0);
+    for (int i = 0; i < NGL; ++i) {
+      if (i + 1 < NGL) f_phase(i + 1);
+      g_phase(i);
+    }
+  }
+  rn_cluster_sync();  // every st.async of this cluster has landed before any of its CTAs may exit
+  if (warp >= 8) return;
+
+  // ---- tail (consumer warps): publish T partials, then the column-group epilogues ------------------------
+  {
+    double* tp = vw.Tpart + (cid * vw.pp8 + colbase) * KP;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        *reinterpret_cast<double2*>(tp + (16 * b + 2 * g + e) * KP + 2 * t) =
+            make_double2(tacc[2 * b + e][0], tacc[2 * b + e][1]);
+  }
+  __threadfence();
+  rn_consumer_sync();
+  if (tid == 0) atomicAdd(&vw.misc_ticket[3], 1);
+
+  double* Ts = reinterpret_cast<double*>(ring);  // the ring is idle now: epilogue scratch lives there
+  double* Gs = Ts + RN_COL_GROUP * KP;
+  double* FtFs = Gs + RN_COL_GROUP * K;
+  double* Vs = FtFs + NFF;
+  double* fin = Vs + KK;
+  double* Us = fin + NOUT;
+  double* Sn = Us + KK;
+  double* red = Sn + KK;
+  const int64_t pp = vw.pp;
+  const int64_t NG = (pp + RN_COL_GROUP - 1) / RN_COL_GROUP;
+  if ((int64_t)blockIdx.x >= NG) return;  // no column group for this CTA (it must not wait: the finisher re-arms)
+  if (tid == 0) {
+    while (rn_ld_acquire(&vw.misc_ticket[3]) < (int)gridDim.x) __nanosleep(64);
+  }
+  rn_consumer_sync();
+  __threadfence();
+  bool ff_ready = false;
+  const int64_t tstride = vw.pp8 * KP;
+  for (int64_t grp = blockIdx.x; grp < NG; grp += gridDim.x) {
+    const int64_t j0 = grp * RN_COL_GROUP;
+    const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
+    rn_consumer_sync();  // previous group's epilogue is done with Ts / Gs
+    for (int i = tid; i < RN_COL_GROUP * KP; i += 256)
+      Ts[i] = (i < 8 * njb * KP) ? rn_sum_strided(vw.Tpart + j0 * KP + i, tstride, n_clusters) : 0.0;
+    if (!ff_ready) {
+      if (tid == 0) {
+        while (rn_ld_acquire(&vw.misc_ticket[2]) < (int)n_clusters) __nanosleep(64);
+      }
+      rn_consumer_sync();
+      __threadfence();
+      if (tid < NFF) {
+        double s = 0.0;
+        for (int64_t i = 0; i < n_clusters; ++i) s += __ldcg(vw.FFpart + i * NFF + tid);
+        FtFs[tid] = s;
+      }
+      rn_consumer_sync();
+      for (int o = tid; o < KK; o += 256) {  // V = crossprod(F) %*% S
+        const int a = o % K, c = o / K;
+        double s = 0.0;
+        for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
+        Vs[a + c * K] = s;
+      }
+      ff_ready = true;
+    }
+    rn_consumer_sync();
+    if (tid < RN_COL_GROUP) {
+      const int64_t j = j0 + tid;
+      double gn[K];
+      if (j < vw.p) {
+        double Tj[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) Tj[c] = Ts[tid * KP + c];
+        rn_update_g_row<K>(vw, ft, v, j, Tj, Ssm, Vs, muh, gn);
+      } else {
+#pragma unroll
+        for (int c = 0; c < K; ++c) gn[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < K; ++c) Gs[tid * K + c] = gn[c];
+    }
+    rn_consumer_sync();
+    for (int o = tid; o < NOUT; o += 256) {
+      double s = 0.0;
+      if (o < KK) {
+        const int a = o % K, b = o / K;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
+      } else if (o < 2 * KK) {
+        const int a = (o - KK) % K, b = (o - KK) / K;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
+      } else {
+        const int c = o - 2 * KK;
+        for (int i = 0; i < RN_COL_GROUP; ++i) s += Gs[i * K + c];
+      }
+      vw.GGpart[grp * NOUT + o] = s;
+    }
+    __threadfence();
+    rn_consumer_sync();
+    if (tid == 0) *s_flag = (atomicAdd(&vw.misc_ticket[0], 1) == (int)NG - 1);
+    rn_consumer_sync();
+    if (!*s_flag) continue;
+    __threadfence();
+    // ---- last column group done: finish the view -----------------------------------------------------------
+    for (int o = tid; o < NOUT; o += 256) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, NG);
+    if (tid == 0) {
+      vw.misc_ticket[0] = 0;
+      vw.misc_ticket[2] = 0;
+      vw.misc_ticket[3] = 0;
+    }
+    rn_consumer_sync();
+    rn_view_finish<K, 256, true>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
+  }
+}

@@ -61,7 +61,7 @@ struct RnView {
   double* Rpart;   // [resid ctas]    partial residual sums
   int32_t* tile_ticket;   // [row tiles]
   int32_t* group_ticket;  // [col groups]
-  int32_t* misc_ticket;   // [0] G-epilogue  [1] residual  [2] F'F partials published
+  int32_t* misc_ticket;   // [0] G-epilogue  [1] residual  [2] F'F partials published  [3] fused: T partials published
   int32_t* flags;         // [0] need_direct
   int32_t row_tiles, cs;       // F-step grid (CUDA-core path)
   int32_t col_groups, rs;      // G-stream grid (CUDA-core path); col_groups is also the stream-K group count
@@ -70,6 +70,11 @@ struct RnView {
   int32_t gepi_ctas;           // G-epilogue grid
   int32_t resid_cs;            // residual grid y
   int32_t sharded;             // 1: rows are sharded over ranks (epilogue scalars come from all-reduce)
+  // one-pass fused path (rn_fused.cuh): second copy of X in the 8-row-group layout, pp8 = fu_csize * 1024 columns;
+  // Tpart is then [fu_clusters][pp8][kp], FFpart [fu_clusters][k*k+k], GGpart [ceil(pp/64)][2*k*k+k]
+  double* X8;
+  int64_t pp8;
+  int32_t fu_csize, fu_clusters;  // CTAs per cluster (1, 2 or 4; 0: view not on the fused path), clusters in the grid
 };
 
 struct RnFit {

@@ -1,0 +1,145 @@
+"""Parity of the one-pass fused kernel (RESNMTF_IMPL_FUSED, rn_fused.cuh: one read of X per update-iteration,
+8-row groups resident in the shared memory of a 1/2/4-CTA cluster) against the CPU oracle, sweep by sweep,
+through the C ABI.  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import numpy as np
+import pytest
+
+from helpers import RTOL, Problem, compare_trace, rel_err
+from resnmtf_b200 import _lib as L
+from resnmtf_b200 import synth
+from test_gpu_parity import single_view_problem, two_view_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def any_width(monkeypatch):
+    """Lets narrow views (p << 1024) take the fused path too: the kernel pads the columns to the cluster width."""
+    monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
+
+
+def assert_fused(fit):
+    assert fit.counters()["impl"] == L.IMPL_FUSED, "the view fell back to the two-pass kernels"
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_fused_every_k(ctx, k, any_width):
+    prob = single_view_problem(300, 200, k, seed=100 + k)
+    compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (7, 5), (8, 8), (9, 9), (63, 7), (64, 8), (65, 9), (129, 65),
+                                   (257, 93), (1000, 37)])
+def test_fused_ragged_shapes(ctx, shape, any_width):
+    n, p = shape
+    k = min(3, n, p)
+    prob = single_view_problem(n, p, k, seed=300 + n + p, n_planted=2)
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+@pytest.mark.parametrize("shape,k", [((100, 1000), 3), ((700, 1024), 8), ((257, 1900), 5), ((90, 2048), 4),
+                                     ((333, 4000), 5), ((1200, 3300), 8), ((40, 4096), 2)])
+def test_fused_cluster_widths(ctx, shape, k):
+    """p up to 1024 runs on single CTAs, up to 2048 on CTA pairs, up to 4096 on 4-CTA clusters (default padding rule)."""
+    n, p = shape
+    prob = single_view_problem(n, p, k, seed=500 + n + p, n_planted=4)
+    fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
+    try:
+        fit.run(1)
+        assert_fused(fit)
+    finally:
+        fit.close()
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+def test_fused_wide_view_falls_back(ctx):
+    """p > 4096 does not fit a 4-CTA cluster: the view runs the two-pass TMA kernels and says so."""
+    prob = single_view_problem(64, 4100, 3, seed=9)
+    fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
+    try:
+        fit.run(2)
+        assert fit.counters()["impl"] == L.IMPL_TMA
+    finally:
+        fit.close()
+    compare_trace(prob, ctx, n_iters=2, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+@pytest.mark.parametrize("err_mode", [L.ERR_AUTO, L.ERR_ALGEBRAIC, L.ERR_DIRECT])
+def test_fused_error_modes(ctx, err_mode, any_width):
+    prob = single_view_problem(500, 260, 4, seed=42)
+    compare_trace(prob, ctx, n_iters=8, err_mode=err_mode, impl=L.IMPL_FUSED)
+
+
+@pytest.mark.parametrize("clusters", [1, 2, 3, 7, 1000])
+def test_fused_forced_cluster_counts(ctx, clusters, monkeypatch):
+    """Any number of clusters (row groups split unevenly, clusters with a single group) gives the same factors."""
+    monkeypatch.setenv("RESNMTF_FU_CLUSTERS", str(clusters))
+    prob = single_view_problem(1500, 1800, 5, seed=7)
+    compare_trace(prob, ctx, n_iters=5, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(phi=200.0), dict(psi=200.0), dict(xi=50.0), dict(phi=200.0, psi=100.0, xi=50.0),
+    dict(phi=1000.0, psi=1000.0, partial=True), dict(phi=5.0, partial=True),
+])
+def test_fused_two_views_coupled(ctx, cfg, any_width):
+    prob = two_view_problem(seed=11, **cfg)
+    compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+def test_fused_mixed_with_two_pass_views(ctx):
+    """A fit whose views do not all qualify: view 1 (p = 1000) runs fused, view 2 (p = 300) the TMA kernels;
+    the phi coupling between them crosses the two kernel families."""
+    rng = np.random.default_rng(21)
+    shapes = [(400, 1000), (400, 300)]
+    k = 4
+    data = [synth.prep(synth.planted_view(n, p, 3, rng, 0.3, 0.3)[0]) for n, p in shapes]
+    inits = [synth.random_factors(n, p, k, rng) for n, p in shapes]
+    rn = [[f"r{i}" for i in range(400)]] * 2
+    cn = [[f"c{i}" for i in range(1000)], [f"d{i}" for i in range(300)]]
+    phi = np.zeros((2, 2))
+    phi[0, 1] = phi[1, 0] = 150.0
+    prob = Problem(data, [k, k], [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits], phi=phi,
+                   row_names=rn, col_names=cn)
+    fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
+    try:
+        fit.run(1)
+        assert_fused(fit)
+    finally:
+        fit.close()
+    compare_trace(prob, ctx, n_iters=5, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+def test_fused_bitwise_repeatable_and_matches_two_pass(ctx):
+    """Fixed summation orders: two runs are bit-identical; the two-pass kernels agree within the parity bar."""
+    prob = single_view_problem(3000, 2000, 6, seed=77)
+    outs = []
+    for impl in (L.IMPL_FUSED, L.IMPL_FUSED, L.IMPL_TMA):
+        fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=impl)
+        try:
+            fit.run(25)
+            outs.append(fit.get_factors(0) + (np.asarray(fit.errors()),))
+        finally:
+            fit.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert rel_err(a, b) <= RTOL
+
+
+def test_fused_convergence_rule(ctx, any_width):
+    """The device-side stop rule (R/main.r:55-81) fires on the oracle's sweep."""
+    prob = single_view_problem(400, 300, 3, seed=5)
+    ref = prob.oracle(max_iters=400)
+    fit = prob.device_fit(ctx, err_mode=L.ERR_AUTO, impl=L.IMPL_FUSED)
+    try:
+        done = fit.run(None, 1.0e-6, max_iters=400)
+        assert_fused(fit)
+        assert done == len(ref["All_Error"])
+        f, s, g, _, _ = fit.get_factors(0)
+        assert rel_err(f, ref["raw_f"][0]) <= RTOL
+        assert rel_err(g, ref["raw_g"][0]) <= RTOL
+        assert rel_err(s, ref["raw_s"][0]) <= RTOL
+        assert rel_err(fit.errors(), ref["All_Error"]) <= 1e-7
+    finally:
+        fit.close()
