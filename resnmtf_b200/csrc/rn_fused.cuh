@@ -6,18 +6,22 @@
 // 8 rows that is resident on chip can do both: P for its rows, the F update (update_f, R/update_steps.r:141-165),
 // and then its contribution X[rows,]' F_new[rows,] to T (update_g, :180-207), before the rows are dropped.
 // 8 rows x p columns of FP64 do not fit one SM (256 KB at p = 4000), so a CLUSTER of C = 1/2/4 CTAs splits the
-// columns (1024 per CTA) and exchanges the 8 x 8 partial of P through distributed shared memory.
+// columns (1008 per CTA) and exchanges the 8 x 8 partial of P through distributed shared memory.
 //
 //   X8 layout (HBM): X8[row group (8 rows)][column pair q][8 x 16 B]; the 16 B piece of row r holds
 //   (X[r][2q], X[r][2q+1]) and sits at piece position r ^ 2(q & 3).  A warp's share of a group (64 column pairs =
 //   8 KB) is one contiguous run = one bulk copy, and a verbatim copy in shared memory is bank-conflict-free for the
 //   LDS.128 fragment reads of both phases (each LDS.128 feeds two m8n8k4 MMAs).
-//   Roles per CTA (320 threads): 8 consumer warps (warp w owns data columns 128w..128w+127 of the CTA's 1024 for
-//   every row group: G fragments and the T accumulators of those columns live in registers for the whole kernel),
-//   1 producer warp (bulk copies into a 24-slot x 8 KB ring: a slot is read twice -- F phase, G phase -- and then
-//   released), 1 epilogue warp (sums the 8 warp partials of P, exchanges the CTA partial with the cluster peers by
-//   st.async + mbarrier complete_tx, runs the F update for the 8 rows redundantly in every CTA, writes F_new to
-//   shared memory for the G phase and -- rank 0 -- to HBM, accumulates F'F and colSums(F)).
+//   Roles per CTA (352 threads = 11 warps).  Warps 3 and 7 -- both on SM sub-partition 3 -- are the producer warp
+//   (bulk copies into a 27-slot x 7 KB ring: a slot is read twice, F phase and G phase, and then released) and the
+//   epilogue warp (sums the 9 warp partials of P, exchanges the CTA partial with the cluster peers by st.async +
+//   mbarrier complete_tx, runs the F update for the 8 rows redundantly in every CTA with the 8 x 8 products as
+//   DMMAs, writes F_new to shared memory for the G phase and -- rank 0 -- to HBM, accumulates F'F and colSums(F)).
+//   The other 9 warps (3 per sub-partition 0..2) are consumers: consumer c owns data columns 112c..112c+111 of the
+//   CTA's 1008 for every row group; the G fragments and the T accumulators of those columns live in registers for
+//   the whole kernel.  Keeping sub-partition 3 free of consumers matters: DMMA and scalar FP64 share one pipe per
+//   sub-partition, and an epilogue warp that queues behind two DMMA streams (first version, ncu: 37 % of consumer
+//   time waiting for F_new) is the critical path of the whole kernel.
 //   Software pipeline of a consumer warp: F phase of group i+1, then G phase of group i, so the exchange and the
 //   F update of group i+1 overlap the G phase MMAs of group i.
 //   Tail: every cluster publishes its T partial [pp8][8]; after a grid-wide arrival counter the 64-column groups
@@ -27,17 +31,19 @@
 #pragma once
 #include "rn_kernels.cuh"
 
-#define RN_FU_THREADS 320
-#define RN_FU_NB 8                                        // 16-column blocks per consumer warp and row group
-#define RN_FU_WCOLS (16 * RN_FU_NB)                       // data columns per consumer warp
-#define RN_FU_CCOLS (8 * RN_FU_WCOLS)                     // data columns per CTA (1024)
+#define RN_FU_THREADS 352                                 // 11 warps: 9 consumers, producer (warp 3), epilogue (warp 7)
+#define RN_FU_NCW 9                                       // consumer warps
+#define RN_FU_NCT (32 * RN_FU_NCW)                        // consumer threads (named barrier 1)
+#define RN_FU_NB 7                                        // 16-column blocks per consumer warp and row group
+#define RN_FU_WCOLS (16 * RN_FU_NB)                       // data columns per consumer warp (112)
+#define RN_FU_CCOLS (RN_FU_NCW * RN_FU_WCOLS)             // data columns per CTA (1008)
 #define RN_FU_SLOT_BYTES (RN_FU_NB * 1024)                // one warp's share of one row group
-#define RN_FU_NSLOT 24                                    // ring slots = 3 row groups
-#define RN_FU_RING_BYTES (RN_FU_NSLOT * RN_FU_SLOT_BYTES) // 192 KB
-#define RN_FU_MAXC 4                                      // largest cluster (columns <= 4096)
+#define RN_FU_NSLOT (3 * RN_FU_NCW)                       // ring slots = 3 row groups
+#define RN_FU_RING_BYTES (RN_FU_NSLOT * RN_FU_SLOT_BYTES) // 189 KB
+#define RN_FU_MAXC 4                                      // largest cluster (columns <= 4032)
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
-#define RN_FU_AUX_DOUBLES (2 * 8 * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8)
+#define RN_FU_AUX_DOUBLES (2 * RN_FU_NCW * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8)
 static inline size_t rn_fused_smem() {
   return (size_t)RN_FU_RING_BYTES + (size_t)RN_FU_AUX_DOUBLES * 8 + (2 * RN_FU_NSLOT + 6) * 8 + 16;
 }
@@ -111,25 +117,46 @@ __device__ __forceinline__ void rn_cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rn_cp_async_wait2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+__device__ __forceinline__ void rn_fu_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RN_FU_NCT) : "memory"); }
+
+// num / den without the ~30-instruction IEEE division sequence: hardware reciprocal seed, two Newton steps and one
+// residual correction (result within 1 ulp; the parity bar is 1e-9).  Operands outside the safe range (zero, huge,
+// tiny, Inf, NaN) take the exact division so that Inf / NaN behave as in R.
+__device__ __forceinline__ double rn_fast_div(double num, double den) {
+  const double ad = fabs(den), an = fabs(num);
+  if (!(ad > 1.0e-280 && ad < 1.0e280 && an < 1.0e280)) return num / den;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  double e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  double q = num * r;
+  const double rem = fma(-den, q, num);
+  return fma(rem, r, q);
+}
 
 template <int K>
 __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView vw, const RnFit ft, const int v,
                                                                   const int fuse_finish) {
   constexpr int KP = 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
-  constexpr int NB = RN_FU_NB, NSLOT = RN_FU_NSLOT, SLOT = RN_FU_SLOT_BYTES;
+  constexpr int NB = RN_FU_NB, NCW = RN_FU_NCW, NCT = RN_FU_NCT, NSLOT = RN_FU_NSLOT, SLOT = RN_FU_SLOT_BYTES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  if (ft.ctrl->done) return;  // uniform over the grid
+  const bool is_consumer = (warp & 3) != 3;
+  const int ci = warp - (warp >> 2);  // consumer index 0..8 (warps 0,1,2, 4,5,6, 8,9,10)
+  const int ctid = ci * 32 + lane;    // consumer thread index 0..287
+  if (ft.ctrl->done) return;          // uniform over the grid
 
   extern __shared__ __align__(128) unsigned char rn_smem[];
   unsigned char* ring = rn_smem;
-  double* Pw = reinterpret_cast<double*>(rn_smem + RN_FU_RING_BYTES);  // [2][8 warps][64]  warp partials of P
-  double* Pex = Pw + 2 * 8 * 64;                                        // [2][MAXC][64]     CTA partials (peers write)
-  double* Fp = Pex + 2 * RN_FU_MAXC * 64;                               // [2][8 rows][8]    F_new of a group
-  double* Ps = Fp + 2 * 64;                                             // [8][8]            P of the current group
-  double* Fo = Ps + 64;                                                 // [4][8][8]         old F rows (cp.async)
-  double* FSs = Fo + 4 * 64;                                            // [8][8]            F S of the current group
-  double* Ssm = FSs + 64;                                               // [K*K] (64 reserved)
+  double* Pw = reinterpret_cast<double*>(rn_smem + RN_FU_RING_BYTES);  // [2][NCW][64]  warp partials of P
+  double* Pex = Pw + 2 * NCW * 64;                                      // [2][MAXC][64] CTA partials (peers write)
+  double* Fp = Pex + 2 * RN_FU_MAXC * 64;                               // [2][8 rows][8] F_new of a group
+  double* Ps = Fp + 2 * 64;                                             // [8][8]        P of the current group
+  double* Fo = Ps + 64;                                                 // [4][8][8]     old F rows (cp.async)
+  double* Msm = Fo + 4 * 64;                                            // [8][8]        M = S W (zero padded)
+  double* Ssm = Msm + 64;                                               // [K*K] (64 reserved)
   double* Wsm = Ssm + 64;
   double* lamh = Wsm + 64;
   double* muh = lamh + 8;
@@ -154,7 +181,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       rn_mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      rn_mbar_init(&pw_full[i], 8);
+      rn_mbar_init(&pw_full[i], NCW);
       rn_mbar_init(&pex_full[i], 1);
       rn_mbar_init(&fp_full[i], 1);
     }
@@ -163,6 +190,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   if (tid < 64) {
     Ssm[tid] = (tid < KK) ? vw.S[tid] : 0.0;
     Wsm[tid] = 0.0;
+    Msm[tid] = 0.0;
   }
   if (tid < 8) {
     lamh[tid] = (tid < K) ? 0.5 * vw.lam[tid] : 0.0;
@@ -176,19 +204,27 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     Wsm[a + b * K] = s;
   }
   __syncthreads();
+  if (tid < KK) {  // M = S W: the denominator (F S) W of update_f is evaluated as F (S W)
+    const int b = tid % K, c = tid / K;
+    double s = 0.0;
+    for (int a = 0; a < K; ++a) s = fma(Ssm[b + a * K], Wsm[a + c * K], s);
+    Msm[b * 8 + c] = s;
+  }
+  __syncthreads();
   rn_cluster_sync();  // peers' mbarriers are initialised before anyone stores into them
 
-  double tacc[2 * NB][2];  // consumer warps: T accumulators of the warp's 128 columns (tile 2b+e: columns 16b+2g+e)
+  double tacc[2 * NB][2];  // consumer warps: T accumulators of the warp's 112 columns (tile 2b+e: columns 16b+2g+e)
 #pragma unroll
   for (int s = 0; s < 2 * NB; ++s) tacc[s][0] = tacc[s][1] = 0.0;
-  const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + (int64_t)(warp & 7) * RN_FU_WCOLS;
+  const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + (int64_t)ci * RN_FU_WCOLS;
 
-  if (warp == 8) {
+  if (warp == 3) {
     // ---- producer warp -------------------------------------------------------------------------------
     for (int i = 0; i < NGL; ++i) {
       const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
-      for (int w = 0; w < 8; ++w) {
-        const int cnt = i * 8 + w;
+#pragma unroll 1
+      for (int w = 0; w < NCW; ++w) {
+        const int cnt = i * NCW + w;
         const int st = cnt % NSLOT;
         const uint32_t ph = (uint32_t)((cnt / NSLOT) & 1);
         rn_mbar_wait(&empty[st], ph ^ 1u);
@@ -199,22 +235,16 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         __syncwarp();
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 7) {
     // ---- epilogue warp: lane (g,t) owns row g, factor columns 2t and 2t+1 of every row group ------------
     const int V = ft.n_views;
     const int kp = vw.kp;
     const int c0 = 2 * t, c1 = 2 * t + 1;
-    double Sa0[8], Sa1[8], Sn0[8], Sn1[8], Wd0[8], Wd1[8];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const bool in = b < K;
-      Sa0[b] = (in && c0 < K) ? Ssm[b + c0 * K] : 0.0;  // (F S)[c0] = sum_b f[b] S[b, c0]
-      Sa1[b] = (in && c1 < K) ? Ssm[b + c1 * K] : 0.0;
-      Sn0[b] = (in && c0 < K) ? Ssm[c0 + b * K] : 0.0;  // ((X G) t(S))[c0] = sum_a P[a] S[c0, a]
-      Sn1[b] = (in && c1 < K) ? Ssm[c1 + b * K] : 0.0;
-      Wd0[b] = (in && c0 < K) ? Wsm[b + c0 * K] : 0.0;  // ((F S) W)[c0] = sum_a FS[a] W[a, c0]
-      Wd1[b] = (in && c1 < K) ? Wsm[b + c1 * K] : 0.0;
-    }
+    // B operands of the 8x8 products: N = P t(S)  (B[a][c] = S[c, a]),  D = F M  (B[b][c] = M[b, c]); lane (g,t)
+    // supplies B[t][g] and B[t+4][g]
+    const double bs0 = (g < K && t < K) ? Ssm[g + t * K] : 0.0;
+    const double bs1 = (g < K && t + 4 < K) ? Ssm[g + (t + 4) * K] : 0.0;
+    const double bm0 = Msm[t * 8 + g], bm1 = Msm[(t + 4) * 8 + g];
     const double lam0 = lamh[c0], lam1 = lamh[c1];
     double phisum = 0.0;
     for (int w = 0; w < V; ++w) phisum += ft.phi[w + v * V];
@@ -236,17 +266,16 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
       prefetch_f(i + 2);
       if (lane == 0) rn_mbar_expect_tx(&pex_full[sl], csize * 512u);
+      // the old F rows of this group are on chip before any peer can be released to overwrite them in HBM
+      rn_cp_async_wait2();
       rn_mbar_wait(&pw_full[sl], ph);
-      double2 acc = *reinterpret_cast<const double2*>(Pw + (sl * 8) * 64 + 2 * lane);
+      double2 acc = *reinterpret_cast<const double2*>(Pw + (sl * NCW) * 64 + 2 * lane);
 #pragma unroll
-      for (int w = 1; w < 8; ++w) {
-        const double2 x = *reinterpret_cast<const double2*>(Pw + (sl * 8 + w) * 64 + 2 * lane);
+      for (int w = 1; w < NCW; ++w) {
+        const double2 x = *reinterpret_cast<const double2*>(Pw + (sl * NCW + w) * 64 + 2 * lane);
         acc.x += x.x;
         acc.y += x.y;
       }
-      // the old F rows of this group are on chip before any peer can be released to overwrite them in HBM
-      rn_cp_async_wait2();
-      __syncwarp();
       for (uint32_t rr = 0; rr < csize; ++rr)
         rn_st_async2(rn_mapa(my_pex + sl * (RN_FU_MAXC * 64 * 8), rr), acc.x, acc.y,
                      rn_mapa(rn_smem_u32(&pex_full[sl]), rr));
@@ -260,44 +289,18 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       *reinterpret_cast<double2*>(Ps + 2 * lane) = tot;
       __syncwarp();
       const double* fo = Fo + (i & 3) * 64 + g * 8;
-      double fr[8], pr[8];
-#pragma unroll
-      for (int b = 0; b < 8; b += 2) {
-        const double2 x = *reinterpret_cast<const double2*>(fo + b);
-        fr[b] = x.x;
-        fr[b + 1] = x.y;
-        const double2 y = *reinterpret_cast<const double2*>(Ps + g * 8 + b);
-        pr[b] = y.x;
-        pr[b + 1] = y.y;
-      }
-      double fs0 = 0.0, fs1 = 0.0, N0 = 0.0, N1 = 0.0;
-#pragma unroll
-      for (int b = 0; b < K; ++b) {
-        fs0 = fma(fr[b], Sa0[b], fs0);
-        fs1 = fma(fr[b], Sa1[b], fs1);
-        N0 = fma(pr[b], Sn0[b], N0);
-        N1 = fma(pr[b], Sn1[b], N1);
-      }
-      *reinterpret_cast<double2*>(FSs + g * 8 + c0) = make_double2(fs0, fs1);
-      __syncwarp();
-      double D0 = 0.0, D1 = 0.0;
-#pragma unroll
-      for (int a = 0; a < K; a += 2) {
-        const double2 x = *reinterpret_cast<const double2*>(FSs + g * 8 + a);
-        D0 = fma(x.x, Wd0[a], D0);
-        D1 = fma(x.x, Wd1[a], D1);
-        if (a + 1 < K) {
-          D0 = fma(x.y, Wd0[a + 1], D0);
-          D1 = fma(x.y, Wd1[a + 1], D1);
-        }
-      }
-      const int64_t r = (g0 + i) * 8 + g;
+      double N0 = 0.0, N1 = 0.0, D0 = 0.0, D1 = 0.0;
+      rn_dmma(N0, N1, Ps[g * 8 + t], bs0);
+      rn_dmma(D0, D1, fo[t], bm0);
+      rn_dmma(N0, N1, Ps[g * 8 + t + 4], bs1);
+      rn_dmma(D0, D1, fo[t + 4], bm1);
       const double2 fmine = *reinterpret_cast<const double2*>(fo + c0);
       const double f0 = fmine.x, f1 = fmine.y;
+      const int64_t r = (g0 + i) * 8 + g;
       double o0 = 0.0, o1 = 0.0;
       if (r < vw.n) {
         if (phisum == 0.0) {  // update_steps.r:152-155
-          double q0 = N0 / (D0 + lam0), q1 = N1 / (D1 + lam1);
+          double q0 = rn_fast_div(N0, D0 + lam0), q1 = rn_fast_div(N1, D1 + lam1);
           if (isnan(q0)) q0 = 1.0;
           if (isnan(q1)) q1 = 1.0;
           o0 = fabs(f0 * q0);
@@ -318,8 +321,8 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
             pc0 += (phw * m0) * nw;
             pc1 += (phw * m1) * nw;
           }
-          o0 = fabs(f0 * ((N0 + pc0 / nv) / ((D0 + phisum * f0) + lam0)));
-          o1 = fabs(f1 * ((N1 + pc1 / nv) / ((D1 + phisum * f1) + lam1)));
+          o0 = fabs(f0 * rn_fast_div(N0 + pc0 / nv, (D0 + phisum * f0) + lam0));
+          o1 = fabs(f1 * rn_fast_div(N1 + pc1 / nv, (D1 + phisum * f1) + lam1));
         }
         if (c0 >= K) o0 = 0.0;
         if (c1 >= K) o1 = 0.0;
@@ -332,15 +335,11 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&fp_full[sl]);
       if (rank == 0) {  // F'F and colSums(F) of this cluster's rows, off the critical path
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const double a = Fp[sl * 64 + rr * 8 + g];
-          const double2 b = *reinterpret_cast<const double2*>(Fp + sl * 64 + rr * 8 + c0);
-          ff0 = fma(a, b.x, ff0);
-          ff1 = fma(a, b.y, ff1);
-          cs0 += b.x;
-          cs1 += b.y;
-        }
+        const double x1 = Fp[sl * 64 + t * 8 + g], x2 = Fp[sl * 64 + (t + 4) * 8 + g];
+        rn_dmma(ff0, ff1, x1, x1);
+        rn_dmma(cs0, cs1, 1.0, x1);
+        rn_dmma(ff0, ff1, x2, x2);
+        rn_dmma(cs0, cs1, 1.0, x2);
       }
     }
     if (rank == 0) {
@@ -374,7 +373,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     const uint32_t off2b = (uint32_t)(g * 128 + ((rb ^ (2 * (g & 3))) * 16));
 
     auto f_phase = [&](int i) {
-      const int cnt = i * 8 + warp;
+      const int cnt = i * NCW + ci;
       const int st = cnt % NSLOT;
       rn_mbar_wait(&full[st], (uint32_t)((cnt / NSLOT) & 1));
       const unsigned char* xs = ring + st * SLOT + off1;
@@ -385,12 +384,12 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         rn_dmma(pe0, pe1, x.x, gfr[s][0]);
         rn_dmma(po0, po1, x.y, gfr[s][1]);
       }
-      *reinterpret_cast<double2*>(Pw + ((i & 1) * 8 + warp) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
+      *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&pw_full[i & 1]);
     };
     auto g_phase = [&](int i) {
-      const int cnt = i * 8 + warp;
+      const int cnt = i * NCW + ci;
       const int st = cnt % NSLOT;
       rn_mbar_wait(&fp_full[i & 1], (uint32_t)((i >> 1) & 1));
       const double fa = Fp[(i & 1) * 64 + ra * 8 + g];
@@ -415,7 +414,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     }
   }
   rn_cluster_sync();  // every st.async of this cluster has landed before any of its CTAs may exit
-  if (warp >= 8) return;
+  if (!is_consumer) return;
 
   // ---- tail (consumer warps): publish T partials, then the column-group epilogues ------------------------
   {
@@ -428,8 +427,8 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
             make_double2(tacc[2 * b + e][0], tacc[2 * b + e][1]);
   }
   __threadfence();
-  rn_consumer_sync();
-  if (tid == 0) atomicAdd(&vw.misc_ticket[3], 1);
+  rn_fu_consumer_sync();
+  if (ctid == 0) atomicAdd(&vw.misc_ticket[3], 1);
 
   double* Ts = reinterpret_cast<double*>(ring);  // the ring is idle now: epilogue scratch lives there
   double* Gs = Ts + RN_COL_GROUP * KP;
@@ -442,32 +441,32 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   const int64_t pp = vw.pp;
   const int64_t NG = (pp + RN_COL_GROUP - 1) / RN_COL_GROUP;
   if ((int64_t)blockIdx.x >= NG) return;  // no column group for this CTA (it must not wait: the finisher re-arms)
-  if (tid == 0) {
+  if (ctid == 0) {
     while (rn_ld_acquire(&vw.misc_ticket[3]) < (int)gridDim.x) __nanosleep(64);
   }
-  rn_consumer_sync();
+  rn_fu_consumer_sync();
   __threadfence();
   bool ff_ready = false;
   const int64_t tstride = vw.pp8 * KP;
   for (int64_t grp = blockIdx.x; grp < NG; grp += gridDim.x) {
     const int64_t j0 = grp * RN_COL_GROUP;
     const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
-    rn_consumer_sync();  // previous group's epilogue is done with Ts / Gs
-    for (int i = tid; i < RN_COL_GROUP * KP; i += 256)
+    rn_fu_consumer_sync();  // previous group's epilogue is done with Ts / Gs
+    for (int i = ctid; i < RN_COL_GROUP * KP; i += NCT)
       Ts[i] = (i < 8 * njb * KP) ? rn_sum_strided(vw.Tpart + j0 * KP + i, tstride, n_clusters) : 0.0;
     if (!ff_ready) {
-      if (tid == 0) {
+      if (ctid == 0) {
         while (rn_ld_acquire(&vw.misc_ticket[2]) < (int)n_clusters) __nanosleep(64);
       }
-      rn_consumer_sync();
+      rn_fu_consumer_sync();
       __threadfence();
-      if (tid < NFF) {
+      if (ctid < NFF) {
         double s = 0.0;
-        for (int64_t i = 0; i < n_clusters; ++i) s += __ldcg(vw.FFpart + i * NFF + tid);
-        FtFs[tid] = s;
+        for (int64_t i = 0; i < n_clusters; ++i) s += __ldcg(vw.FFpart + i * NFF + ctid);
+        FtFs[ctid] = s;
       }
-      rn_consumer_sync();
-      for (int o = tid; o < KK; o += 256) {  // V = crossprod(F) %*% S
+      rn_fu_consumer_sync();
+      for (int o = ctid; o < KK; o += NCT) {  // V = crossprod(F) %*% S
         const int a = o % K, c = o / K;
         double s = 0.0;
         for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
@@ -475,24 +474,24 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       }
       ff_ready = true;
     }
-    rn_consumer_sync();
-    if (tid < RN_COL_GROUP) {
-      const int64_t j = j0 + tid;
+    rn_fu_consumer_sync();
+    if (ctid < RN_COL_GROUP) {
+      const int64_t j = j0 + ctid;
       double gn[K];
       if (j < vw.p) {
         double Tj[K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) Tj[c] = Ts[tid * KP + c];
+        for (int c = 0; c < K; ++c) Tj[c] = Ts[ctid * KP + c];
         rn_update_g_row<K>(vw, ft, v, j, Tj, Ssm, Vs, muh, gn);
       } else {
 #pragma unroll
         for (int c = 0; c < K; ++c) gn[c] = 0.0;
       }
 #pragma unroll
-      for (int c = 0; c < K; ++c) Gs[tid * K + c] = gn[c];
+      for (int c = 0; c < K; ++c) Gs[ctid * K + c] = gn[c];
     }
-    rn_consumer_sync();
-    for (int o = tid; o < NOUT; o += 256) {
+    rn_fu_consumer_sync();
+    for (int o = ctid; o < NOUT; o += NCT) {
       double s = 0.0;
       if (o < KK) {
         const int a = o % K, b = o / K;
@@ -507,19 +506,19 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       vw.GGpart[grp * NOUT + o] = s;
     }
     __threadfence();
-    rn_consumer_sync();
-    if (tid == 0) *s_flag = (atomicAdd(&vw.misc_ticket[0], 1) == (int)NG - 1);
-    rn_consumer_sync();
+    rn_fu_consumer_sync();
+    if (ctid == 0) *s_flag = (atomicAdd(&vw.misc_ticket[0], 1) == (int)NG - 1);
+    rn_fu_consumer_sync();
     if (!*s_flag) continue;
     __threadfence();
     // ---- last column group done: finish the view -----------------------------------------------------------
-    for (int o = tid; o < NOUT; o += 256) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, NG);
-    if (tid == 0) {
+    for (int o = ctid; o < NOUT; o += NCT) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, NG);
+    if (ctid == 0) {
       vw.misc_ticket[0] = 0;
       vw.misc_ticket[2] = 0;
       vw.misc_ticket[3] = 0;
     }
-    rn_consumer_sync();
-    rn_view_finish<K, 256, true>(vw, ft, v, tid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
+    rn_fu_consumer_sync();
+    rn_view_finish<K, NCT, true>(vw, ft, v, ctid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
   }
 }

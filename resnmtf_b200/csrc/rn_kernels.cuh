@@ -298,7 +298,7 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Ssm[b + c * K], s);
     Us[a + c * K] = s;
   }
-  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
   else __syncthreads();
   for (int o = tid; o < KK; o += NT) {  // update_s
     const int a = o % K, b = o / K;
@@ -322,7 +322,7 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     }
     Sn[o] = out;
   }
-  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
   else __syncthreads();
   for (int o = tid; o < KK; o += NT) vw.S[o] = Sn[o];
   if (tid < K) {  // update_lm
@@ -336,7 +336,7 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     for (int b = 0; b < K; ++b) s = fma(FtFs[a + b * K], Sn[b + c * K], s);
     Us[a + c * K] = s;
   }
-  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
   else __syncthreads();
   for (int o = tid; o < KK; o += NT) {
     const int a = o % K, b = o / K;
@@ -344,7 +344,7 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     for (int c = 0; c < K; ++c) q = fma(Us[a + c * K], GtGn[c + b * K], q);
     red[o] = (q - 2.0 * An[o]) * Sn[o];
   }
-  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, 256;" ::: "memory");
+  if constexpr (CONSUMER_BAR) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
   else __syncthreads();
   if (tid == 0) {
     double s = 0.0;

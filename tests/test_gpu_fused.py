@@ -37,10 +37,10 @@ def test_fused_ragged_shapes(ctx, shape, any_width):
     compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
 
 
-@pytest.mark.parametrize("shape,k", [((100, 1000), 3), ((700, 1024), 8), ((257, 1900), 5), ((90, 2048), 4),
-                                     ((333, 4000), 5), ((1200, 3300), 8), ((40, 4096), 2)])
+@pytest.mark.parametrize("shape,k", [((100, 1000), 3), ((700, 1008), 8), ((257, 1900), 5), ((90, 2016), 4),
+                                     ((333, 4000), 5), ((1200, 3300), 8), ((40, 4032), 2)])
 def test_fused_cluster_widths(ctx, shape, k):
-    """p up to 1024 runs on single CTAs, up to 2048 on CTA pairs, up to 4096 on 4-CTA clusters (default padding rule)."""
+    """p up to 1008 runs on single CTAs, up to 2016 on CTA pairs, up to 4032 on 4-CTA clusters (default padding rule)."""
     n, p = shape
     prob = single_view_problem(n, p, k, seed=500 + n + p, n_planted=4)
     fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
@@ -53,7 +53,7 @@ def test_fused_cluster_widths(ctx, shape, k):
 
 
 def test_fused_wide_view_falls_back(ctx):
-    """p > 4096 does not fit a 4-CTA cluster: the view runs the two-pass TMA kernels and says so."""
+    """p > 4032 does not fit a 4-CTA cluster: the view runs the two-pass TMA kernels and says so."""
     prob = single_view_problem(64, 4100, 3, seed=9)
     fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
     try:
