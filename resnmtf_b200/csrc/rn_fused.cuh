@@ -13,15 +13,16 @@
 //   8 KB) is one contiguous run = one bulk copy, and a verbatim copy in shared memory is bank-conflict-free for the
 //   LDS.128 fragment reads of both phases (each LDS.128 feeds two m8n8k4 MMAs).
 //   Roles per CTA (352 threads = 11 warps).  Warps 3 and 7 -- both on SM sub-partition 3 -- are the producer warp
-//   (bulk copies into a 27-slot x 7 KB ring: a slot is read twice, F phase and G phase, and then released) and the
-//   epilogue warp (sums the 9 warp partials of P, exchanges the CTA partial with the cluster peers by st.async +
-//   mbarrier complete_tx, runs the F update for the 8 rows redundantly in every CTA with the 8 x 8 products as
-//   DMMAs, writes F_new to shared memory for the G phase and -- rank 0 -- to HBM, accumulates F'F and colSums(F)).
-//   The other 9 warps (3 per sub-partition 0..2) are consumers: consumer c owns data columns 112c..112c+111 of the
-//   CTA's 1008 for every row group; the G fragments and the T accumulators of those columns live in registers for
-//   the whole kernel.  Keeping sub-partition 3 free of consumers matters: DMMA and scalar FP64 share one pipe per
-//   sub-partition, and an epilogue warp that queues behind two DMMA streams (first version, ncu: 37 % of consumer
-//   time waiting for F_new) is the critical path of the whole kernel.
+//   (bulk copies into a ring of 3 row groups x 63 KB: a warp's slot is read twice, F phase and G phase, and then
+//   released) and the epilogue warp (sums the 9 warp partials of P, exchanges the CTA partial with the cluster
+//   peers by st.async + mbarrier complete_tx, runs the F update for the 8 rows redundantly in every CTA with the
+//   8 x 8 products as DMMAs, writes F_new to shared memory for the G phase and -- rank 0 -- to HBM, accumulates F'F
+//   and colSums(F)).  The other 9 warps (3 per sub-partition 0..2) are consumers: consumer c owns the 7 blocks of
+//   16 columns 7c..7c+6 of the CTA's 63 for every row group; the G fragments and the T accumulators of those
+//   columns live in registers for the whole kernel.  Keeping sub-partition 3 free of consumers matters: DMMA and
+//   scalar FP64 share one pipe per sub-partition, and an epilogue warp that queues behind DMMA streams becomes the
+//   critical path of the whole kernel (measured on C2, k = 8: epilogue sharing a sub-partition with two consumers
+//   178 us per iteration, with one light consumer 162 us, alone 146 us).
 //   Software pipeline of a consumer warp: F phase of group i+1, then G phase of group i, so the exchange and the
 //   F update of group i+1 overlap the G phase MMAs of group i.
 //   Tail: every cluster publishes its T partial [pp8][8]; after a grid-wide arrival counter the 64-column groups
@@ -35,11 +36,11 @@
 #define RN_FU_NCW 9                                       // consumer warps
 #define RN_FU_NCT (32 * RN_FU_NCW)                        // consumer threads (named barrier 1)
 #define RN_FU_NB 7                                        // 16-column blocks per consumer warp and row group
-#define RN_FU_WCOLS (16 * RN_FU_NB)                       // data columns per consumer warp (112)
-#define RN_FU_CCOLS (RN_FU_NCW * RN_FU_WCOLS)             // data columns per CTA (1008)
-#define RN_FU_SLOT_BYTES (RN_FU_NB * 1024)                // one warp's share of one row group
-#define RN_FU_NSLOT (3 * RN_FU_NCW)                       // ring slots = 3 row groups
-#define RN_FU_RING_BYTES (RN_FU_NSLOT * RN_FU_SLOT_BYTES) // 189 KB
+#define RN_FU_CBLOCKS 63                                  // 16-column blocks per CTA
+#define RN_FU_CCOLS (16 * RN_FU_CBLOCKS)                  // data columns per CTA (1008)
+#define RN_FU_GROUP_BYTES (RN_FU_CBLOCKS * 1024)          // a CTA's share of one row group (63 KB)
+#define RN_FU_NSLOT (3 * RN_FU_NCW)                       // (row group in the ring, consumer warp) slots
+#define RN_FU_RING_BYTES (3 * RN_FU_GROUP_BYTES)          // 189 KB = 3 row groups
 #define RN_FU_MAXC 4                                      // largest cluster (columns <= 4032)
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
@@ -117,6 +118,19 @@ __device__ __forceinline__ void rn_cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rn_cp_async_wait2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+// sum of p[0], p[stride], ..., p[(n-1)*stride] in index order, all loads of a 32-batch in flight at once (one L2 round
+// trip per batch instead of one per 8): the cross-cluster / cross-group reductions of the tail are latency-bound
+__device__ __forceinline__ double rn_sum_wide(const double* p, int64_t stride, int n) {
+  double s = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    double v[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[q] = (i0 + q < n) ? __ldcg(p + (int64_t)(i0 + q) * stride) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s += v[q];
+  }
+  return s;
+}
 __device__ __forceinline__ void rn_fu_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RN_FU_NCT) : "memory"); }
 
 // num / den without the ~30-instruction IEEE division sequence: hardware reciprocal seed, two Newton steps and one
@@ -140,12 +154,14 @@ template <int K>
 __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView vw, const RnFit ft, const int v,
                                                                   const int fuse_finish) {
   constexpr int KP = 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
-  constexpr int NB = RN_FU_NB, NCW = RN_FU_NCW, NCT = RN_FU_NCT, NSLOT = RN_FU_NSLOT, SLOT = RN_FU_SLOT_BYTES;
+  constexpr int NB = RN_FU_NB, NCW = RN_FU_NCW, NCT = RN_FU_NCT, NSLOT = RN_FU_NSLOT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const bool is_consumer = (warp & 3) != 3;
+  const bool is_consumer = warp != 3 && warp != 7;
   const int ci = warp - (warp >> 2);  // consumer index 0..8 (warps 0,1,2, 4,5,6, 8,9,10)
   const int ctid = ci * 32 + lane;    // consumer thread index 0..287
+  constexpr int nb = NB;              // column blocks of this consumer (uniform; the loops below allow nb < NB)
+  const int boff = NB * ci;
   if (ft.ctrl->done) return;          // uniform over the grid
 
   extern __shared__ __align__(128) unsigned char rn_smem[];
@@ -216,21 +232,23 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   double tacc[2 * NB][2];  // consumer warps: T accumulators of the warp's 112 columns (tile 2b+e: columns 16b+2g+e)
 #pragma unroll
   for (int s = 0; s < 2 * NB; ++s) tacc[s][0] = tacc[s][1] = 0.0;
-  const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + (int64_t)ci * RN_FU_WCOLS;
+  const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + 16 * boff;
 
   if (warp == 3) {
     // ---- producer warp -------------------------------------------------------------------------------
     for (int i = 0; i < NGL; ++i) {
       const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
+      const int gs = i % 3;
+      const uint32_t ph = (uint32_t)((i / 3) & 1);
 #pragma unroll 1
       for (int w = 0; w < NCW; ++w) {
-        const int cnt = i * NCW + w;
-        const int st = cnt % NSLOT;
-        const uint32_t ph = (uint32_t)((cnt / NSLOT) & 1);
+        const int wnb = NB;
+        const int wboff = NB * w;
+        const int st = gs * NCW + w;
         rn_mbar_wait(&empty[st], ph ^ 1u);
         if (lane == 0) {
-          rn_mbar_expect_tx(&full[st], SLOT);
-          rn_bulk_g2s(ring + st * SLOT, src + w * (SLOT / 8), SLOT, &full[st]);
+          rn_mbar_expect_tx(&full[st], (uint32_t)wnb * 1024u);
+          rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + wboff * 1024, src + wboff * 128, (uint32_t)wnb * 1024u, &full[st]);
         }
         __syncwarp();
       }
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int64_t col = colbase + 8 * s + 2 * t + e;
-        gfr[s][e] = (col < vw.pp) ? vw.G[col * KP + g] : 0.0;
+        gfr[s][e] = (s < 2 * nb && col < vw.pp) ? vw.G[col * KP + g] : 0.0;
       }
     const int ra = (t & 1) + 4 * (t >> 1);  // G-phase K slot t <-> rows {0,1,4,5} (first MMA), {2,3,6,7} (second)
     const int rb = ra + 2;
@@ -373,39 +391,41 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     const uint32_t off2b = (uint32_t)(g * 128 + ((rb ^ (2 * (g & 3))) * 16));
 
     auto f_phase = [&](int i) {
-      const int cnt = i * NCW + ci;
-      const int st = cnt % NSLOT;
-      rn_mbar_wait(&full[st], (uint32_t)((cnt / NSLOT) & 1));
-      const unsigned char* xs = ring + st * SLOT + off1;
+      const int gs = i % 3;
+      rn_mbar_wait(&full[gs * NCW + ci], (uint32_t)((i / 3) & 1));
+      const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024 + off1;
       double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;
 #pragma unroll
       for (int s = 0; s < 2 * NB; ++s) {
-        const double2 x = *reinterpret_cast<const double2*>(xs + s * 512);
-        rn_dmma(pe0, pe1, x.x, gfr[s][0]);
-        rn_dmma(po0, po1, x.y, gfr[s][1]);
+        if (s < 2 * nb) {  // uniform over the warp
+          const double2 x = *reinterpret_cast<const double2*>(xs + s * 512);
+          rn_dmma(pe0, pe1, x.x, gfr[s][0]);
+          rn_dmma(po0, po1, x.y, gfr[s][1]);
+        }
       }
       *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&pw_full[i & 1]);
     };
     auto g_phase = [&](int i) {
-      const int cnt = i * NCW + ci;
-      const int st = cnt % NSLOT;
+      const int gs = i % 3;
       rn_mbar_wait(&fp_full[i & 1], (uint32_t)((i >> 1) & 1));
       const double fa = Fp[(i & 1) * 64 + ra * 8 + g];
       const double fb = Fp[(i & 1) * 64 + rb * 8 + g];
-      const unsigned char* xs = ring + st * SLOT;
+      const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024;
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        const double2 xa = *reinterpret_cast<const double2*>(xs + off2a + b * 1024);
-        const double2 xb = *reinterpret_cast<const double2*>(xs + off2b + b * 1024);
-        rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xa.x, fa);
-        rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xa.y, fa);
-        rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
-        rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
+        if (b < nb) {  // uniform over the warp
+          const double2 xa = *reinterpret_cast<const double2*>(xs + off2a + b * 1024);
+          const double2 xb = *reinterpret_cast<const double2*>(xs + off2b + b * 1024);
+          rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xa.x, fa);
+          rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xa.y, fa);
+          rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
+          rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
+        }
       }
       __syncwarp();
-      if (lane == 0) rn_mbar_arrive(&empty[st]);
+      if (lane == 0) rn_mbar_arrive(&empty[gs * NCW + ci]);
     };
     if (NGL > 0) f_phase(0);
     for (int i = 0; i < NGL; ++i) {
@@ -423,8 +443,9 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int e = 0; e < 2; ++e)
-        *reinterpret_cast<double2*>(tp + (16 * b + 2 * g + e) * KP + 2 * t) =
-            make_double2(tacc[2 * b + e][0], tacc[2 * b + e][1]);
+        if (b < nb)
+          *reinterpret_cast<double2*>(tp + (16 * b + 2 * g + e) * KP + 2 * t) =
+              make_double2(tacc[2 * b + e][0], tacc[2 * b + e][1]);
   }
   __threadfence();
   rn_fu_consumer_sync();
@@ -453,18 +474,14 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
     rn_fu_consumer_sync();  // previous group's epilogue is done with Ts / Gs
     for (int i = ctid; i < RN_COL_GROUP * KP; i += NCT)
-      Ts[i] = (i < 8 * njb * KP) ? rn_sum_strided(vw.Tpart + j0 * KP + i, tstride, n_clusters) : 0.0;
+      Ts[i] = (i < 8 * njb * KP) ? rn_sum_wide(vw.Tpart + j0 * KP + i, tstride, (int)n_clusters) : 0.0;
     if (!ff_ready) {
       if (ctid == 0) {
         while (rn_ld_acquire(&vw.misc_ticket[2]) < (int)n_clusters) __nanosleep(64);
       }
       rn_fu_consumer_sync();
       __threadfence();
-      if (ctid < NFF) {
-        double s = 0.0;
-        for (int64_t i = 0; i < n_clusters; ++i) s += __ldcg(vw.FFpart + i * NFF + ctid);
-        FtFs[ctid] = s;
-      }
+      if (ctid < NFF) FtFs[ctid] = rn_sum_wide(vw.FFpart + ctid, NFF, (int)n_clusters);
       rn_fu_consumer_sync();
       for (int o = ctid; o < KK; o += NCT) {  // V = crossprod(F) %*% S
         const int a = o % K, c = o / K;
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     if (!*s_flag) continue;
     __threadfence();
     // ---- last column group done: finish the view -----------------------------------------------------------
-    for (int o = ctid; o < NOUT; o += NCT) fin[o] = rn_sum_strided(vw.GGpart + o, NOUT, NG);
+    for (int o = ctid; o < NOUT; o += NCT) fin[o] = rn_sum_wide(vw.GGpart + o, NOUT, (int)NG);
     if (ctid == 0) {
       vw.misc_ticket[0] = 0;
       vw.misc_ticket[2] = 0;
