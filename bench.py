@@ -12,8 +12,10 @@ one update-iteration (update_matrices sweep + error, R/main.r:56-80) of each of 
   e2e        the same through the reference-facing call (one res_nmtf_inner-style fit per k through the C
              ABI with HOST buffers: H2D of X and the initial factors, `steps` sweeps, D2H of the factors
              and the error history), host-timed around the calls
-  roofline   the dominant kernel (rn_g_step_tma: X'.F stream + fused G/S update) against the measured HBM copy
-             peak
+  roofline   the dominant kernel against the measured HBM copy peak.  Default path: rn_fused_step, the one-pass
+             kernel that does the F step and the G step with a single read of X (algorithmic bytes per launch
+             8(np + 2nk + 3pk): X once, F read + written, G read as fragments + read + written); with
+             RESNMTF_IMPL=3 the two-pass TMA kernels (rn_f_step_tma / rn_g_step_tma, one read of X each)
   cpu_baseline / --impl reference: the NumPy restatement of the reference's own operation sequence
              (3 GEMM passes over X + materialised X_hat, oracle/resnmtf_oracle.py) on the host cores
 
@@ -184,11 +186,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if there is one."""
+def ncu_traffic(kernel):
+    """dram bytes per launch (k = 8) of `kernel` from the committed ncu capture, if there is one."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get("rn_g_step_tma_dram_bytes_per_launch")
+            return json.load(fh).get(f"{kernel}_dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -253,24 +255,31 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel, measured live (CUDA events between launches) --------------
     prof_iters = 20
-    bytes_f = bytes_g = ms_f = ms_g = 0.0
+    kern = {"rn_f_step_tma": [0.0, 0.0], "rn_g_step_tma": [0.0, 0.0], "rn_fused_step": [0.0, 0.0]}  # bytes, ms
     for k in K_SWEEP:
         pr = fits[k].profile(prof_iters)
-        ms_f += pr["f_step"]["ms"]
-        ms_g += pr["g_stream"]["ms"]
-        bytes_f += prof_iters * 8.0 * (N_ROWS * N_COLS + 2 * N_ROWS * k + N_COLS * k)
-        bytes_g += prof_iters * 8.0 * (N_ROWS * N_COLS + N_ROWS * k + 2 * N_COLS * k)
+        for name, cls, nbytes in (
+                ("rn_f_step_tma", "f_step", 8.0 * (N_ROWS * N_COLS + 2 * N_ROWS * k + N_COLS * k)),
+                ("rn_g_step_tma", "g_stream", 8.0 * (N_ROWS * N_COLS + N_ROWS * k + 2 * N_COLS * k)),
+                ("rn_fused_step", "fused_step", 8.0 * (N_ROWS * N_COLS + 2 * N_ROWS * k + 3 * N_COLS * k))):
+            if pr[cls]["ms"] > 0.0:
+                kern[name][0] += prof_iters * nbytes
+                kern[name][1] += pr[cls]["ms"]
     peak, peak_src = measured_peak()
-    dom = ("rn_g_step_tma", bytes_g, ms_g) if ms_g >= ms_f else ("rn_f_step_tma", bytes_f, ms_f)
-    achieved = dom[1] / dom[2] * 1e-6
+    ran = {nm: bm for nm, bm in kern.items() if bm[1] > 0.0}
+    dom = max(ran, key=lambda nm: ran[nm][1])  # the kernel the step spends most of its time in
+    achieved = ran[dom][0] / ran[dom][1] * 1e-6
     alg_bytes_step = sum(fits[k].counters()["alg_bytes_per_iter"] for k in K_SWEEP)
     roofline = {
-        "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
-        "other_kernel": {"name": "rn_f_step_tma" if dom[0] == "rn_g_step_tma" else "rn_g_step_tma",
-                         "achieved": (bytes_f / ms_f if dom[0] == "rn_g_step_tma" else bytes_g / ms_g) * 1e-6},
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(dom),
+        "us_per_launch": 1e3 * ran[dom][1] / (prof_iters * len(K_SWEEP)),
+        "other_kernels": {nm: {"achieved": bm[0] / bm[1] * 1e-6} for nm, bm in ran.items() if nm != dom},
         "whole_step_achieved": alg_bytes_step * args.steps / ms * 1e-6,
         "alg_bytes_per_step": alg_bytes_step,
+        "note": ("one-pass kernel: X is read once per update-iteration (B_min of SURVEY 8d); the co-limiter is the "
+                 "FP64 tensor pipe (DMMA) of 3 of 4 sub-partitions on the 132 SMs a 4-CTA cluster grid can occupy"
+                 if dom == "rn_fused_step" else "two-pass kernels: X is read once per kernel, twice per iteration"),
     }
 
     # ---- e2e: reference-facing fit call per k with HOST buffers ----------------------------------------

@@ -157,8 +157,9 @@ int resnmtf_fit_get_view_errors(resnmtf_fit* fit, double* err, double* data_norm
 int resnmtf_fit_get_counters(resnmtf_fit* fit, resnmtf_counters* out);
 
 /* Runs n_iters sweeps with CUDA events between the kernel launches (no graph) and returns the summed
- * device time per kernel class: ms[0] F step (X.G + F update), ms[1] G stream (X'.F), ms[2] G epilogue
- * (G, S, lambda, mu update + algebraic error), ms[3] direct residual pass, ms[4] iteration
+ * device time per kernel class: ms[0] F step (X.G + F update), ms[1] G step (X'.F + G, S, lambda, mu update +
+ * algebraic error), ms[2] one-pass fused step (views on RESNMTF_IMPL_FUSED: both of the above in one launch), ms[3]
+ * direct residual pass, ms[4] iteration
  * bookkeeping; launches[i] is the number of timed intervals of that class. */
 int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[5], int64_t launches[5]);
 

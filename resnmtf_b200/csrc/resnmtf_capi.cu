@@ -978,6 +978,9 @@ static int build_plan(resnmtf_fit* fit) {
       n_tpart = (size_t)nc * d.pp8 * KP;
       n_ffpart = (size_t)nc * (K * K + K);
       n_ggpart = (size_t)std::max(d.col_groups, d.gepi_ctas) * (2 * K * K + K);
+      if (rn_env_int("RESNMTF_FU_TIMELINE", 0) && !d.fu_timeline &&
+          (rc = rn_alloc(fit, &d.fu_timeline, (size_t)sms * 12)))
+        return rc;
       if (!d.X8) {  // second copy of X in the 8-row-group layout (shared by every fit attached to the same data)
         const size_t x8_count = (size_t)d.ldx * d.pp8;
         bool convert = true;
@@ -1350,6 +1353,28 @@ extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, in
   fit->counters.direct_error_passes = fit->h_ctrl.direct_passes;
   fit->counters.alg_bytes_per_iter = alg_bytes_per_iter(fit);
   if (iters_done) *iters_done = fit->h_ctrl.iters - it0;
+  for (int v = 0; v < fit->V; ++v) {  // developer timeline of the last fused launch (RESNMTF_FU_TIMELINE=1)
+    const RnView& d = fit->views[v].d;
+    if (!d.fu_timeline || !d.fu_csize) continue;
+    const int grid = d.fu_clusters * d.fu_csize;
+    std::vector<long long> tl((size_t)grid * 12);
+    RN_CUDA(cudaMemcpy(tl.data(), d.fu_timeline, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long t0 = tl[0];
+    for (int b = 0; b < grid; ++b) t0 = std::min(t0, tl[(size_t)b * 12]);
+    static const char* nm[9] = {"entry", "setup done", "main loop done", "cluster sync", "all T published",
+                                "Ts + F'F ready", "group epilogue done", "view finished", "G'G|A partials summed"};
+    std::fprintf(stderr, "[resnmtf fused timeline] view %d, grid %d (ns after the first CTA's entry: min / max)\n", v, grid);
+    for (int sidx = 0; sidx < 9; ++sidx) {
+      long long lo = -1, hi = -1;
+      for (int b = 0; b < grid; ++b) {
+        const long long x = tl[(size_t)b * 12 + sidx];
+        if (x < t0) continue;  // stamp not written by this CTA in the last launch
+        if (lo < 0 || x - t0 < lo) lo = x - t0;
+        if (x - t0 > hi) hi = x - t0;
+      }
+      std::fprintf(stderr, "  %-22s %8lld %8lld\n", nm[sidx], lo, hi);
+    }
+  }
   if (conv && fit->h_ctrl.done == 2)
     return rn_fail(RESNMTF_E_NAN, "mean error is NaN: missing value where TRUE/FALSE needed (R/main.r:55)");
   return RESNMTF_OK;

@@ -118,18 +118,26 @@ __device__ __forceinline__ void rn_cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void rn_cp_async_wait2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
-// sum of p[0], p[stride], ..., p[(n-1)*stride] in index order, all loads of a 32-batch in flight at once (one L2 round
+// sum of p[0], p[stride], ..., p[(n-1)*stride] in index order, all loads of a 40-batch in flight at once (one L2 round
 // trip per batch instead of one per 8): the cross-cluster / cross-group reductions of the tail are latency-bound
 __device__ __forceinline__ double rn_sum_wide(const double* p, int64_t stride, int n) {
   double s = 0.0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    double v[32];
+  for (int i0 = 0; i0 < n; i0 += 40) {
+    double v[40];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) v[q] = (i0 + q < n) ? __ldcg(p + (int64_t)(i0 + q) * stride) : 0.0;
+    for (int q = 0; q < 40; ++q) v[q] = (i0 + q < n) ? __ldcg(p + (int64_t)(i0 + q) * stride) : 0.0;
 #pragma unroll
-    for (int q = 0; q < 32; ++q) s += v[q];
+    for (int q = 0; q < 40; ++q) s += v[q];
   }
   return s;
+}
+// developer timeline: stamp slot `which` of this CTA with the global nanosecond timer (no-op unless enabled)
+__device__ __forceinline__ void rn_fu_stamp(const RnView& vw, int which) {
+  if (vw.fu_timeline) {
+    long long tns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+    vw.fu_timeline[(int64_t)blockIdx.x * 12 + which] = tns;
+  }
 }
 __device__ __forceinline__ void rn_fu_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RN_FU_NCT) : "memory"); }
 
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   constexpr int nb = NB;              // column blocks of this consumer (uniform; the loops below allow nb < NB)
   const int boff = NB * ci;
   if (ft.ctrl->done) return;          // uniform over the grid
+  if (tid == 0) rn_fu_stamp(vw, 0);
 
   extern __shared__ __align__(128) unsigned char rn_smem[];
   unsigned char* ring = rn_smem;
@@ -228,6 +237,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   }
   __syncthreads();
   rn_cluster_sync();  // peers' mbarriers are initialised before anyone stores into them
+  if (tid == 0) rn_fu_stamp(vw, 1);
 
   double tacc[2 * NB][2];  // consumer warps: T accumulators of the warp's 112 columns (tile 2b+e: columns 16b+2g+e)
 #pragma unroll
@@ -433,8 +443,10 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       g_phase(i);
     }
   }
+  if (tid == 0) rn_fu_stamp(vw, 2);
   rn_cluster_sync();  // every st.async of this cluster has landed before any of its CTAs may exit
   if (!is_consumer) return;
+  if (tid == 0) rn_fu_stamp(vw, 3);
 
   // ---- tail (consumer warps): publish T partials, then the column-group epilogues ------------------------
   {
@@ -463,10 +475,12 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   const int64_t NG = (pp + RN_COL_GROUP - 1) / RN_COL_GROUP;
   if ((int64_t)blockIdx.x >= NG) return;  // no column group for this CTA (it must not wait: the finisher re-arms)
   if (ctid == 0) {
-    while (rn_ld_acquire(&vw.misc_ticket[3]) < (int)gridDim.x) __nanosleep(64);
+    while (rn_ld_acquire(&vw.misc_ticket[3]) < (int)gridDim.x) __nanosleep(32);
+    while (rn_ld_acquire(&vw.misc_ticket[2]) < (int)n_clusters) __nanosleep(32);
   }
   rn_fu_consumer_sync();
   __threadfence();
+  if (ctid == 0) rn_fu_stamp(vw, 4);
   bool ff_ready = false;
   const int64_t tstride = vw.pp8 * KP;
   for (int64_t grp = blockIdx.x; grp < NG; grp += gridDim.x) {
@@ -476,11 +490,6 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     for (int i = ctid; i < RN_COL_GROUP * KP; i += NCT)
       Ts[i] = (i < 8 * njb * KP) ? rn_sum_wide(vw.Tpart + j0 * KP + i, tstride, (int)n_clusters) : 0.0;
     if (!ff_ready) {
-      if (ctid == 0) {
-        while (rn_ld_acquire(&vw.misc_ticket[2]) < (int)n_clusters) __nanosleep(64);
-      }
-      rn_fu_consumer_sync();
-      __threadfence();
       if (ctid < NFF) FtFs[ctid] = rn_sum_wide(vw.FFpart + ctid, NFF, (int)n_clusters);
       rn_fu_consumer_sync();
       for (int o = ctid; o < KK; o += NCT) {  // V = crossprod(F) %*% S
@@ -492,6 +501,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       ff_ready = true;
     }
     rn_fu_consumer_sync();
+    if (ctid == 0) rn_fu_stamp(vw, 5);
     if (ctid < RN_COL_GROUP) {
       const int64_t j = j0 + ctid;
       double gn[K];
@@ -526,6 +536,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     rn_fu_consumer_sync();
     if (ctid == 0) *s_flag = (atomicAdd(&vw.misc_ticket[0], 1) == (int)NG - 1);
     rn_fu_consumer_sync();
+    if (ctid == 0) rn_fu_stamp(vw, 6);
     if (!*s_flag) continue;
     __threadfence();
     // ---- last column group done: finish the view -----------------------------------------------------------
@@ -536,6 +547,8 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       vw.misc_ticket[3] = 0;
     }
     rn_fu_consumer_sync();
+    if (ctid == 0) rn_fu_stamp(vw, 8);
     rn_view_finish<K, NCT, true>(vw, ft, v, ctid, fin, FtFs, Ssm, Us, Sn, red, fuse_finish);
+    if (ctid == 0) rn_fu_stamp(vw, 7);
   }
 }

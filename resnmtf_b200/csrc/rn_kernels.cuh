@@ -283,6 +283,13 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
   const double* GtGn = fin;
   const double* An = fin + KK;
   const double* csGn = fin + 2 * KK;
+  // this runs in ONE CTA at the very end of the iteration: issue the global loads its serial part needs now
+  double lam_old = 0.0, mu_old = 0.0, xn = 0.0;
+  if (tid < K) {
+    lam_old = vw.lam[tid];
+    mu_old = vw.mu[tid];
+  }
+  if (tid == 0) xn = vw.scal[0];
   for (int o = tid; o < KK; o += NT) {
     vw.GtG[o] = GtGn[o];
     vw.A[o] = An[o];
@@ -326,8 +333,8 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
   else __syncthreads();
   for (int o = tid; o < KK; o += NT) vw.S[o] = Sn[o];
   if (tid < K) {  // update_lm
-    vw.lam[tid] = FtFs[KK + tid] * vw.lam[tid];
-    vw.mu[tid] = csGn[tid] * vw.mu[tid];
+    vw.lam[tid] = FtFs[KK + tid] * lam_old;
+    vw.mu[tid] = csGn[tid] * mu_old;
   }
   // algebraic error: (||X||^2 - 2 <A,S'> + <(F'F S') G'G, S'>) / ||X||^2
   for (int o = tid; o < KK; o += NT) {
@@ -349,14 +356,12 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
   if (tid == 0) {
     double s = 0.0;
     for (int i = 0; i < KK; ++i) s += red[i];
-    const double xn = vw.scal[0];
     const double e = (xn + s) / xn;
     vw.scal[1] = e;
     vw.scal[2] = e;
     vw.flags[0] = (ft.err_mode == 2) ? 1 : 0;  // DIRECT: the residual pass that follows overwrites scal[1]
     if (ft.err_mode == 0 && e < 1.0e-3) ft.ctrl->want_direct = 1;  // AUTO: cancellation would cost digits
-    if (fuse_finish) {
-      __threadfence();
+    if (fuse_finish) {  // the other views' errors were written by earlier launches, this view's by this thread
       if (ft.err_mode == 0 && ft.ctrl->want_direct) ft.ctrl->done = 3;  // pause: host re-does the error
       else rn_finish_dev(ft);
     }

@@ -199,7 +199,7 @@ class DeviceFit:
         ms = (C.c_double * 5)()
         cnt = (C.c_int64 * 5)()
         L.check(self._lib.resnmtf_fit_profile(self._h, int(n_iters), ms, cnt))
-        names = ("f_step", "g_stream", "g_epilogue", "residual", "finish")
+        names = ("f_step", "g_stream", "fused_step", "residual", "finish")
         return {nm: {"ms": float(ms[i]), "intervals": int(cnt[i])} for i, nm in enumerate(names)}
 
     # ---- outputs -----------------------------------------------------------------------------

@@ -43,10 +43,10 @@ def main():
             fit.run(args.iters)
             c = fit.counters()
             line = f"k={k} impl={ {1: 'DFMA', 2: 'DMMA', 3: 'TMA', 4: 'FUSED'}.get(c['impl'], c['impl']) }"
-            for name in ("f_step", "g_stream", "g_epilogue", "residual", "finish"):
+            for name in ("f_step", "g_stream", "fused_step", "residual", "finish"):
                 ms = prof[name]["ms"] / max(1, args.iters)
                 line += f" | {name} {ms * 1e3:8.1f} us"
-                if ms > 0 and (name in ("f_step", "g_stream") or (name == "g_epilogue" and c["impl"] == 4)):  # fused: class 2
+                if ms > 0 and name in ("f_step", "g_stream", "fused_step"):
                     line += f" ({xbytes / ms * 1e-6:7.0f} GB/s)"
             it_ms = c["device_ms"] / args.iters
             line += f" || graph: {it_ms * 1e3:8.1f} us/iter, {c['alg_bytes_per_iter'] / it_ms * 1e-6:7.0f} GB/s alg"
