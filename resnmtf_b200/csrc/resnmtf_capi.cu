@@ -272,13 +272,40 @@ static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, c
 }
 
 // Cluster size of the fused path for a view, 0 when it does not qualify: k <= 8, not row-sharded, p within
-// 4 x 1024 columns and not padded by more than RESNMTF_FUSED_MAX_PAD percent (default 130).
+// 8 x 1008 columns and not padded by more than RESNMTF_FUSED_MAX_PAD percent (default 135: the one-pass kernel
+// costs ~0.68 of the two-pass pair per padded column).
 static int fused_csize(const RnView& d, int n_ranks) {
   if (d.k > 8 || n_ranks > 1) return 0;
-  const double max_pad = rn_env_int("RESNMTF_FUSED_MAX_PAD", 130) / 100.0;
-  for (int c = 1; c <= RN_FU_MAXC; c *= 2)
+  const double max_pad = rn_env_int("RESNMTF_FUSED_MAX_PAD", 135) / 100.0;
+  for (int c = 1; c <= RN_FU_MAXC; ++c)
     if ((int64_t)c * RN_FU_CCOLS >= d.p) return ((double)c * RN_FU_CCOLS <= max_pad * (double)d.p) ? c : 0;
   return 0;
+}
+
+// Most clusters of `csz` CTAs of the fused kernel the device keeps resident at once (0: the cluster does not fit).
+static int fused_max_clusters(int K, int csz, int sms) {
+  GStepSkFn fn = fused_step_fn(K);
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rn_fused_smem()) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(csz * sms));
+  cfg.blockDim = dim3(RN_FU_THREADS);
+  cfg.dynamicSmemBytes = rn_fused_smem();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csz;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
 }
 
 // Launch of a streaming kernel with (optionally) a persisting-L2 access-policy window over the head of X.
@@ -936,33 +963,26 @@ static int build_plan(resnmtf_fit* fit) {
     RnView& d = vh.d;
     // the one-pass fused kernel serves the views that qualify (fused_csize); the others of the fit run the
     // two-pass TMA kernels
-    const int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->n_ranks) : 0;
+    int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->n_ranks) : 0;
+    if (csz && rn_env_int("RESNMTF_FUSED_PHI", 0) == 0) {
+      // a phi-coupled view gathers rows of its partners' F inside the F update: on the fused kernel that is a chain
+      // of dependent global loads on the one warp every consumer waits for (measured on the C4 structure: 12.7 ms
+      // per iteration against 5.0 ms two-pass), so such views stay on the two-pass kernels
+      for (int w = 0; w < fit->V; ++w)
+        if (w != v && fit->h_phi[(size_t)w + (size_t)v * fit->V] != 0.0) csz = 0;
+    }
+    const int K = d.k, KP = d.kp;
+    // the persistent cluster grid must be resident at once; a cluster shape that strands too many SMs loses to the
+    // two-pass kernels, which use all of them
+    const int max_clusters = csz ? fused_max_clusters(K, csz, sms) : 0;
+    if (csz && (max_clusters < 1 || max_clusters * csz * 100 < sms * rn_env_int("RESNMTF_FUSED_MIN_SM_PCT", 70))) csz = 0;
     const int impl = (impl_fit == RESNMTF_IMPL_FUSED && !csz) ? RESNMTF_IMPL_TMA : impl_fit;
     vh.impl = impl;
     const bool mma = use_mma(vh, impl);
-    const int K = d.k, KP = d.kp;
     size_t n_ppart, n_tpart, n_ffpart, n_ggpart;
     d.fu_csize = d.fu_clusters = 0;
     if (csz) {
       any_fused = true;
-      GStepSkFn fn = fused_step_fn(K);
-      RN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rn_fused_smem()));
-      int max_clusters = 0;
-      {
-        cudaLaunchConfig_t cfg;
-        std::memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)(csz * sms));
-        cfg.blockDim = dim3(RN_FU_THREADS);
-        cfg.dynamicSmemBytes = rn_fused_smem();
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)csz;
-        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        RN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
-      }
-      RN_CHECK(max_clusters >= 1, RESNMTF_E_CUDA, "the fused kernel's cluster does not fit on this device");
       const int64_t groups = (d.n + 7) / 8;
       int nc = (int)std::min<int64_t>(max_clusters, groups);
       nc = std::max(1, std::min(nc, rn_env_int("RESNMTF_FU_CLUSTERS", nc)));

@@ -5,7 +5,7 @@
 // T = X' F_new, and F_new[r,] depends on the WHOLE row r of X (P = X G) -- but only on that row.  So a group of
 // 8 rows that is resident on chip can do both: P for its rows, the F update (update_f, R/update_steps.r:141-165),
 // and then its contribution X[rows,]' F_new[rows,] to T (update_g, :180-207), before the rows are dropped.
-// 8 rows x p columns of FP64 do not fit one SM (256 KB at p = 4000), so a CLUSTER of C = 1/2/4 CTAs splits the
+// 8 rows x p columns of FP64 do not fit one SM (256 KB at p = 4000), so a CLUSTER of C = 1..8 CTAs splits the
 // columns (1008 per CTA) and exchanges the 8 x 8 partial of P through distributed shared memory.
 //
 //   X8 layout (HBM): X8[row group (8 rows)][column pair q][8 x 16 B]; the 16 B piece of row r holds
@@ -41,7 +41,7 @@
 #define RN_FU_GROUP_BYTES (RN_FU_CBLOCKS * 1024)          // a CTA's share of one row group (63 KB)
 #define RN_FU_NSLOT (3 * RN_FU_NCW)                       // (row group in the ring, consumer warp) slots
 #define RN_FU_RING_BYTES (3 * RN_FU_GROUP_BYTES)          // 189 KB = 3 row groups
-#define RN_FU_MAXC 4                                      // largest cluster (columns <= 4032)
+#define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
 #define RN_FU_AUX_DOUBLES (2 * RN_FU_NCW * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8)

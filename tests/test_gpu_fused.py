@@ -14,8 +14,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def any_width(monkeypatch):
-    """Lets narrow views (p << 1024) take the fused path too: the kernel pads the columns to the cluster width."""
+    """Lets narrow views (p << 1008) take the fused path too (the kernel pads the columns to the cluster width), and
+    phi-coupled views as well (by default they stay on the two-pass kernels: the gather sits on the critical warp)."""
     monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
+    monkeypatch.setenv("RESNMTF_FUSED_PHI", "1")
 
 
 def assert_fused(fit):
@@ -40,7 +42,7 @@ def test_fused_ragged_shapes(ctx, shape, any_width):
 @pytest.mark.parametrize("shape,k", [((100, 1000), 3), ((700, 1008), 8), ((257, 1900), 5), ((90, 2016), 4),
                                      ((333, 4000), 5), ((1200, 3300), 8), ((40, 4032), 2)])
 def test_fused_cluster_widths(ctx, shape, k):
-    """p up to 1008 runs on single CTAs, up to 2016 on CTA pairs, up to 4032 on 4-CTA clusters (default padding rule)."""
+    """p up to 1008 runs on single CTAs, up to 2016 on CTA pairs, ... up to 4032 on 4-CTA clusters (default padding rule)."""
     n, p = shape
     prob = single_view_problem(n, p, k, seed=500 + n + p, n_planted=4)
     fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
@@ -53,8 +55,8 @@ def test_fused_cluster_widths(ctx, shape, k):
 
 
 def test_fused_wide_view_falls_back(ctx):
-    """p > 4032 does not fit a 4-CTA cluster: the view runs the two-pass TMA kernels and says so."""
-    prob = single_view_problem(64, 4100, 3, seed=9)
+    """p > 8064 does not fit an 8-CTA cluster: the view runs the two-pass TMA kernels and says so."""
+    prob = single_view_problem(64, 8100, 3, seed=9)
     fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
     try:
         fit.run(2)
@@ -87,9 +89,10 @@ def test_fused_two_views_coupled(ctx, cfg, any_width):
     compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
 
 
-def test_fused_mixed_with_two_pass_views(ctx):
+def test_fused_mixed_with_two_pass_views(ctx, monkeypatch):
     """A fit whose views do not all qualify: view 1 (p = 1000) runs fused, view 2 (p = 300) the TMA kernels;
     the phi coupling between them crosses the two kernel families."""
+    monkeypatch.setenv("RESNMTF_FUSED_PHI", "1")
     rng = np.random.default_rng(21)
     shapes = [(400, 1000), (400, 300)]
     k = 4
@@ -143,3 +146,18 @@ def test_fused_convergence_rule(ctx, any_width):
         assert rel_err(fit.errors(), ref["All_Error"]) <= 1e-7
     finally:
         fit.close()
+
+
+@pytest.mark.parametrize("p,k", [(2100, 3), (5000, 5), (5900, 4), (7000, 8), (8064, 6)])
+def test_fused_odd_cluster_sizes(ctx, p, k, monkeypatch):
+    """Clusters of 3, 5, 6, 7 and 8 CTAs (p up to 8 x 1008 columns)."""
+    monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
+    monkeypatch.setenv("RESNMTF_FUSED_MIN_SM_PCT", "1")
+    prob = single_view_problem(150, p, k, seed=900 + p, n_planted=4)
+    fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
+    try:
+        fit.run(1)
+        assert_fused(fit)
+    finally:
+        fit.close()
+    compare_trace(prob, ctx, n_iters=3, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
