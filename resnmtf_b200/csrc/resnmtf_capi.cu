@@ -884,6 +884,7 @@ extern "C" int resnmtf_fit_set_restrictions(resnmtf_fit* fit, const double* phi,
         RN_CHECK(fit->views[v].d.k == fit->views[w].d.k, RESNMTF_E_INVALID,
                  "xi couples views with different k (non-conformable arrays in the reference)");
   fit->meta_dirty = true;
+  fit->plan_dirty = true;  // which views qualify for the fused kernel depends on their phi partners
   return RESNMTF_OK;
 }
 
@@ -909,6 +910,7 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
     modes[slot] = RN_MODE_NA;
     ptrs[slot] = nullptr;
     fit->meta_dirty = true;
+    fit->plan_dirty = true;
     return RESNMTF_OK;
   }
   std::vector<int32_t> map((size_t)dim_v, -1);
@@ -927,6 +929,7 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
   modes[slot] = RN_MODE_MAP;
   ptrs[slot] = own[w];
   fit->meta_dirty = true;
+  fit->plan_dirty = true;
   return RESNMTF_OK;
 }
 
@@ -964,12 +967,13 @@ static int build_plan(resnmtf_fit* fit) {
     // the one-pass fused kernel serves the views that qualify (fused_csize); the others of the fit run the
     // two-pass TMA kernels
     int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->n_ranks) : 0;
-    if (csz && rn_env_int("RESNMTF_FUSED_PHI", 0) == 0) {
-      // a phi-coupled view gathers rows of its partners' F inside the F update: on the fused kernel that is a chain
-      // of dependent global loads on the one warp every consumer waits for (measured on the C4 structure: 12.7 ms
-      // per iteration against 5.0 ms two-pass), so such views stay on the two-pass kernels
-      for (int w = 0; w < fit->V; ++w)
-        if (w != v && fit->h_phi[(size_t)w + (size_t)v * fit->V] != 0.0) csz = 0;
+    if (csz) {  // the fused kernel prefetches the phi gathers of at most RN_FU_MAXPART partner views
+      int partners = 0;
+      for (int w = 0; w < fit->V; ++w) {
+        const size_t slot = (size_t)w + (size_t)v * fit->V;
+        if (w != v && fit->h_phi[slot] != 0.0 && fit->h_rowmode[slot] != RN_MODE_NA) ++partners;
+      }
+      if (partners > RN_FU_MAXPART || (partners > 0 && rn_env_int("RESNMTF_FUSED_PHI", 1) == 0)) csz = 0;
     }
     const int K = d.k, KP = d.kp;
     // the persistent cluster grid must be resident at once; a cluster shape that strands too many SMs loses to the

@@ -12,17 +12,25 @@
 //   (X[r][2q], X[r][2q+1]) and sits at piece position r ^ 2(q & 3).  A warp's share of a group (64 column pairs =
 //   8 KB) is one contiguous run = one bulk copy, and a verbatim copy in shared memory is bank-conflict-free for the
 //   LDS.128 fragment reads of both phases (each LDS.128 feeds two m8n8k4 MMAs).
-//   Roles per CTA (352 threads = 11 warps).  Warps 3 and 7 -- both on SM sub-partition 3 -- are the producer warp
+//   Roles per CTA (384 threads = 12 warps).  Warps 3, 7 and 11 -- all on SM sub-partition 3 -- are the producer warp
 //   (bulk copies into a ring of 3 row groups x 63 KB: a warp's slot is read twice, F phase and G phase, and then
 //   released) and the epilogue warp (sums the 9 warp partials of P, exchanges the CTA partial with the cluster
 //   peers by st.async + mbarrier complete_tx, runs the F update for the 8 rows redundantly in every CTA with the
 //   8 x 8 products as DMMAs, writes F_new to shared memory for the G phase and -- rank 0 -- to HBM, accumulates F'F
-//   and colSums(F)).  The other 9 warps (3 per sub-partition 0..2) are consumers: consumer c owns the 7 blocks of
+//   and colSums(F)) and the auxiliary warp (everything the F update needs that does not depend on P: it prefetches
+//   the old F rows and, for phi-coupled views, forms the coupling sum, two row groups ahead of the epilogue warp,
+//   which is instruction-bound -- one warp of dependent code per row group -- and must only carry the critical
+//   path).  The other 9 warps (3 per sub-partition 0..2) are consumers: consumer c owns the 7 blocks of
 //   16 columns 7c..7c+6 of the CTA's 63 for every row group; the G fragments and the T accumulators of those
 //   columns live in registers for the whole kernel.  Keeping sub-partition 3 free of consumers matters: DMMA and
 //   scalar FP64 share one pipe per sub-partition, and an epilogue warp that queues behind DMMA streams becomes the
 //   critical path of the whole kernel (measured on C2, k = 8: epilogue sharing a sub-partition with two consumers
 //   178 us per iteration, with one light consumer 162 us, alone 146 us).
+//   phi coupling (star_prod_relevant, R/utils.r:63-78) gathers rows of the partner views' F through int32 row maps:
+//   two dependent global loads per partner and row, which must not sit on the epilogue warp's critical path.  They
+//   run as a cp.async pipeline in the auxiliary warp: map entries of row group i+4, partner rows of group i+2 (using
+//   the entries fetched two iterations earlier), coupling sum of group i from shared memory, handed to the epilogue
+//   warp through a 4-slot mbarrier ring together with the old F rows.
 //   Software pipeline of a consumer warp: F phase of group i+1, then G phase of group i, so the exchange and the
 //   F update of group i+1 overlap the G phase MMAs of group i.
 //   Tail: every cluster publishes its T partial [pp8][8]; after a grid-wide arrival counter the 64-column groups
@@ -32,7 +40,7 @@
 #pragma once
 #include "rn_kernels.cuh"
 
-#define RN_FU_THREADS 352                                 // 11 warps: 9 consumers, producer (warp 3), epilogue (warp 7)
+#define RN_FU_THREADS 384                                 // 12 warps: 9 consumers, producer (3), epilogue (7), auxiliary (11)
 #define RN_FU_NCW 9                                       // consumer warps
 #define RN_FU_NCT (32 * RN_FU_NCW)                        // consumer threads (named barrier 1)
 #define RN_FU_NB 7                                        // 16-column blocks per consumer warp and row group
@@ -44,9 +52,13 @@
 #define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
-#define RN_FU_AUX_DOUBLES (2 * RN_FU_NCW * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8)
+#define RN_FU_MAXPART 7                                   // most phi partners of a view on the fused path
+// Pw | Pex | Fp | Ps | Fo | Msm | Ssm | Wsm | lamh | muh | partner table | SrcIdx | Fg | Pcn
+#define RN_FU_AUX_DOUBLES                                                                                      \
+  (2 * RN_FU_NCW * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8 + 48 + 8 * 8 * 8 / 2 + \
+   3 * RN_FU_MAXPART * 64 + 4 * 64)
 static inline size_t rn_fused_smem() {
-  return (size_t)RN_FU_RING_BYTES + (size_t)RN_FU_AUX_DOUBLES * 8 + (2 * RN_FU_NSLOT + 6) * 8 + 16;
+  return (size_t)RN_FU_RING_BYTES + (size_t)RN_FU_AUX_DOUBLES * 8 + (2 * RN_FU_NSLOT + 6 + 8) * 8 + 16;
 }
 
 // position (in doubles) of X[r][j] in the X8 layout with pp8 (even) columns
@@ -117,7 +129,11 @@ __device__ __forceinline__ void rn_cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(rn_smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void rn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void rn_cp_async_wait2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+__device__ __forceinline__ void rn_cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rn_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rn_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void rn_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // sum of p[0], p[stride], ..., p[(n-1)*stride] in index order, all loads of a 40-batch in flight at once (one L2 round
 // trip per batch instead of one per 8): the cross-cluster / cross-group reductions of the tail are latency-bound
 __device__ __forceinline__ double rn_sum_wide(const double* p, int64_t stride, int n) {
@@ -165,7 +181,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   constexpr int NB = RN_FU_NB, NCW = RN_FU_NCW, NCT = RN_FU_NCT, NSLOT = RN_FU_NSLOT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const bool is_consumer = warp != 3 && warp != 7;
+  const bool is_consumer = (warp & 3) != 3;
   const int ci = warp - (warp >> 2);  // consumer index 0..8 (warps 0,1,2, 4,5,6, 8,9,10)
   const int ctid = ci * 32 + lane;    // consumer thread index 0..287
   constexpr int nb = NB;              // column blocks of this consumer (uniform; the loops below allow nb < NB)
@@ -185,12 +201,22 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   double* Wsm = Ssm + 64;
   double* lamh = Wsm + 64;
   double* muh = lamh + 8;
-  uint64_t* full = reinterpret_cast<uint64_t*>(muh + 8);
+  double* cpl_ph = muh + 8;                                                // phi partner table (epilogue warp)
+  double* cpl_nw = cpl_ph + 8;
+  const double** cpl_F = reinterpret_cast<const double**>(cpl_nw + 8);
+  const int32_t** cpl_map = reinterpret_cast<const int32_t**>(cpl_nw + 16);
+  int* cpl_kp = reinterpret_cast<int*>(cpl_nw + 24);                       // [8] kp, then [8] = number of partners
+  int32_t* SrcIdx = reinterpret_cast<int32_t*>(cpl_nw + 40);               // [8 groups][8 partners][8 rows]
+  double* Fg = cpl_nw + 40 + 8 * 8 * 8 / 2;                                // [3 groups][MAXPART][8 rows][8]
+  double* Pcn = Fg + 3 * RN_FU_MAXPART * 64;                               // [4 groups][8 rows][8] coupling sums / n
+  uint64_t* full = reinterpret_cast<uint64_t*>(Pcn + 4 * 64);
   uint64_t* empty = full + NSLOT;
   uint64_t* pw_full = empty + NSLOT;
   uint64_t* pex_full = pw_full + 2;
   uint64_t* fp_full = pex_full + 2;
-  int* s_flag = reinterpret_cast<int*>(fp_full + 2);
+  uint64_t* aux_full = fp_full + 2;   // [4] old F rows + coupling sum of a row group are in shared memory
+  uint64_t* aux_empty = aux_full + 4;  // [4] the epilogue warp is done with them
+  int* s_flag = reinterpret_cast<int*>(aux_empty + 4);
 
   const uint32_t rank = rn_cluster_rank(), csize = rn_cluster_size();
   const int64_t n_clusters = gridDim.x / csize, cid = blockIdx.x / csize;
@@ -209,6 +235,10 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       rn_mbar_init(&pw_full[i], NCW);
       rn_mbar_init(&pex_full[i], 1);
       rn_mbar_init(&fp_full[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      rn_mbar_init(&aux_full[i], 1);
+      rn_mbar_init(&aux_empty[i], 1);
     }
     rn_mbar_init_fence();
   }
@@ -263,8 +293,111 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         __syncwarp();
       }
     }
+  } else if (warp == 11) {
+    // ---- auxiliary warp: lane (g,t) <-> row g, factor columns 2t, 2t+1; runs two row groups ahead of the epilogue --
+    const int V = ft.n_views;
+    const int kp = vw.kp;
+    const int c0 = 2 * t, c1 = 2 * t + 1;
+    double phisum = 0.0;
+    for (int w = 0; w < V; ++w) phisum += ft.phi[w + v * V];
+    const double nv = (double)vw.n_glob;
+    // phi partners in view order (zero phi and NA pairs are skipped, as in star_prod_relevant)
+    const bool coupled = phisum != 0.0;
+    if (coupled) {
+      if (lane == 0) {
+        int np_ = 0;
+        for (int w = 0; w < V && np_ < RN_FU_MAXPART; ++w) {
+          const double phw = ft.phi[w + v * V];
+          if (phw == 0.0) continue;
+          const int mode = ft.rowmode[w + v * V];
+          if (mode == RN_MODE_NA) continue;
+          const RnView* ow = ft.views + w;
+          cpl_ph[np_] = phw;
+          cpl_nw[np_] = (double)ow->n_glob;
+          cpl_F[np_] = ow->F;
+          cpl_kp[np_] = ow->kp;
+          cpl_map[np_] = (mode == RN_MODE_MAP) ? ft.rowmap[w + v * V] : nullptr;  // NULL pair: nothing overwritten
+          ++np_;
+        }
+        cpl_kp[8] = np_;
+      }
+      __syncwarp();
+    }
+    const int np = coupled ? cpl_kp[8] : 0;
+    auto prefetch_f = [&](int i) {  // old F rows of local group i -> Fo[i & 3]
+      if (i < NGL) {
+        const int64_t r = (g0 + i) * 8 + g;
+        rn_cp_async8(Fo + (i & 3) * 64 + g * 8 + c0, vw.F + rn_fidx(r, c0, kp));
+        rn_cp_async8(Fo + (i & 3) * 64 + g * 8 + c1, vw.F + rn_fidx(r, c1, kp));
+      }
+    };
+    auto prefetch_idx = [&](int i) {  // row-map entries of local group i (lane t of a row: partners t, t+4)
+      if (i < NGL) {
+        const int64_t r = (g0 + i) * 8 + g;
+        if (r < vw.n)
+          for (int pi = t; pi < np; pi += 4) {
+            const int32_t* mp = cpl_map[pi];
+            if (mp) rn_cp_async4(SrcIdx + ((i & 7) * 8 + pi) * 8 + g, mp + r);
+          }
+      }
+    };
+    auto prefetch_gather = [&](int i) {  // partner rows of local group i (its map entries are in shared memory)
+      if (i < NGL) {
+        const int64_t r = (g0 + i) * 8 + g;
+        if (r < vw.n)
+          for (int pi = 0; pi < np; ++pi) {
+            if (!cpl_map[pi]) continue;
+            const int src = SrcIdx[((i & 7) * 8 + pi) * 8 + g];
+            if (src < 0) continue;
+            double* dst = Fg + ((i % 3) * RN_FU_MAXPART + pi) * 64 + g * 8;
+            rn_cp_async8(dst + c0, cpl_F[pi] + rn_fidx(src, c0, cpl_kp[pi]));
+            rn_cp_async8(dst + c1, cpl_F[pi] + rn_fidx(src, c1, cpl_kp[pi]));
+          }
+      }
+    };
+    if (coupled) {
+      for (int i = 0; i < 4; ++i) prefetch_idx(i);
+      rn_cp_async_commit();
+      rn_cp_async_wait_all();
+      __syncwarp();
+    }
+    for (int i = 0; i < 2; ++i) {  // one cp.async batch per row group: the batch of group i is complete at iteration i
+      prefetch_f(i);
+      if (coupled) prefetch_gather(i);
+      rn_cp_async_commit();
+    }
+    for (int i = 0; i < NGL; ++i) {
+      // the slots written below held group i-2 (old F rows) and i-4 (coupling sum): the epilogue is done with them
+      if (i >= 2) rn_mbar_wait(&aux_empty[(i - 2) & 3], (uint32_t)(((i - 2) >> 2) & 1));
+      rn_cp_async_wait1();  // batch i: old F rows + partner rows of this group, map entries of group i+2
+      __syncwarp();
+      prefetch_f(i + 2);
+      if (coupled) {
+        prefetch_gather(i + 2);
+        prefetch_idx(i + 4);
+      }
+      rn_cp_async_commit();
+      if (coupled) {
+        const double2 fmine = *reinterpret_cast<const double2*>(Fo + (i & 3) * 64 + g * 8 + c0);
+        double pc0 = 0.0, pc1 = 0.0;
+        for (int pi = 0; pi < np; ++pi) {
+          const int src = cpl_map[pi] ? SrcIdx[((i & 7) * 8 + pi) * 8 + g] : -1;
+          double m0 = fmine.x, m1 = fmine.y;  // row not shared with this partner: the view's own row (utils.r:69-73)
+          if (src >= 0) {
+            const double2 mm = *reinterpret_cast<const double2*>(Fg + ((i % 3) * RN_FU_MAXPART + pi) * 64 + g * 8 + c0);
+            m0 = mm.x;
+            m1 = mm.y;
+          }
+          pc0 += (cpl_ph[pi] * m0) * cpl_nw[pi];
+          pc1 += (cpl_ph[pi] * m1) * cpl_nw[pi];
+        }
+        *reinterpret_cast<double2*>(Pcn + (i & 3) * 64 + g * 8 + c0) = make_double2(pc0 / nv, pc1 / nv);
+      }
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&aux_full[i & 3]);
+    }
   } else if (warp == 7) {
-    // ---- epilogue warp: lane (g,t) owns row g, factor columns 2t and 2t+1 of every row group ------------
+    // ---- epilogue warp: lane (g,t) owns row g, factor columns 2t and 2t+1 of every row group; critical path only --
     const int V = ft.n_views;
     const int kp = vw.kp;
     const int c0 = 2 * t, c1 = 2 * t + 1;
@@ -276,26 +409,17 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     const double lam0 = lamh[c0], lam1 = lamh[c1];
     double phisum = 0.0;
     for (int w = 0; w < V; ++w) phisum += ft.phi[w + v * V];
-    const double nv = (double)vw.n_glob;
+    const bool coupled = phisum != 0.0;
     double ff0 = 0.0, ff1 = 0.0, cs0 = 0.0, cs1 = 0.0;
     const uint32_t my_pex = rn_smem_u32(Pex + rank * 64 + 2 * lane);
-    auto prefetch_f = [&](int i) {  // old F rows of local group i -> Fo[i & 3]
-      if (i < NGL) {
-        const int64_t r = (g0 + i) * 8 + g;
-        rn_cp_async8(Fo + (i & 3) * 64 + g * 8 + c0, vw.F + rn_fidx(r, c0, kp));
-        rn_cp_async8(Fo + (i & 3) * 64 + g * 8 + c1, vw.F + rn_fidx(r, c1, kp));
-      }
-      rn_cp_async_commit();
-    };
-    prefetch_f(0);
-    prefetch_f(1);
+    const int sig0 = rn_sigma(c0), sig1 = rn_sigma(c1);
     for (int i = 0; i < NGL; ++i) {
       const int sl = i & 1;
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
-      prefetch_f(i + 2);
       if (lane == 0) rn_mbar_expect_tx(&pex_full[sl], csize * 512u);
-      // the old F rows of this group are on chip before any peer can be released to overwrite them in HBM
-      rn_cp_async_wait2();
+      // old F rows (+ coupling sum) of this group are in shared memory -- in particular before any peer can be
+      // released to overwrite those rows in HBM
+      rn_mbar_wait(&aux_full[i & 3], (uint32_t)((i >> 2) & 1));
       rn_mbar_wait(&pw_full[sl], ph);
       double2 acc = *reinterpret_cast<const double2*>(Pw + (sl * NCW) * 64 + 2 * lane);
 #pragma unroll
@@ -307,6 +431,17 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       for (uint32_t rr = 0; rr < csize; ++rr)
         rn_st_async2(rn_mapa(my_pex + sl * (RN_FU_MAXC * 64 * 8), rr), acc.x, acc.y,
                      rn_mapa(rn_smem_u32(&pex_full[sl]), rr));
+      // operands that do not depend on the exchange, loaded while it is in flight
+      const double* fo = Fo + (i & 3) * 64 + g * 8;
+      const double fa0 = fo[t], fa1 = fo[t + 4];
+      const double2 fmine = *reinterpret_cast<const double2*>(fo + c0);
+      double2 pcn = make_double2(0.0, 0.0);
+      if (coupled) pcn = *reinterpret_cast<const double2*>(Pcn + (i & 3) * 64 + g * 8 + c0);
+      double N0 = 0.0, N1 = 0.0, D0 = 0.0, D1 = 0.0;
+      rn_dmma(D0, D1, fa0, bm0);
+      rn_dmma(D0, D1, fa1, bm1);
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&aux_empty[i & 3]);
       rn_mbar_wait_cluster(&pex_full[sl], ph);
       double2 tot = *reinterpret_cast<const double2*>(Pex + (sl * RN_FU_MAXC) * 64 + 2 * lane);
       for (uint32_t rr = 1; rr < csize; ++rr) {
@@ -316,53 +451,37 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       }
       *reinterpret_cast<double2*>(Ps + 2 * lane) = tot;
       __syncwarp();
-      const double* fo = Fo + (i & 3) * 64 + g * 8;
-      double N0 = 0.0, N1 = 0.0, D0 = 0.0, D1 = 0.0;
       rn_dmma(N0, N1, Ps[g * 8 + t], bs0);
-      rn_dmma(D0, D1, fo[t], bm0);
       rn_dmma(N0, N1, Ps[g * 8 + t + 4], bs1);
-      rn_dmma(D0, D1, fo[t + 4], bm1);
-      const double2 fmine = *reinterpret_cast<const double2*>(fo + c0);
       const double f0 = fmine.x, f1 = fmine.y;
-      const int64_t r = (g0 + i) * 8 + g;
+      const int64_t grp = g0 + i;
+      const int64_t r = grp * 8 + g;
       double o0 = 0.0, o1 = 0.0;
       if (r < vw.n) {
-        if (phisum == 0.0) {  // update_steps.r:152-155
+        if (!coupled) {  // update_steps.r:152-155
           double q0 = rn_fast_div(N0, D0 + lam0), q1 = rn_fast_div(N1, D1 + lam1);
           if (isnan(q0)) q0 = 1.0;
           if (isnan(q1)) q1 = 1.0;
           o0 = fabs(f0 * q0);
           o1 = fabs(f1 * q1);
         } else {  // update_steps.r:156-163 with star_prod_relevant (utils.r:63-78)
-          double pc0 = 0.0, pc1 = 0.0;
-          for (int w = 0; w < V; ++w) {
-            const double phw = ft.phi[w + v * V];
-            if (phw == 0.0) continue;
-            const int mode = ft.rowmode[w + v * V];
-            if (mode == RN_MODE_NA) continue;
-            const RnView* ow = ft.views + w;
-            const double nw = (double)ow->n_glob;
-            int64_t src = -1;
-            if (mode == RN_MODE_MAP) src = ft.rowmap[w + v * V][r];
-            const double m0 = (src >= 0) ? ow->F[rn_fidx(src, c0, ow->kp)] : f0;
-            const double m1 = (src >= 0) ? ow->F[rn_fidx(src, c1, ow->kp)] : f1;
-            pc0 += (phw * m0) * nw;
-            pc1 += (phw * m1) * nw;
-          }
-          o0 = fabs(f0 * rn_fast_div(N0 + pc0 / nv, (D0 + phisum * f0) + lam0));
-          o1 = fabs(f1 * rn_fast_div(N1 + pc1 / nv, (D1 + phisum * f1) + lam1));
+          o0 = fabs(f0 * rn_fast_div(N0 + pcn.x, (D0 + phisum * f0) + lam0));
+          o1 = fabs(f1 * rn_fast_div(N1 + pcn.y, (D1 + phisum * f1) + lam1));
         }
         if (c0 >= K) o0 = 0.0;
         if (c1 >= K) o1 = 0.0;
-        if (rank == 0) {
-          if (c0 < K) vw.F[rn_fidx(r, c0, kp)] = o0;
-          if (c1 < K) vw.F[rn_fidx(r, c1, kp)] = o1;
-        }
       }
       *reinterpret_cast<double2*>(Fp + sl * 64 + g * 8 + c0) = make_double2(o0, o1);
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&fp_full[sl]);
-      if (rank == 0) {  // F'F and colSums(F) of this cluster's rows, off the critical path
+      if (rank == 0) {  // off the critical path: F_new to HBM, F'F and colSums(F) of this cluster's rows
+        if (r < vw.n) {
+          // rn_fidx(r, c, kp) with r = 8 grp + g: 8 row groups per 64-row panel of F
+          double* fpan = vw.F + (grp >> 3) * kp * RN_ROW_TILE + (g & 1);
+          const int piece = (((int)(grp & 7)) << 2) | (g >> 1);
+          if (c0 < K) fpan[c0 * RN_ROW_TILE + 2 * (piece ^ sig0)] = o0;
+          if (c1 < K) fpan[c1 * RN_ROW_TILE + 2 * (piece ^ sig1)] = o1;
+        }
         const double x1 = Fp[sl * 64 + t * 8 + g], x2 = Fp[sl * 64 + (t + 4) * 8 + g];
         rn_dmma(ff0, ff1, x1, x1);
         rn_dmma(cs0, cs1, 1.0, x1);

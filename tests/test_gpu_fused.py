@@ -14,10 +14,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def any_width(monkeypatch):
-    """Lets narrow views (p << 1008) take the fused path too (the kernel pads the columns to the cluster width), and
-    phi-coupled views as well (by default they stay on the two-pass kernels: the gather sits on the critical warp)."""
+    """Lets narrow views (p << 1008) take the fused path too: the kernel pads the columns to the cluster width."""
     monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
-    monkeypatch.setenv("RESNMTF_FUSED_PHI", "1")
 
 
 def assert_fused(fit):
@@ -89,10 +87,9 @@ def test_fused_two_views_coupled(ctx, cfg, any_width):
     compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
 
 
-def test_fused_mixed_with_two_pass_views(ctx, monkeypatch):
+def test_fused_mixed_with_two_pass_views(ctx):
     """A fit whose views do not all qualify: view 1 (p = 1000) runs fused, view 2 (p = 300) the TMA kernels;
     the phi coupling between them crosses the two kernel families."""
-    monkeypatch.setenv("RESNMTF_FUSED_PHI", "1")
     rng = np.random.default_rng(21)
     shapes = [(400, 1000), (400, 300)]
     k = 4
@@ -161,3 +158,37 @@ def test_fused_odd_cluster_sizes(ctx, p, k, monkeypatch):
     finally:
         fit.close()
     compare_trace(prob, ctx, n_iters=3, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)
+
+
+def test_fused_many_phi_partners(ctx, any_width):
+    """Five views, every pair phi-coupled with partial, permuted row overlaps (4 partners per view: both lanes-per-row
+    passes of the map prefetch), psi and xi on top; many row groups so the prefetch pipeline runs in steady state."""
+    rng = np.random.default_rng(31)
+    V, n, k = 5, 700, 3
+    ps = [90, 120, 70, 100, 80]
+    data = [synth.prep(synth.planted_view(n, p, 3, rng, 0.3, 0.3)[0]) for p in ps]
+    inits = [synth.random_factors(n, p, k, rng) for p in ps]
+    rn = []
+    for v in range(V):  # view v names 70 % of a common pool, in its own order
+        pool = rng.permutation(900)[:n]
+        rn.append([f"r{j}" for j in pool])
+    cn = [[f"c{v}_{j}" for j in range(p)] for v, p in enumerate(ps)]
+    cn[1] = [f"c0_{j}" for j in range(90)] + [f"x{j}" for j in range(30)]  # views 0 and 1 share 90 columns
+    phi = np.zeros((V, V))
+    phi[np.triu_indices(V, 1)] = rng.uniform(5.0, 300.0, size=V * (V - 1) // 2)
+    psi = np.zeros((V, V))
+    psi[0, 1] = 40.0
+    xi = np.zeros((V, V))
+    xi[np.triu_indices(V, 1)] = 3.0
+    from oracle import resnmtf_oracle as O
+
+    prob = Problem(data, [k] * V, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
+                   phi=O.init_rest_mats(phi, V), psi=O.init_rest_mats(psi, V), xi=O.init_rest_mats(xi, V),
+                   row_names=rn, col_names=cn)
+    fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=L.IMPL_FUSED)
+    try:
+        fit.run(1)
+        assert_fused(fit)
+    finally:
+        fit.close()
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=L.IMPL_FUSED)

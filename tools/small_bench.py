@@ -52,7 +52,7 @@ def sym(V, val, pairs=None):
     return m + m.T
 
 
-if __name__ == "__main__":
+def main():
     ctx = Context()
     run(ctx, "C1 toy 100x50 + 100x30, phi", [(100, 50), (100, 30)], 3, phi=sym(2, 200.0), iters=2000)
     run(ctx, "test data 2 x 180x180", [(180, 180)] * 2, 3, iters=2000)
@@ -62,3 +62,7 @@ if __name__ == "__main__":
     run(ctx, "C4 8 x 100000x2000 k=8 phi,psi,xi", [(100000, 2000)] * 8, 8, phi=sym(8, 200.0), psi=sym(8, 200.0),
         xi=sym(8, 50.0), iters=10)
     ctx.close()
+
+
+if __name__ == "__main__":
+    main()
