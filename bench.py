@@ -281,6 +281,13 @@ def run_gpu(args):
                  "FP64 tensor pipe (DMMA) of 3 of 4 sub-partitions on the 132 SMs a 4-CTA cluster grid can occupy"
                  if dom == "rn_fused_step" else "two-pass kernels: X is read once per kernel, twice per iteration"),
     }
+    if dom == "rn_fused_step":
+        # second limiter, for the record: FP64 MMA work (k padded to 8, two phases) against the DMMA rate measured by
+        # tools/microbench.cu on this GPU model (18.5 T FMA/s chip-wide; DMMA and scalar FP64 share one pipe)
+        fma = 2.0 * N_ROWS * N_COLS * 8 * prof_iters * len(K_SWEEP)
+        roofline["fp64_mma"] = {"achieved_tfma_per_s": fma / (ran[dom][1] * 1e-3) * 1e-12, "chip_peak_tfma_per_s": 18.5,
+                                "usable_fraction_of_chip": 132.0 * 3 / (148 * 4),
+                                "peak_source": "tools/microbench.cu (DESIGN.md section 4), not MEASURED_PEAKS.json"}
 
     # ---- e2e: reference-facing fit call per k with HOST buffers ----------------------------------------
     e2e = None

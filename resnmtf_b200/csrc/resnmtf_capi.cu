@@ -841,7 +841,7 @@ extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f,
   RN_CUDA(cudaMemcpyAsync(vh.d.S, s, (size_t)K * K * sizeof(double), cudaMemcpyHostToDevice, st));
   if (lambda) RN_CUDA(cudaMemcpyAsync(vh.d.lam, lambda, K * sizeof(double), cudaMemcpyHostToDevice, st));
   if (mu) RN_CUDA(cudaMemcpyAsync(vh.d.mu, mu, K * sizeof(double), cudaMemcpyHostToDevice, st));
-  rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);
+  rn_factor_sums<<<2 * vh.d.k + vh.d.k * vh.d.k, 1024, 0, st>>>(vh.d);
   {
     int rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)K);  // F rows are sharded, G is replicated
     if (rc2) return rc2;
@@ -1484,12 +1484,12 @@ extern "C" int resnmtf_fit_normalise(resnmtf_fit* fit) {
   for (int v = 0; v < fit->V; ++v) {
     const ViewHost& vh = fit->views[v];
     RN_CHECK(vh.has_factors, RESNMTF_E_STATE, "resnmtf_fit_normalise: factors were never set");
-    rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);
+    rn_factor_sums<<<2 * vh.d.k + vh.d.k * vh.d.k, 1024, 0, st>>>(vh.d);
     int rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)vh.d.k);
     if (rc2) return rc2;
     const int64_t m = std::max(vh.d.n, vh.d.p);
     rn_normalise<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(vh.d);
-    rn_factor_sums<<<1, 1024, 0, st>>>(vh.d);  // keep G'G / colsums consistent with the scaled factors
+    rn_factor_sums<<<2 * vh.d.k + vh.d.k * vh.d.k, 1024, 0, st>>>(vh.d);  // keep G'G / colsums consistent with the scaled factors
     if ((rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)vh.d.k))) return rc2;
   }
   RN_CUDA(cudaGetLastError());

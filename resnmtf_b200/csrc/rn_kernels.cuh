@@ -1672,48 +1672,34 @@ __global__ void __launch_bounds__(256) rn_xnorm2(const RnView vw, double* part, 
   }
 }
 
-// Column sums of F and G plus G'G of the current factors (single CTA, 1024 threads): used after
-// set_factors (lambda/mu defaults, the G'G the first F step needs) and by the final normalisation.
+// Column sums of F and G plus G'G of the current factors: used after set_factors (lambda/mu defaults, the G'G the
+// first F step needs) and by the final normalisation.  grid (2k + k*k), 1024 threads: one CTA per output value,
+// fixed-order tree inside the CTA (bit-reproducible).
 __global__ void __launch_bounds__(1024) rn_factor_sums(const RnView vw) {
   const int tid = threadIdx.x;
   const int K = vw.k, KP = vw.kp;
+  const int o = blockIdx.x;
   __shared__ double bs[1024];
-  for (int c = 0; c < K; ++c) {
-    double s = 0.0;
-    for (int64_t r = tid; r < vw.n; r += 1024) s += vw.F[rn_fidx(r, c, KP)];
-    bs[tid] = s;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-      if (tid < o) bs[tid] += bs[tid + o];
-      __syncthreads();
-    }
-    if (tid == 0) vw.csF[c] = bs[0];
-    __syncthreads();
-  }
-  for (int c = 0; c < K; ++c) {
-    double s = 0.0;
+  double s = 0.0;
+  if (o < K) {
+    for (int64_t r = tid; r < vw.n; r += 1024) s += vw.F[rn_fidx(r, o, KP)];
+  } else if (o < 2 * K) {
+    const int c = o - K;
     for (int64_t j = tid; j < vw.p; j += 1024) s += vw.G[j * KP + c];
-    bs[tid] = s;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-      if (tid < o) bs[tid] += bs[tid + o];
-      __syncthreads();
-    }
-    if (tid == 0) vw.csG[c] = bs[0];
+  } else {
+    const int a = (o - 2 * K) % K, b = (o - 2 * K) / K;
+    for (int64_t j = tid; j < vw.p; j += 1024) s = fma(vw.G[j * KP + a], vw.G[j * KP + b], s);
+  }
+  bs[tid] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (tid < w) bs[tid] += bs[tid + w];
     __syncthreads();
   }
-  for (int o2 = 0; o2 < K * K; ++o2) {
-    const int a = o2 % K, b = o2 / K;
-    double s = 0.0;
-    for (int64_t j = tid; j < vw.p; j += 1024) s = fma(vw.G[j * KP + a], vw.G[j * KP + b], s);
-    bs[tid] = s;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-      if (tid < o) bs[tid] += bs[tid + o];
-      __syncthreads();
-    }
-    if (tid == 0) vw.GtG[o2] = bs[0];
-    __syncthreads();
+  if (tid == 0) {
+    if (o < K) vw.csF[o] = bs[0];
+    else if (o < 2 * K) vw.csG[o - K] = bs[0];
+    else vw.GtG[o - 2 * K] = bs[0];
   }
 }
 
