@@ -157,23 +157,6 @@ __device__ __forceinline__ void rn_fu_stamp(const RnView& vw, int which) {
 }
 __device__ __forceinline__ void rn_fu_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RN_FU_NCT) : "memory"); }
 
-// num / den without the ~30-instruction IEEE division sequence: hardware reciprocal seed, two Newton steps and one
-// residual correction (result within 1 ulp; the parity bar is 1e-9).  Operands outside the safe range (zero, huge,
-// tiny, Inf, NaN) take the exact division so that Inf / NaN behave as in R.
-__device__ __forceinline__ double rn_fast_div(double num, double den) {
-  const double ad = fabs(den), an = fabs(num);
-  if (!(ad > 1.0e-280 && ad < 1.0e280 && an < 1.0e280)) return num / den;
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-  double e = fma(-den, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-den, r, 1.0);
-  r = fma(r, e, r);
-  double q = num * r;
-  const double rem = fma(-den, q, num);
-  return fma(rem, r, q);
-}
-
 template <int K>
 __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView vw, const RnFit ft, const int v,
                                                                   const int fuse_finish) {
@@ -458,18 +441,21 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       const int64_t r = grp * 8 + g;
       double o0 = 0.0, o1 = 0.0;
       if (r < vw.n) {
+        // padding columns (c >= K) would divide 0 by 0 and take the slow exact path on the critical warp: the
+        // denominators of those lanes are replaced by 1, their outputs are zero anyway
+        const bool v0 = c0 < K, v1 = c1 < K;
         if (!coupled) {  // update_steps.r:152-155
-          double q0 = rn_fast_div(N0, D0 + lam0), q1 = rn_fast_div(N1, D1 + lam1);
+          double q0 = rn_fast_div(N0, v0 ? D0 + lam0 : 1.0), q1 = rn_fast_div(N1, v1 ? D1 + lam1 : 1.0);
           if (isnan(q0)) q0 = 1.0;
           if (isnan(q1)) q1 = 1.0;
           o0 = fabs(f0 * q0);
           o1 = fabs(f1 * q1);
         } else {  // update_steps.r:156-163 with star_prod_relevant (utils.r:63-78)
-          o0 = fabs(f0 * rn_fast_div(N0 + pcn.x, (D0 + phisum * f0) + lam0));
-          o1 = fabs(f1 * rn_fast_div(N1 + pcn.y, (D1 + phisum * f1) + lam1));
+          o0 = fabs(f0 * rn_fast_div(N0 + pcn.x, v0 ? (D0 + phisum * f0) + lam0 : 1.0));
+          o1 = fabs(f1 * rn_fast_div(N1 + pcn.y, v1 ? (D1 + phisum * f1) + lam1 : 1.0));
         }
-        if (c0 >= K) o0 = 0.0;
-        if (c1 >= K) o1 = 0.0;
+        if (!v0) o0 = 0.0;
+        if (!v1) o1 = 0.0;
       }
       *reinterpret_cast<double2*>(Fp + sl * 64 + g * 8 + c0) = make_double2(o0, o1);
       __syncwarp();
@@ -519,11 +505,15 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     const uint32_t off2a = (uint32_t)(g * 128 + ((ra ^ (2 * (g & 3))) * 16));
     const uint32_t off2b = (uint32_t)(g * 128 + ((rb ^ (2 * (g & 3))) * 16));
 
+    // One loop iteration = F phase of group i+1, then G phase of group i.  The publication of the F-phase partial
+    // (two DADDs behind the MMA chains, a shared-memory store, an mbarrier arrive) is issued after the first MMAs of
+    // the G phase so that the DMMA pipe does not drain at the phase boundary.
+    double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;
     auto f_phase = [&](int i) {
       const int gs = i % 3;
       rn_mbar_wait(&full[gs * NCW + ci], (uint32_t)((i / 3) & 1));
       const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024 + off1;
-      double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;
+      pe0 = pe1 = po0 = po1 = 0.0;
 #pragma unroll
       for (int s = 0; s < 2 * NB; ++s) {
         if (s < 2 * nb) {  // uniform over the warp
@@ -532,12 +522,16 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
           rn_dmma(po0, po1, x.y, gfr[s][1]);
         }
       }
+    };
+    auto publish = [&](int i) {
       *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&pw_full[i & 1]);
     };
-    auto g_phase = [&](int i) {
+    auto g_phase = [&](int i, bool publish_next) {
       const int gs = i % 3;
+      // F_new of group i is always there before the epilogue warp could use the partial of group i+1, so waiting for
+      // it ahead of the publication below delays nothing
       rn_mbar_wait(&fp_full[i & 1], (uint32_t)((i >> 1) & 1));
       const double fa = Fp[(i & 1) * 64 + ra * 8 + g];
       const double fb = Fp[(i & 1) * 64 + rb * 8 + g];
@@ -552,14 +546,19 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
           rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
           rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
         }
+        if (b == 1 && publish_next) publish(i + 1);
       }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&empty[gs * NCW + ci]);
     };
-    if (NGL > 0) f_phase(0);
+    if (NGL > 0) {
+      f_phase(0);
+      publish(0);
+    }
     for (int i = 0; i < NGL; ++i) {
-      if (i + 1 < NGL) f_phase(i + 1);
-      g_phase(i);
+      const bool more = i + 1 < NGL;
+      if (more) f_phase(i + 1);
+      g_phase(i, more);
     }
   }
   if (tid == 0) rn_fu_stamp(vw, 2);
@@ -659,11 +658,20 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     if (!*s_flag) continue;
     __threadfence();
     // ---- last column group done: finish the view -----------------------------------------------------------
-    for (int o = ctid; o < NOUT; o += NCT) fin[o] = rn_sum_wide(vw.GGpart + o, NOUT, (int)NG);
-    if (ctid == 0) {
-      vw.misc_ticket[0] = 0;
-      vw.misc_ticket[2] = 0;
-      vw.misc_ticket[3] = 0;
+    {  // G'G | A | colSums(G): the two halves of the column-group partials are summed side by side (one L2 round trip)
+      static_assert(2 * NOUT <= NCT, "two threads per output");
+      const int half = (int)((NG + 1) / 2);
+      double part = 0.0;
+      if (ctid < NOUT) part = rn_sum_wide(vw.GGpart + ctid, NOUT, half);
+      else if (ctid < 2 * NOUT) part = rn_sum_wide(vw.GGpart + (int64_t)half * NOUT + (ctid - NOUT), NOUT, (int)NG - half);
+      if (ctid >= NOUT && ctid < 2 * NOUT) red[ctid - NOUT] = part;  // scratch: red is the last array carved from the idle ring
+      if (ctid == 0) {
+        vw.misc_ticket[0] = 0;
+        vw.misc_ticket[2] = 0;
+        vw.misc_ticket[3] = 0;
+      }
+      rn_fu_consumer_sync();
+      if (ctid < NOUT) fin[ctid] = part + red[ctid];
     }
     rn_fu_consumer_sync();
     if (ctid == 0) rn_fu_stamp(vw, 8);

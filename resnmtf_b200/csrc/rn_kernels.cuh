@@ -91,6 +91,23 @@ __device__ __forceinline__ int rn_ld_acquire(const int* p) {
   return v;
 }
 
+// num / den without the ~30-instruction IEEE division sequence: hardware reciprocal seed, two Newton steps and one
+// residual correction (result within 1 ulp; the parity bar is 1e-9).  Operands outside the safe range (zero, huge,
+// tiny, Inf, NaN) take the exact division so that Inf / NaN behave as in R.
+__device__ __forceinline__ double rn_fast_div(double num, double den) {
+  const double ad = fabs(den), an = fabs(num);
+  if (!(ad > 1.0e-280 && ad < 1.0e280 && an < 1.0e280)) return num / den;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  double e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  double q = num * r;
+  const double rem = fma(-den, q, num);
+  return fma(rem, r, q);
+}
+
 // stream-K partition of U units over C CTAs: CTA c owns [begin(c), begin(c+1)); the first U % C CTAs
 // get one unit more.
 struct RnSplit {
@@ -214,7 +231,7 @@ __device__ __forceinline__ void rn_update_g_row(const RnView& vw, const RnFit& f
   if (ft.psi_total == 0.0) {
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      double ratio = N[c] / (D[c] + muh[c]);
+      double ratio = rn_fast_div(N[c], D[c] + muh[c]);
       if (isnan(ratio)) ratio = 1.0;
       gn[c] = fabs(gj[c] * ratio);
     }
@@ -244,9 +261,9 @@ __device__ __forceinline__ void rn_update_g_row(const RnView& vw, const RnFit& f
     const double pv = (double)vw.p;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      const double num = N[c] + pc[c] / pv;
+      const double num = N[c] + rn_fast_div(pc[c], pv);
       const double den = (D[c] + psisum * gj[c]) + muh[c];
-      gn[c] = fabs(gj[c] * (num / den));
+      gn[c] = fabs(gj[c] * rn_fast_div(num, den));
     }
   }
 #pragma unroll
@@ -284,12 +301,19 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
   const double* An = fin + KK;
   const double* csGn = fin + 2 * KK;
   // this runs in ONE CTA at the very end of the iteration: issue the global loads its serial part needs now
-  double lam_old = 0.0, mu_old = 0.0, xn = 0.0;
+  double lam_old = 0.0, mu_old = 0.0, xn = 0.0, err_before = 0.0;
+  RnCtrl cc;
   if (tid < K) {
     lam_old = vw.lam[tid];
     mu_old = vw.mu[tid];
   }
-  if (tid == 0) xn = vw.scal[0];
+  if (tid == 0) {
+    xn = vw.scal[0];
+    if (fuse_finish) {  // the views before this one finished in earlier launches: their errors are final
+      cc = *ft.ctrl;
+      for (int w = 0; w < v; ++w) err_before += ft.views[w].scal[1];
+    }
+  }
   for (int o = tid; o < KK; o += NT) {
     vw.GtG[o] = GtGn[o];
     vw.A[o] = An[o];
@@ -360,10 +384,27 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     vw.scal[1] = e;
     vw.scal[2] = e;
     vw.flags[0] = (ft.err_mode == 2) ? 1 : 0;  // DIRECT: the residual pass that follows overwrites scal[1]
-    if (ft.err_mode == 0 && e < 1.0e-3) ft.ctrl->want_direct = 1;  // AUTO: cancellation would cost digits
+    const bool want = ft.err_mode == 0 && e < 1.0e-3;  // AUTO: cancellation would cost digits
+    if (want) ft.ctrl->want_direct = 1;
     if (fuse_finish) {  // the other views' errors were written by earlier launches, this view's by this thread
-      if (ft.err_mode == 0 && ft.ctrl->want_direct) ft.ctrl->done = 3;  // pause: host re-does the error
-      else rn_finish_dev(ft);
+      if (ft.err_mode == 0 && (want || cc.want_direct)) {
+        ft.ctrl->done = 3;  // pause: host re-does the error
+      } else {  // rn_finish_dev on the control block read at entry (same summation order over the views)
+        double sum = err_before + e;
+        for (int w = v + 1; w < V; ++w) sum += ft.views[w].scal[1];
+        const double mean = sum / (double)V;
+        RnCtrl* c = ft.ctrl;
+        if (cc.hist_count < ft.hist_cap) ft.hist[cc.hist_count] = mean;
+        c->hist_count = cc.hist_count + 1;
+        c->iters = cc.iters + 1;
+        const double diff = fabs(mean - cc.prev_err);
+        c->last_diff = diff;
+        c->prev_err = mean;
+        if (cc.conv_mode) {
+          if (isnan(mean)) c->done = 2;
+          else if (!(diff > cc.tol)) c->done = 1;
+        }
+      }
     }
   }
 }
