@@ -5,6 +5,7 @@ import warnings
 import numpy as np
 import pytest
 
+from helpers import rel_err
 from oracle import resnmtf_oracle as O
 from resnmtf_b200 import synth
 from resnmtf_b200.api import apply_resnmtf, res_nmtf_inner
@@ -104,3 +105,21 @@ def test_res_nmtf_inner_matches_oracle_end_to_end(ctx, block_data):
         assert np.array_equal(res["row_clusters"][v], rows_o[v])
         assert np.array_equal(res["col_clusters"][v], cols_o[v])
     assert np.isclose(res["Error"], ref["Error"], rtol=1e-9)
+
+
+def test_device_svd_initialisation_matches_lapack():
+    """The GPU route of the SVD initialisation (Gram matrix of the smaller side + eigendecomposition)
+    against the full LAPACK svd the reference calls (R/update_steps.r:92), on a planted and on a shuffled (nearly
+    degenerate) spectrum, both orientations."""
+    from resnmtf_b200 import api
+
+    rng = np.random.default_rng(17)
+    x = synth.prep(synth.planted_view(1300, 700, 4, rng, row_prob=0.2, col_prob=0.2, height=5.0, sigma=1.0)[0])
+    shuffled = rng.permutation(x.ravel()).reshape(x.shape)
+    for m in (x, shuffled, np.ascontiguousarray(x.T)):
+        out = api._svd_topk_device(np.asfortranarray(m), 6, -1)
+        assert out is not None, "torch CUDA path unavailable on the GPU box"
+        u, d, vt = np.linalg.svd(m, full_matrices=False)
+        assert rel_err(out[1], d[:6]) <= 1e-11
+        assert np.max(np.abs(out[0] - np.abs(u[:, :6]))) <= 1e-10
+        assert np.max(np.abs(out[2] - np.abs(vt[:6].T))) <= 1e-10
