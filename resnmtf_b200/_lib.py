@@ -128,9 +128,16 @@ def device_count():
     return int(load().resnmtf_device_count())
 
 
+_device_checked = False
+
+
 def require_device():
-    """Fails loudly when the CUDA path cannot run (no library, no GPU)."""
+    """Fails loudly when the CUDA path cannot run (no library, no GPU).  The positive answer is cached: the driver
+    query behind it costs ~20 ms and every fit / data handle passes through here."""
+    global _device_checked
     lib = load()
-    if lib.resnmtf_device_count() < 1:
-        raise RuntimeError("resnmtf_b200: no CUDA device visible and there is no CPU fallback")
+    if not _device_checked:
+        if lib.resnmtf_device_count() < 1:
+            raise RuntimeError("resnmtf_b200: no CUDA device visible and there is no CPU fallback")
+        _device_checked = True
     return lib

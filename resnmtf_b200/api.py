@@ -24,22 +24,20 @@ from .stability import stability_check
 # --------------------------------------------------------------------------------------------------
 
 
-def _svd_topk_device(x, k, device):
-    """Top-k singular triplets through the Gram matrix of the smaller side, ON THE GPU: X'X (or XX') is one FP64 GEMM,
-    its eigendecomposition one cuSOLVER call, U = X V / d one more GEMM -- library code through torch, this is the
-    boundary input of a fit (SURVEY 8a row a11 / 8f row N3), not the update path.  The reference's full svd(x) (LAPACK,
-    R/update_steps.r:92) is what dominates the wall time of apply_resnmtf once the loop runs on the device (host
-    profile on 4000 x 1500: 33 of 45 s); the Gram route agrees with it to ~1e-14 on planted and on shuffled (nearly
-    degenerate) spectra.  Returns None when torch / CUDA is unavailable."""
+def _torch_cuda():
+    """torch with a CUDA device, or None (torch is plumbing here: device tensors + library GEMM / eigensolver for the
+    boundary inputs of a fit, never the update path)."""
     try:
         import torch
     except Exception:  # pragma: no cover - torch is part of the image
         return None
-    if not torch.cuda.is_available():
-        return None
-    n, p = x.shape
-    dev = torch.device("cuda", int(device) if device is not None and device >= 0 else torch.cuda.current_device())
-    xt = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)  # p x n, row-major (== column-major n x p)
+    return torch if torch.cuda.is_available() else None
+
+
+def _gram_topk_torch(torch, xt, k):
+    """Top-k singular triplets of the n x p matrix whose column-major storage is the row-major p x n tensor ``xt``,
+    through the Gram matrix of the smaller side.  Returns device tensors |U| (n x k), d (k), |V| (p x k)."""
+    p, n = xt.shape
     if p <= n:
         w, v = torch.linalg.eigh(xt @ xt.T)
         w, v = w[-k:].flip(0), v[:, -k:].flip(1)
@@ -50,7 +48,81 @@ def _svd_topk_device(x, k, device):
         w, u = w[-k:].flip(0), u[:, -k:].flip(1)
         d = torch.sqrt(torch.clamp(w, min=0.0))
         v = (xt @ u) / d[None, :]
-    return np.abs(u.cpu().numpy()), d.cpu().numpy(), np.abs(v.cpu().numpy())
+    return u.abs(), d, v.abs()
+
+
+def _svd_topk_device(x, k, device):
+    """Top-k singular triplets through the Gram matrix of the smaller side, ON THE GPU: X'X (or XX') is one FP64 GEMM,
+    its eigendecomposition one cuSOLVER call, U = X V / d one more GEMM -- library code through torch, this is the
+    boundary input of a fit (SURVEY 8a row a11 / 8f row N3), not the update path.  The reference's full svd(x) (LAPACK,
+    R/update_steps.r:92) is what dominates the wall time of apply_resnmtf once the loop runs on the device (host
+    profile on 4000 x 1500: 33 of 45 s); the Gram route agrees with it to ~1e-14 on planted and on shuffled (nearly
+    degenerate) spectra.  Returns None when torch / CUDA is unavailable."""
+    torch = _torch_cuda()
+    if torch is None:
+        return None
+    dev = torch.device("cuda", int(device) if device is not None and device >= 0 else torch.cuda.current_device())
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)  # p x n, row-major (== column-major n x p)
+    u, d, v = _gram_topk_torch(torch, xt, k)
+    return u.cpu().numpy(), d.cpu().numpy(), v.cpu().numpy()
+
+
+def _init_from_svd(f, d, g, k, rng, sigma=0.05):
+    """R/update_steps.r:93-105 on the top-k triplets: S = |diag(d)| + |noise|, columns rescaled like the final
+    normalisation (quirk Q7), lambda / mu = column sums of the normalised factors."""
+    s = np.abs(np.diag(d)) + np.abs(np.sqrt(sigma) * rng.standard_normal((k, k)))
+    csf, csg = f.sum(axis=0), g.sum(axis=0)
+    s = s * (csf * csg)[None, :]
+    f = f / csf[None, :]
+    g = g / csg[None, :]
+    return f, s, g, f.sum(axis=0), g.sum(axis=0)
+
+
+def shuffled_fits_device(data, n_clusts, num_repeats, rng, ctx, max_iters=0):
+    """obtain_shuffled_f (R/obtain_bicl.r:31-42) with every matrix-sized step on the device: per
+    repeat and view the full random permutation of the entries (shuffle_view, :11-22, incl. its rejection of all-zero
+    rows / columns), the re-normalisation apply_resnmtf applies to the shuffled data (check_inputs, R/utils.r:20-27,
+    86-88), the SVD initialisation and the fit itself; only the n x k factors come back.  The shuffle refits run
+    with phi = xi = psi = NULL (R/obtain_bicl.r:35-39), so no shared-index maps are needed.  Randomness: one seed per
+    shuffled view and the k x k initialisation noise are drawn from ``rng`` in the reference's order; the permutation
+    itself comes from a device generator keyed by that seed.  Returns None when torch / CUDA is unavailable."""
+    torch = _torch_cuda()
+    if torch is None:
+        return None
+    dev = torch.device("cuda", int(ctx.device))
+    n_v = len(data)
+    k = int(n_clusts)
+    xs = [torch.from_numpy(np.ascontiguousarray((m.x if hasattr(m, "x") else m).T)).to(dev) for m in data]
+    shapes = [(int(x.shape[1]), int(x.shape[0])) for x in xs]  # (n, p)
+    f_mess = []
+    with torch.cuda.device(dev):
+        for _ in range(int(num_repeats)):
+            messed = []
+            for xd in xs:
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(int(rng.integers(0, 2 ** 62)))
+                while True:  # the storage order of xd is R's column-major vector order
+                    perm = torch.randperm(xd.numel(), generator=gen, device=dev)
+                    m = xd.reshape(-1)[perm].reshape(xd.shape)
+                    if not bool((m.sum(dim=0) == 0).any() or (m.sum(dim=1) == 0).any()):
+                        break
+                del perm
+                messed.append(m / m.sum(dim=1, keepdim=True))  # L1 column normalisation (columns of X = rows of m)
+            fit = DeviceFit(ctx, [s_[0] for s_ in shapes], [s_[1] for s_ in shapes], [k] * n_v)
+            try:
+                for v_, m in enumerate(messed):
+                    u, d, g = _gram_topk_torch(torch, m, k)
+                    f0, s0, g0, lam, mu = _init_from_svd(u.cpu().numpy(), d.cpu().numpy(), g.cpu().numpy(), k, rng)
+                    torch.cuda.current_stream().synchronize()  # the library reads m on its own stream
+                    fit.set_data_device(v_, m.data_ptr(), shapes[v_][0])
+                    fit.set_factors(v_, f0, s0, g0, lam, mu)
+                fit.run(None, 1.0e-6, max_iters)
+                fit.normalise()
+                f_mess.append([fit.get_factors(v_)[0] for v_ in range(n_v)])
+            finally:
+                fit.close()
+            del messed
+    return f_mess
 
 
 def _svd_topk(x, k, device=None):
@@ -89,16 +161,12 @@ def init_mats_inner(x, k_vec, rng, sigma=0.05, device=None):
     for i, xi in enumerate(x):
         k = int(k_vec[i])
         f, d, g = _svd_topk(xi, k, device)
-        s = np.abs(np.diag(d)) + np.abs(np.sqrt(sigma) * rng.standard_normal((k, k)))
-        csf, csg = f.sum(axis=0), g.sum(axis=0)
-        s = s * (csf * csg)[None, :]
-        f = f / csf[None, :]
-        g = g / csg[None, :]
+        f, s, g, lam, mu = _init_from_svd(f, d, g, k, rng, sigma)
         fs.append(f)
         ss.append(s)
         gs.append(g)
-        lams.append(f.sum(axis=0))
-        mus.append(g.sum(axis=0))
+        lams.append(lam)
+        mus.append(mu)
     return fs, ss, gs, lams, mus
 
 

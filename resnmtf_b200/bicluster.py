@@ -159,8 +159,14 @@ def shuffle_view(x_i, rng):
 
 def obtain_shuffled_f(data, n_views, num_repeats, n_clusts, rng, ctx):
     """R/obtain_bicl.r:31-42: refit on shuffled data through apply_resnmtf (k_val, no_clusts, no stability)."""
-    from .api import apply_resnmtf
+    from .api import apply_resnmtf, shuffled_fits_device
 
+    # matrix-sized views: shuffle, re-normalise, initialise and fit without leaving the device (SURVEY 8f N2); small
+    # ones (and hosts without torch CUDA) take the reference's route literally
+    if min(int(np.prod((m.x if hasattr(m, "x") else m).shape)) for m in data) >= 250_000:
+        f_mess = shuffled_fits_device(data, n_clusts, num_repeats, rng, ctx)
+        if f_mess is not None:
+            return f_mess
     f_mess = []
     for _ in range(num_repeats):
         messed = [shuffle_view(m.x if hasattr(m, "x") else m, rng) for m in data]

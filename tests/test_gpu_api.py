@@ -123,3 +123,30 @@ def test_device_svd_initialisation_matches_lapack():
         assert rel_err(out[1], d[:6]) <= 1e-11
         assert np.max(np.abs(out[0] - np.abs(u[:, :6]))) <= 1e-10
         assert np.max(np.abs(out[2] - np.abs(vt[:6].T))) <= 1e-10
+
+
+def test_device_shuffle_refits_path():
+    """Views of >= 250k entries take the device-resident shuffle refits (permutation, re-normalisation, SVD
+    initialisation and fit on the GPU).  The reference's own assertions still hold (three planted
+    blocks of 200 rows / columns survive the spurious-bicluster removal: test-resnmtf.R:63-118 scaled up), the run is
+    reproducible from the seed, and the shuffled factors have the reference's shape and normalisation."""
+    from resnmtf_b200 import api
+    from resnmtf_b200.device import default_context
+
+    views, _ = synth.block_views(2, block=200, n_blocks=3, seed=4)
+    outs = []
+    for _ in range(2):
+        res = apply_resnmtf(views, k_val=3, stability=False, spurious=True, rng=np.random.default_rng(12), max_iters=500)
+        outs.append(res)
+        for v in range(2):
+            assert sorted(res["row_clusters"][v].sum(axis=0).tolist()) == [200.0, 200.0, 200.0]
+            assert sorted(res["col_clusters"][v].sum(axis=0).tolist()) == [200.0, 200.0, 200.0]
+    for v in range(2):
+        assert np.array_equal(outs[0]["output_f"][v], outs[1]["output_f"][v])
+        assert np.array_equal(outs[0]["row_clusters"][v], outs[1]["row_clusters"][v])
+    prepped = [synth.prep(x) for x in views]
+    f_mess = api.shuffled_fits_device(prepped, 3, 2, np.random.default_rng(1), default_context(), max_iters=500)
+    assert f_mess is not None and len(f_mess) == 2 and len(f_mess[0]) == 2
+    for rep in f_mess:
+        for f in rep:
+            assert f.shape == (600, 3) and np.all(f >= 0) and np.allclose(f.sum(axis=0), 1.0, atol=1e-12)
