@@ -150,3 +150,24 @@ def test_device_shuffle_refits_path():
     for rep in f_mess:
         for f in rep:
             assert f.shape == (600, 3) and np.all(f >= 0) and np.allclose(f.sum(axis=0), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("method", ["euclidean", "manhattan", "cosine"])
+def test_device_bisilhouette_matches_host(method):
+    """The GPU bisilhouette against the host restatement of the same definition: overlapping and
+    empty clusters, a cluster with a single row, all three distances."""
+    from resnmtf_b200 import bicluster as B
+
+    rng = np.random.default_rng(23)
+    x = synth.prep(synth.planted_view(400, 150, 3, rng, row_prob=0.3, col_prob=0.3)[0])
+    rc = (rng.random((400, 5)) < 0.25).astype(float)
+    cc = (rng.random((150, 5)) < 0.3).astype(float)
+    rc[:, 3] = 0.0            # empty row cluster
+    rc[:, 4] = 0.0
+    rc[17, 4] = 1.0           # single-row cluster
+    host = B.bisilhouette(x, rc, cc, method=method)
+    dev = B.bisilhouette_device(x, rc, cc, method=method)
+    assert dev is not None
+    assert len(dev["vals"]) == len(host["vals"])
+    assert np.allclose(dev["vals"], host["vals"], rtol=1e-10, atol=1e-12)
+    assert abs(dev["bisil"] - host["bisil"]) <= 1e-12
