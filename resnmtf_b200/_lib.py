@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libresnmtf_b200.so")
+LIB_PATH = os.environ.get("RESNMTF_B200_LIB") or os.path.join(_HERE, "libresnmtf_b200.so")  # env override: A/B builds of the kernels
 
 OK = 0
 E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_NAN, E_UNSUPPORTED, E_COMM = -1, -2, -3, -4, -5, -6, -7

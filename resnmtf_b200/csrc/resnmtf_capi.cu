@@ -1050,9 +1050,10 @@ static int build_plan(resnmtf_fit* fit) {
       n_tpart = (size_t)nc * d.pp8 * KP;
       n_ffpart = (size_t)nc * (K * K + K);
       n_ggpart = (size_t)std::max(d.col_groups, d.gepi_ctas) * (2 * K * K + K);
-      if (rn_env_int("RESNMTF_FU_TIMELINE", 0) && !d.fu_timeline &&
-          (rc = rn_alloc(fit, &d.fu_timeline, (size_t)sms * 12)))
-        return rc;
+      if (rn_env_int("RESNMTF_FU_TIMELINE", 0) && !d.fu_timeline) {
+        if ((rc = rn_alloc(fit, &d.fu_timeline, (size_t)sms * 12))) return rc;
+        if ((rc = rn_alloc(fit, &d.fu_trace, (size_t)((d.n + 7) / 8 + 8) * 32))) return rc;
+      }
       if (!d.X8) {  // second copy of X in the 8-row-group layout (shared by every fit attached to the same data)
         const size_t x8_count = (size_t)d.ldx * d.pp8;
         bool convert = true;
@@ -1445,6 +1446,49 @@ extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, in
         if (x - t0 > hi) hi = x - t0;
       }
       std::fprintf(stderr, "  %-22s %8lld %8lld\n", nm[sidx], lo, hi);
+    }
+    if (d.fu_trace) {  // per-row-group trace of CTA 0 (cluster 0): averages over its groups, ns
+      const int64_t groups = (d.n + 7) / 8;
+      const int ngl = (int)(groups / d.fu_clusters + (groups % d.fu_clusters ? 1 : 0));
+      std::vector<long long> tr((size_t)ngl * 32);
+      RN_CUDA(cudaMemcpy(tr.data(), d.fu_trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      // stamps of group i: F phase 0 (asks for X) / 7 (X there); G phase 1 (F-phase MMAs of group i+1 issued, asks for
+      // F_new of i) / 2 (F_new there) / 3 (done); epilogue 4 (warp partials in) / 5 (cluster partials in) / 6 (F_new out)
+      double wait_x = 0, f_ph = 0, wait_f = 0, g_ph = 0, period = 0, ep_exch = 0, ep_math = 0, early = 0, pub2in = 0;
+      int cnt = 0;
+      for (int i = 4; i + 2 < ngl; ++i) {  // steady state
+        const long long* a = &tr[(size_t)i * 32];
+        const long long* nx = &tr[(size_t)(i + 1) * 32];
+        wait_x += (double)(nx[7] - nx[0]);
+        f_ph += (double)(a[1] - nx[7]);
+        wait_f += (double)(a[2] - a[1]);
+        g_ph += (double)(a[3] - a[2]);
+        period += (double)(nx[3] - a[3]);
+        ep_exch += (double)(a[5] - a[4]);
+        ep_math += (double)(a[6] - a[5]);
+        early += (double)(a[1] - a[6]);    // > 0: F_new of group i was out before consumer warp 0 asked for it
+        pub2in += (double)(nx[4] - a[2]);  // consumer warp 0 publishes group i+1 just after stamp 2 of group i
+        ++cnt;
+      }
+      if (cnt > 0) {  // per consumer warp: G-phase start and publication of the next group, relative to warp 0's stamp 2
+        std::fprintf(stderr, "  per warp (ns after consumer warp 0 got F_new): G phase starts | publishes next group\n   ");
+        for (int w = 0; w < 9; ++w) {
+          double gs_ = 0, pb = 0;
+          for (int i = 4; i + 2 < ngl; ++i) {
+            gs_ += (double)(tr[(size_t)i * 32 + 17 + w] - tr[(size_t)i * 32 + 2]);
+            pb += (double)(tr[(size_t)(i + 1) * 32 + 8 + w] - tr[(size_t)i * 32 + 2]);
+          }
+          std::fprintf(stderr, " w%d %.0f|%.0f", w, gs_ / cnt, pb / cnt);
+        }
+        std::fprintf(stderr, "\n");
+      }
+      if (cnt > 0)
+        std::fprintf(stderr,
+                     "  per row group (CTA 0, %d groups, ns): period %.0f | consumer warp 0: wait X %.0f, F phase %.0f, "
+                     "wait F_new %.0f, G phase %.0f | epilogue: own publish -> all warp partials in %.0f, -> cluster "
+                     "partials in %.0f, -> F_new out %.0f; F_new out %.0f before it is asked for\n",
+                     cnt, period / cnt, wait_x / cnt, f_ph / cnt, wait_f / cnt, g_ph / cnt, pub2in / cnt, ep_exch / cnt,
+                     ep_math / cnt, early / cnt);
     }
   }
   if (conv && fit->h_ctrl.done == 2)

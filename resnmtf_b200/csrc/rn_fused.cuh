@@ -52,6 +52,9 @@
 #define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
+#ifndef RN_FU_F_CHAINS
+#define RN_FU_F_CHAINS 2  // independent accumulator chains of the F phase (2 or 4; A/B measured)
+#endif
 #define RN_FU_MAXPART 7                                   // most phi partners of a view on the fused path
 // Pw | Pex | Fp | Ps | Fo | Msm | Ssm | Wsm | lamh | muh | partner table | SrcIdx | Fg | Pcn
 #define RN_FU_AUX_DOUBLES                                                                                      \
@@ -153,6 +156,15 @@ __device__ __forceinline__ void rn_fu_stamp(const RnView& vw, int which) {
     long long tns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
     vw.fu_timeline[(int64_t)blockIdx.x * 12 + which] = tns;
+  }
+}
+// developer trace of CTA 0: stamp `which` of local row group i (consumer warp 0: 0 F phase starts, 1 F phase MMAs
+// issued, 2 F_new awaited, 3 G phase done; epilogue warp: 4 all warp partials in, 5 cluster partials in, 6 F_new out)
+__device__ __forceinline__ void rn_fu_trace(const RnView& vw, int i, int which) {
+  if (vw.fu_trace && blockIdx.x == 0) {
+    long long tns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+    vw.fu_trace[i * 32 + which] = tns;
   }
 }
 __device__ __forceinline__ void rn_fu_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RN_FU_NCT) : "memory"); }
@@ -404,6 +416,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       // released to overwrite those rows in HBM
       rn_mbar_wait(&aux_full[i & 3], (uint32_t)((i >> 2) & 1));
       rn_mbar_wait(&pw_full[sl], ph);
+      if (lane == 0) rn_fu_trace(vw, i, 4);
       double2 acc = *reinterpret_cast<const double2*>(Pw + (sl * NCW) * 64 + 2 * lane);
 #pragma unroll
       for (int w = 1; w < NCW; ++w) {
@@ -426,6 +439,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&aux_empty[i & 3]);
       rn_mbar_wait_cluster(&pex_full[sl], ph);
+      if (lane == 0) rn_fu_trace(vw, i, 5);
       double2 tot = *reinterpret_cast<const double2*>(Pex + (sl * RN_FU_MAXC) * 64 + 2 * lane);
       for (uint32_t rr = 1; rr < csize; ++rr) {
         const double2 x = *reinterpret_cast<const double2*>(Pex + (sl * RN_FU_MAXC + rr) * 64 + 2 * lane);
@@ -460,6 +474,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       *reinterpret_cast<double2*>(Fp + sl * 64 + g * 8 + c0) = make_double2(o0, o1);
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&fp_full[sl]);
+      if (lane == 0) rn_fu_trace(vw, i, 6);
       if (rank == 0) {  // off the critical path: F_new to HBM, F'F and colSums(F) of this cluster's rows
         if (r < vw.n) {
           // rn_fidx(r, c, kp) with r = 8 grp + g: 8 row groups per 64-row panel of F
@@ -505,34 +520,47 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     const uint32_t off2a = (uint32_t)(g * 128 + ((ra ^ (2 * (g & 3))) * 16));
     const uint32_t off2b = (uint32_t)(g * 128 + ((rb ^ (2 * (g & 3))) * 16));
 
-    // One loop iteration = F phase of group i+1, then G phase of group i.  The publication of the F-phase partial
-    // (two DADDs behind the MMA chains, a shared-memory store, an mbarrier arrive) is issued after the first MMAs of
-    // the G phase so that the DMMA pipe does not drain at the phase boundary.
-    double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;
+    // One loop iteration = F phase of group i+1, its publication, then G phase of group i.  The partial is published
+    // the moment the F phase ends: F_new of group i+1 is needed one G phase + one F phase later and the chain behind
+    // the publication (9 warps in, exchange, F update) takes most of that (trace: RESNMTF_FU_TIMELINE=1) -- publishing
+    // after the first G-phase MMAs instead (tried: no pipe drain at the phase boundary) cost 350 ns of that slack.
+    // four independent accumulator chains (even / odd column of a pair x even / odd step): with two, a warp that has
+    // the DMMA pipe to itself (its two neighbours at a barrier) is limited by the dependent-MMA latency
+    double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0, qe0 = 0.0, qe1 = 0.0, qo0 = 0.0, qo1 = 0.0;
     auto f_phase = [&](int i) {
       const int gs = i % 3;
+      if (tid == 0) rn_fu_trace(vw, i, 0);
       rn_mbar_wait(&full[gs * NCW + ci], (uint32_t)((i / 3) & 1));
+      if (tid == 0) rn_fu_trace(vw, i, 7);
       const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024 + off1;
-      pe0 = pe1 = po0 = po1 = 0.0;
+      pe0 = pe1 = po0 = po1 = qe0 = qe1 = qo0 = qo1 = 0.0;
 #pragma unroll
       for (int s = 0; s < 2 * NB; ++s) {
         if (s < 2 * nb) {  // uniform over the warp
           const double2 x = *reinterpret_cast<const double2*>(xs + s * 512);
-          rn_dmma(pe0, pe1, x.x, gfr[s][0]);
-          rn_dmma(po0, po1, x.y, gfr[s][1]);
+          if ((s & 1) && RN_FU_F_CHAINS == 4) {
+            rn_dmma(qe0, qe1, x.x, gfr[s][0]);
+            rn_dmma(qo0, qo1, x.y, gfr[s][1]);
+          } else {
+            rn_dmma(pe0, pe1, x.x, gfr[s][0]);
+            rn_dmma(po0, po1, x.y, gfr[s][1]);
+          }
         }
       }
     };
     auto publish = [&](int i) {
-      *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
+      *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) =
+          make_double2((pe0 + po0) + (qe0 + qo0), (pe1 + po1) + (qe1 + qo1));
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&pw_full[i & 1]);
+      if (lane == 0) rn_fu_trace(vw, i, 8 + ci);  // per-warp publication time
     };
-    auto g_phase = [&](int i, bool publish_next) {
+    auto g_phase = [&](int i) {
       const int gs = i % 3;
-      // F_new of group i is always there before the epilogue warp could use the partial of group i+1, so waiting for
-      // it ahead of the publication below delays nothing
+      if (tid == 0) rn_fu_trace(vw, i, 1);
       rn_mbar_wait(&fp_full[i & 1], (uint32_t)((i >> 1) & 1));
+      if (tid == 0) rn_fu_trace(vw, i, 2);
+      if (lane == 0) rn_fu_trace(vw, i, 17 + ci);  // per-warp start of the G phase
       const double fa = Fp[(i & 1) * 64 + ra * 8 + g];
       const double fb = Fp[(i & 1) * 64 + rb * 8 + g];
       const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024;
@@ -546,19 +574,21 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
           rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
           rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
         }
-        if (b == 1 && publish_next) publish(i + 1);
       }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&empty[gs * NCW + ci]);
+      if (tid == 0) rn_fu_trace(vw, i, 3);
     };
     if (NGL > 0) {
       f_phase(0);
       publish(0);
     }
     for (int i = 0; i < NGL; ++i) {
-      const bool more = i + 1 < NGL;
-      if (more) f_phase(i + 1);
-      g_phase(i, more);
+      if (i + 1 < NGL) {
+        f_phase(i + 1);
+        publish(i + 1);
+      }
+      g_phase(i);
     }
   }
   if (tid == 0) rn_fu_stamp(vw, 2);

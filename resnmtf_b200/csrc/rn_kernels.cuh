@@ -91,7 +91,7 @@ __device__ __forceinline__ int rn_ld_acquire(const int* p) {
   return v;
 }
 
-// num / den without the ~30-instruction IEEE division sequence: hardware reciprocal seed, two Newton steps and one
+// num / den without the ~30-instruction IEEE division sequence: hardware reciprocal seed, one Newton step and one
 // residual correction (result within 1 ulp; the parity bar is 1e-9).  Operands outside the safe range (zero, huge,
 // tiny, Inf, NaN) take the exact division so that Inf / NaN behave as in R.
 __device__ __forceinline__ double rn_fast_div(double num, double den) {
@@ -99,10 +99,8 @@ __device__ __forceinline__ double rn_fast_div(double num, double den) {
   if (!(ad > 1.0e-280 && ad < 1.0e280 && an < 1.0e280)) return num / den;
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-  double e = fma(-den, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-den, r, 1.0);
-  r = fma(r, e, r);
+  const double e = fma(-den, r, 1.0);  // seed error <= 2^-20: one Newton step leaves 2^-40, the correction below
+  r = fma(r, e, r);                    // squares that again
   double q = num * r;
   const double rem = fma(-den, q, num);
   return fma(rem, r, q);
