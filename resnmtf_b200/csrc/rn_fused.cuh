@@ -40,18 +40,34 @@
 #pragma once
 #include "rn_kernels.cuh"
 
+#ifndef RN_FU_NCW
+#define RN_FU_NCW 9                                       // consumer warps: 9 (3 per sub-partition 0..2) or 12 (4 per)
+#endif
+#if RN_FU_NCW == 9
 #define RN_FU_THREADS 384                                 // 12 warps: 9 consumers, producer (3), epilogue (7), auxiliary (11)
-#define RN_FU_NCW 9                                       // consumer warps
-#define RN_FU_NCT (32 * RN_FU_NCW)                        // consumer threads (named barrier 1)
 #define RN_FU_NB 7                                        // 16-column blocks per consumer warp and row group
+#define RN_FU_WARP_NB(c) 7
+#define RN_FU_WARP_BOFF(c) (7 * (c))
+#else
+#define RN_FU_THREADS 480                                 // 15 warps: 12 consumers (warps 12..14 too) + the three above
+#define RN_FU_NB 6                                        // most blocks of a consumer: 5,5,5,6 on each sub-partition
+#define RN_FU_WARP_NB(c) ((c) >= 9 ? 6 : 5)
+#define RN_FU_WARP_BOFF(c) (5 * (c) + ((c) > 9 ? (c) - 9 : 0))
+#endif
+#define RN_FU_NCT (32 * RN_FU_NCW)                        // consumer threads (named barrier 1)
 #define RN_FU_CBLOCKS 63                                  // 16-column blocks per CTA
 #define RN_FU_CCOLS (16 * RN_FU_CBLOCKS)                  // data columns per CTA (1008)
 #define RN_FU_GROUP_BYTES (RN_FU_CBLOCKS * 1024)          // a CTA's share of one row group (63 KB)
 #define RN_FU_NSLOT (3 * RN_FU_NCW)                       // (row group in the ring, consumer warp) slots
 #define RN_FU_RING_BYTES (3 * RN_FU_GROUP_BYTES)          // 189 KB = 3 row groups
+#ifndef RN_FU_MAXC
 #define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
+#endif
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
+#ifndef RN_FU_PUBLISH_AFTER
+#define RN_FU_PUBLISH_AFTER -1  // -1: publish the F-phase partial at the end of the F phase; b >= 0: after block b of the G phase
+#endif
 #ifndef RN_FU_F_CHAINS
 #define RN_FU_F_CHAINS 2  // independent accumulator chains of the F phase (2 or 4; A/B measured)
 #endif
@@ -177,10 +193,10 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const bool is_consumer = (warp & 3) != 3;
-  const int ci = warp - (warp >> 2);  // consumer index 0..8 (warps 0,1,2, 4,5,6, 8,9,10)
-  const int ctid = ci * 32 + lane;    // consumer thread index 0..287
-  constexpr int nb = NB;              // column blocks of this consumer (uniform; the loops below allow nb < NB)
-  const int boff = NB * ci;
+  const int ci = warp - (warp >> 2);  // consumer index (warps 0,1,2, 4,5,6, 8,9,10 [, 12,13,14])
+  const int ctid = ci * 32 + lane;    // consumer thread index
+  const int nb = RN_FU_WARP_NB(ci);   // column blocks of this consumer (the loops below allow nb < NB)
+  const int boff = RN_FU_WARP_BOFF(ci);
   if (ft.ctrl->done) return;          // uniform over the grid
   if (tid == 0) rn_fu_stamp(vw, 0);
 
@@ -277,8 +293,8 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       const uint32_t ph = (uint32_t)((i / 3) & 1);
 #pragma unroll 1
       for (int w = 0; w < NCW; ++w) {
-        const int wnb = NB;
-        const int wboff = NB * w;
+        const int wnb = RN_FU_WARP_NB(w);
+        const int wboff = RN_FU_WARP_BOFF(w);
         const int st = gs * NCW + w;
         rn_mbar_wait(&empty[st], ph ^ 1u);
         if (lane == 0) {
@@ -574,6 +590,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
           rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
           rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
         }
+        if (b == RN_FU_PUBLISH_AFTER && i + 1 < NGL) publish(i + 1);
       }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&empty[gs * NCW + ci]);
@@ -586,7 +603,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     for (int i = 0; i < NGL; ++i) {
       if (i + 1 < NGL) {
         f_phase(i + 1);
-        publish(i + 1);
+        if (RN_FU_PUBLISH_AFTER < 0) publish(i + 1);
       }
       g_phase(i);
     }
