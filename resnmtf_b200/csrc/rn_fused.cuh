@@ -40,41 +40,22 @@
 #pragma once
 #include "rn_kernels.cuh"
 
-#ifndef RN_FU_NCW
-#define RN_FU_NCW 9                                       // consumer warps: 9 (3 per sub-partition 0..2) or 12 (4 per)
-#endif
-#if RN_FU_NCW == 9
+#define RN_FU_NCW 9                                       // consumer warps (3 per sub-partition 0..2)
 #define RN_FU_THREADS 384                                 // 12 warps: 9 consumers, producer (3), epilogue (7), auxiliary (11)
 #define RN_FU_NB 7                                        // 16-column blocks per consumer warp and row group
-#define RN_FU_WARP_NB(c) 7
-#define RN_FU_WARP_BOFF(c) (7 * (c))
-#else
-#define RN_FU_THREADS 480                                 // 15 warps: 12 consumers (warps 12..14 too) + the three above
-#define RN_FU_NB 6                                        // most blocks of a consumer: 5,5,5,6 on each sub-partition
-#define RN_FU_WARP_NB(c) ((c) >= 9 ? 6 : 5)
-#define RN_FU_WARP_BOFF(c) (5 * (c) + ((c) > 9 ? (c) - 9 : 0))
-#endif
 #define RN_FU_NCT (32 * RN_FU_NCW)                        // consumer threads (named barrier 1)
 #define RN_FU_CBLOCKS 63                                  // 16-column blocks per CTA
 #define RN_FU_CCOLS (16 * RN_FU_CBLOCKS)                  // data columns per CTA (1008)
 #define RN_FU_GROUP_BYTES (RN_FU_CBLOCKS * 1024)          // a CTA's share of one row group (63 KB)
 #define RN_FU_NSLOT (3 * RN_FU_NCW)                       // (row group in the ring, consumer warp) slots
 #define RN_FU_RING_BYTES (3 * RN_FU_GROUP_BYTES)          // 189 KB = 3 row groups
-#ifndef RN_FU_MAXC
 #define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
-#endif
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
-#ifndef RN_FU_PUBLISH_AFTER
-#define RN_FU_PUBLISH_AFTER -1  // -1: publish the F-phase partial at the end of the F phase; b >= 0: after block b of the G phase
-#endif
-#ifndef RN_FU_F_CHAINS
-#define RN_FU_F_CHAINS 2  // independent accumulator chains of the F phase (2 or 4; A/B measured)
-#endif
 #define RN_FU_MAXPART 7                                   // most phi partners of a view on the fused path
-// Pw | Pex | Fp | Ps | Fo | Msm | Ssm | Wsm | lamh | muh | partner table | SrcIdx | Fg | Pcn
-#define RN_FU_AUX_DOUBLES                                                                                      \
-  (2 * RN_FU_NCW * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 64 + 8 + 8 + 48 + 8 * 8 * 8 / 2 + \
+// Pw | Pex | Fp | Ps (= Wsm during set-up) | Fo | Msm | Ssm | lamh | muh | partner table | SrcIdx | Fg | Pcn
+#define RN_FU_AUX_DOUBLES                                                                                 \
+  (2 * RN_FU_NCW * 64 + 2 * RN_FU_MAXC * 64 + 2 * 64 + 64 + 4 * 64 + 64 + 64 + 8 + 8 + 48 + 6 * 8 * 8 / 2 + \
    3 * RN_FU_MAXPART * 64 + 4 * 64)
 static inline size_t rn_fused_smem() {
   return (size_t)RN_FU_RING_BYTES + (size_t)RN_FU_AUX_DOUBLES * 8 + (2 * RN_FU_NSLOT + 6 + 8) * 8 + 16;
@@ -193,10 +174,10 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const bool is_consumer = (warp & 3) != 3;
-  const int ci = warp - (warp >> 2);  // consumer index (warps 0,1,2, 4,5,6, 8,9,10 [, 12,13,14])
+  const int ci = warp - (warp >> 2);  // consumer index 0..8 (warps 0,1,2, 4,5,6, 8,9,10)
   const int ctid = ci * 32 + lane;    // consumer thread index
-  const int nb = RN_FU_WARP_NB(ci);   // column blocks of this consumer (the loops below allow nb < NB)
-  const int boff = RN_FU_WARP_BOFF(ci);
+  constexpr int nb = NB;              // column blocks of this consumer (uniform; the loops below allow nb < NB)
+  const int boff = NB * ci;
   if (ft.ctrl->done) return;          // uniform over the grid
   if (tid == 0) rn_fu_stamp(vw, 0);
 
@@ -209,16 +190,16 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   double* Fo = Ps + 64;                                                 // [4][8][8]     old F rows (cp.async)
   double* Msm = Fo + 4 * 64;                                            // [8][8]        M = S W (zero padded)
   double* Ssm = Msm + 64;                                               // [K*K] (64 reserved)
-  double* Wsm = Ssm + 64;
-  double* lamh = Wsm + 64;
+  double* Wsm = Ps;  // only needed to form M during the set-up, before the epilogue warp first writes Ps
+  double* lamh = Ssm + 64;
   double* muh = lamh + 8;
   double* cpl_ph = muh + 8;                                                // phi partner table (epilogue warp)
   double* cpl_nw = cpl_ph + 8;
   const double** cpl_F = reinterpret_cast<const double**>(cpl_nw + 8);
   const int32_t** cpl_map = reinterpret_cast<const int32_t**>(cpl_nw + 16);
   int* cpl_kp = reinterpret_cast<int*>(cpl_nw + 24);                       // [8] kp, then [8] = number of partners
-  int32_t* SrcIdx = reinterpret_cast<int32_t*>(cpl_nw + 40);               // [8 groups][8 partners][8 rows]
-  double* Fg = cpl_nw + 40 + 8 * 8 * 8 / 2;                                // [3 groups][MAXPART][8 rows][8]
+  int32_t* SrcIdx = reinterpret_cast<int32_t*>(cpl_nw + 40);               // [6 groups][8 partners][8 rows]
+  double* Fg = cpl_nw + 40 + 6 * 8 * 8 / 2;                                // [3 groups][MAXPART][8 rows][8]
   double* Pcn = Fg + 3 * RN_FU_MAXPART * 64;                               // [4 groups][8 rows][8] coupling sums / n
   uint64_t* full = reinterpret_cast<uint64_t*>(Pcn + 4 * 64);
   uint64_t* empty = full + NSLOT;
@@ -285,25 +266,28 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   for (int s = 0; s < 2 * NB; ++s) tacc[s][0] = tacc[s][1] = 0.0;
   const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + 16 * boff;
 
+  // bulk copies of local row group i into its ring slots, one per consumer warp, each as soon as that warp has
+  // released the slot (executed by the whole producer warp)
+  auto produce = [&](int i) {
+    const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
+    const int gs = i % 3;
+    const uint32_t ph = (uint32_t)((i / 3) & 1);
+#pragma unroll 1
+    for (int w = 0; w < NCW; ++w) {
+      const int wnb = NB;
+      const int wboff = NB * w;
+      const int st = gs * NCW + w;
+      rn_mbar_wait(&empty[st], ph ^ 1u);
+      if (lane == 0) {
+        rn_mbar_expect_tx(&full[st], (uint32_t)wnb * 1024u);
+        rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + wboff * 1024, src + wboff * 128, (uint32_t)wnb * 1024u, &full[st]);
+      }
+      __syncwarp();
+    }
+  };
   if (warp == 3) {
     // ---- producer warp -------------------------------------------------------------------------------
-    for (int i = 0; i < NGL; ++i) {
-      const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
-      const int gs = i % 3;
-      const uint32_t ph = (uint32_t)((i / 3) & 1);
-#pragma unroll 1
-      for (int w = 0; w < NCW; ++w) {
-        const int wnb = RN_FU_WARP_NB(w);
-        const int wboff = RN_FU_WARP_BOFF(w);
-        const int st = gs * NCW + w;
-        rn_mbar_wait(&empty[st], ph ^ 1u);
-        if (lane == 0) {
-          rn_mbar_expect_tx(&full[st], (uint32_t)wnb * 1024u);
-          rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + wboff * 1024, src + wboff * 128, (uint32_t)wnb * 1024u, &full[st]);
-        }
-        __syncwarp();
-      }
-    }
+    for (int i = 0; i < NGL; ++i) produce(i);
   } else if (warp == 11) {
     // ---- auxiliary warp: lane (g,t) <-> row g, factor columns 2t, 2t+1; runs two row groups ahead of the epilogue --
     const int V = ft.n_views;
@@ -348,7 +332,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         if (r < vw.n)
           for (int pi = t; pi < np; pi += 4) {
             const int32_t* mp = cpl_map[pi];
-            if (mp) rn_cp_async4(SrcIdx + ((i & 7) * 8 + pi) * 8 + g, mp + r);
+            if (mp) rn_cp_async4(SrcIdx + ((i % 6) * 8 + pi) * 8 + g, mp + r);
           }
       }
     };
@@ -358,7 +342,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         if (r < vw.n)
           for (int pi = 0; pi < np; ++pi) {
             if (!cpl_map[pi]) continue;
-            const int src = SrcIdx[((i & 7) * 8 + pi) * 8 + g];
+            const int src = SrcIdx[((i % 6) * 8 + pi) * 8 + g];
             if (src < 0) continue;
             double* dst = Fg + ((i % 3) * RN_FU_MAXPART + pi) * 64 + g * 8;
             rn_cp_async8(dst + c0, cpl_F[pi] + rn_fidx(src, c0, cpl_kp[pi]));
@@ -377,7 +361,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       if (coupled) prefetch_gather(i);
       rn_cp_async_commit();
     }
-    for (int i = 0; i < NGL; ++i) {
+    auto aux_step = [&](int i) {
       // the slots written below held group i-2 (old F rows) and i-4 (coupling sum): the epilogue is done with them
       if (i >= 2) rn_mbar_wait(&aux_empty[(i - 2) & 3], (uint32_t)(((i - 2) >> 2) & 1));
       rn_cp_async_wait1();  // batch i: old F rows + partner rows of this group, map entries of group i+2
@@ -392,7 +376,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         const double2 fmine = *reinterpret_cast<const double2*>(Fo + (i & 3) * 64 + g * 8 + c0);
         double pc0 = 0.0, pc1 = 0.0;
         for (int pi = 0; pi < np; ++pi) {
-          const int src = cpl_map[pi] ? SrcIdx[((i & 7) * 8 + pi) * 8 + g] : -1;
+          const int src = cpl_map[pi] ? SrcIdx[((i % 6) * 8 + pi) * 8 + g] : -1;
           double m0 = fmine.x, m1 = fmine.y;  // row not shared with this partner: the view's own row (utils.r:69-73)
           if (src >= 0) {
             const double2 mm = *reinterpret_cast<const double2*>(Fg + ((i % 3) * RN_FU_MAXPART + pi) * 64 + g * 8 + c0);
@@ -406,7 +390,8 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&aux_full[i & 3]);
-    }
+    };
+    for (int i = 0; i < NGL; ++i) aux_step(i);
   } else if (warp == 7) {
     // ---- epilogue warp: lane (g,t) owns row g, factor columns 2t and 2t+1 of every row group; critical path only --
     const int V = ft.n_views;
@@ -540,33 +525,25 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     // the moment the F phase ends: F_new of group i+1 is needed one G phase + one F phase later and the chain behind
     // the publication (9 warps in, exchange, F update) takes most of that (trace: RESNMTF_FU_TIMELINE=1) -- publishing
     // after the first G-phase MMAs instead (tried: no pipe drain at the phase boundary) cost 350 ns of that slack.
-    // four independent accumulator chains (even / odd column of a pair x even / odd step): with two, a warp that has
-    // the DMMA pipe to itself (its two neighbours at a barrier) is limited by the dependent-MMA latency
-    double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0, qe0 = 0.0, qe1 = 0.0, qo0 = 0.0, qo1 = 0.0;
+    double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;  // two accumulator chains: even / odd column of a pair
     auto f_phase = [&](int i) {
       const int gs = i % 3;
       if (tid == 0) rn_fu_trace(vw, i, 0);
       rn_mbar_wait(&full[gs * NCW + ci], (uint32_t)((i / 3) & 1));
       if (tid == 0) rn_fu_trace(vw, i, 7);
       const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024 + off1;
-      pe0 = pe1 = po0 = po1 = qe0 = qe1 = qo0 = qo1 = 0.0;
+      pe0 = pe1 = po0 = po1 = 0.0;
 #pragma unroll
       for (int s = 0; s < 2 * NB; ++s) {
         if (s < 2 * nb) {  // uniform over the warp
           const double2 x = *reinterpret_cast<const double2*>(xs + s * 512);
-          if ((s & 1) && RN_FU_F_CHAINS == 4) {
-            rn_dmma(qe0, qe1, x.x, gfr[s][0]);
-            rn_dmma(qo0, qo1, x.y, gfr[s][1]);
-          } else {
-            rn_dmma(pe0, pe1, x.x, gfr[s][0]);
-            rn_dmma(po0, po1, x.y, gfr[s][1]);
-          }
+          rn_dmma(pe0, pe1, x.x, gfr[s][0]);
+          rn_dmma(po0, po1, x.y, gfr[s][1]);
         }
       }
     };
     auto publish = [&](int i) {
-      *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) =
-          make_double2((pe0 + po0) + (qe0 + qo0), (pe1 + po1) + (qe1 + qo1));
+      *reinterpret_cast<double2*>(Pw + ((i & 1) * NCW + ci) * 64 + 2 * lane) = make_double2(pe0 + po0, pe1 + po1);
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&pw_full[i & 1]);
       if (lane == 0) rn_fu_trace(vw, i, 8 + ci);  // per-warp publication time
@@ -590,7 +567,6 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
           rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
           rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
         }
-        if (b == RN_FU_PUBLISH_AFTER && i + 1 < NGL) publish(i + 1);
       }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&empty[gs * NCW + ci]);
@@ -603,7 +579,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     for (int i = 0; i < NGL; ++i) {
       if (i + 1 < NGL) {
         f_phase(i + 1);
-        if (RN_FU_PUBLISH_AFTER < 0) publish(i + 1);
+        publish(i + 1);
       }
       g_phase(i);
     }
