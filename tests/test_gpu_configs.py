@@ -24,17 +24,20 @@ def test_c2_full_size_two_sweeps_vs_oracle_and_paths_agree(ctx):
     x = synth.prep(x)
     f, s, g = synth.random_factors(n, p, k, np.random.default_rng(1))
     prob = Problem([x], [k], [f], [s], [g])
+    compare_trace(prob, ctx, n_iters=2, err_mode=L.ERR_AUTO, impl=L.IMPL_FUSED)  # the default path at this size
     compare_trace(prob, ctx, n_iters=2, err_mode=L.ERR_AUTO, impl=L.IMPL_TMA)
     outs = {}
-    for impl, mode in ((L.IMPL_TMA, L.ERR_ALGEBRAIC), (L.IMPL_DMMA, L.ERR_DIRECT), (L.IMPL_DFMA, L.ERR_DIRECT)):
+    for impl, mode in ((L.IMPL_TMA, L.ERR_ALGEBRAIC), (L.IMPL_FUSED, L.ERR_ALGEBRAIC), (L.IMPL_DMMA, L.ERR_DIRECT),
+                       (L.IMPL_DFMA, L.ERR_DIRECT)):
         fit = prob.device_fit(ctx, err_mode=mode, impl=impl)
         fit.run(5)
         errs = fit.errors()
+        assert fit.counters()["impl"] == impl
         fit.normalise()
         outs[impl] = (fit.get_factors(0), errs)
         fit.close()
     ref = outs[L.IMPL_TMA]
-    for impl in (L.IMPL_DMMA, L.IMPL_DFMA):
+    for impl in (L.IMPL_FUSED, L.IMPL_DMMA, L.IMPL_DFMA):
         for a, b in zip(outs[impl][0][:3], ref[0][:3]):
             assert rel_err(a, b) <= RTOL
         assert rel_err(outs[impl][1], ref[1]) <= RTOL  # direct vs algebraic error
@@ -42,7 +45,25 @@ def test_c2_full_size_two_sweeps_vs_oracle_and_paths_agree(ctx):
     np.testing.assert_allclose(ref[0][2].sum(0), np.ones(k), rtol=0, atol=1e-12)
 
 
-def test_c3_structure_four_views_phi_psi(ctx):
+@pytest.fixture(params=["default kernels", "fused kernel"])
+def kernel_family(request, monkeypatch):
+    """The reduced-size views are narrower than the fused kernel's padding rule admits, so they default to the
+    two-pass kernels; the second pass of each structure test lifts the rule (the full-size configs run fused)."""
+    if request.param == "fused kernel":
+        monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
+    return request.param
+
+
+def assert_family(prob, ctx, family):
+    fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC)
+    try:
+        fit.run(1)
+        assert fit.counters()["impl"] == (L.IMPL_FUSED if family == "fused kernel" else L.IMPL_TMA)
+    finally:
+        fit.close()
+
+
+def test_c3_structure_four_views_phi_psi(ctx, kernel_family):
     """4 views; 1-2 and 3-4 share rows (phi = 200), 1&3 and 2&4 share columns (psi = 200); k = 5."""
     n, p, k = 12500, 1250, 5
     _, r12, _ = planted(8, 8, 5, 1)  # placeholders replaced below
@@ -63,10 +84,11 @@ def test_c3_structure_four_views_phi_psi(ctx):
     inits = [synth.random_factors(n, p, k, irng) for _ in range(4)]
     prob = Problem(data, [k] * 4, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
                    phi=O.init_rest_mats(phi, 4), psi=O.init_rest_mats(psi, 4), row_names=rn, col_names=cn)
+    assert_family(prob, ctx, kernel_family)
     compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_AUTO)
 
 
-def test_c4_structure_eight_views_phi_xi_psi(ctx):
+def test_c4_structure_eight_views_phi_xi_psi(ctx, kernel_family):
     """8 views, all sharing rows and columns, phi = psi = 200 and xi = 50 on every pair; k = 8."""
     n, p, k, V = 6250, 500, 8, 8
     rng = np.random.default_rng(synth.config_seed(4, 0))
@@ -81,4 +103,5 @@ def test_c4_structure_eight_views_phi_xi_psi(ctx):
     prob = Problem(data, [k] * V, [i[0] for i in inits], [i[1] for i in inits], [i[2] for i in inits],
                    phi=O.init_rest_mats(200.0 * up, V), xi=O.init_rest_mats(50.0 * up, V),
                    psi=O.init_rest_mats(200.0 * up, V), row_names=rn, col_names=cn)
+    assert_family(prob, ctx, kernel_family)
     compare_trace(prob, ctx, n_iters=3, err_mode=L.ERR_AUTO)
