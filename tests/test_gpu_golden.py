@@ -11,9 +11,11 @@ from resnmtf_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA, L.IMPL_FUSED])
 @pytest.mark.parametrize("name", CASES)
-def test_fixed_sweeps_match_golden(ctx, name, impl):
+def test_fixed_sweeps_match_golden(ctx, name, impl, monkeypatch):
+    if impl == L.IMPL_FUSED:  # the golden views are narrow: lift the fused kernel's padding rule
+        monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
     prob, z, V = load(name)
     fit = prob.device_fit(ctx, err_mode=L.ERR_AUTO, impl=impl)
     try:
@@ -32,8 +34,11 @@ def test_fixed_sweeps_match_golden(ctx, name, impl):
         fit.close()
 
 
+@pytest.mark.parametrize("family", ["default kernels", "fused kernel"])
 @pytest.mark.parametrize("name", CASES)
-def test_converged_run_matches_golden(ctx, name):
+def test_converged_run_matches_golden(ctx, name, family, monkeypatch):
+    if family == "fused kernel":
+        monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
     prob, z, V = load(name)
     fit = prob.device_fit(ctx)
     try:
