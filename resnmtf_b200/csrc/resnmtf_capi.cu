@@ -1396,7 +1396,9 @@ extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, in
   fit->counters.kernel_launches = 0;
   const int64_t it0 = fit->h_ctrl.iters;
   RN_CUDA(cudaEventRecord(fit->ctx->ev0, st));
-  const int64_t conv_batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 8));
+  // sweeps enqueued between two reads of the device-side stop flag: a read costs a stream synchronisation (~30 us), a
+  // sweep launched after the flag fired returns at once (~3 us)
+  const int64_t conv_batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 32));
   for (;;) {
     const int64_t donei = fit->h_ctrl.iters - it0;
     int64_t b;
