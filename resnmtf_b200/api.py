@@ -299,7 +299,8 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
                                  no_clusts, **common)
         if stability:
             results = stability_check(data, results, k_vec, phi, xi, psi, n_iters, spurious, num_repeats,
-                                      no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng, ctx=ctx)
+                                      no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng, ctx=ctx,
+                                      use_parallel=use_parallel)
         return results
     ks = list(range(int(k_min), int(k_max) + 1))
     if no_clusts:
@@ -361,5 +362,5 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
     if stability:
         results = stability_check(data, results, ks[best], phi, xi, psi, n_iters, spurious, num_repeats,
                                   no_clusts, distance, sample_rate, n_stability, stab_thres, remove_unstable,
-                                  rng=rng, ctx=ctx)
+                                  rng=rng, ctx=ctx, use_parallel=use_parallel)
     return results

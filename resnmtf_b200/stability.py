@@ -131,19 +131,42 @@ def stability_repeat(results, data, dim_1, k, phi, xi, psi, n_iters, num_repeats
 
 
 def stability_check(data, results, k, phi, xi, psi, n_iters, spurious, num_repeats, no_clusts, distance,
-                    sample_rate=0.9, n_stability=5, stab_thres=0.6, remove_unstable=True, rng=None, ctx=None):
+                    sample_rate=0.9, n_stability=5, stab_thres=0.6, remove_unstable=True, rng=None, ctx=None,
+                    use_parallel=True):
     """R/stability_analysis.r:302-338.  ``k`` may be a vector (the fixed-k caller passes k_vec; base R's
-    matrix(ncol = k) then uses its first element -- quirk Q9)."""
+    matrix(ncol = k) then uses its first element -- quirk Q9).  The ``n_stability`` repeats are independent fits
+    (SURVEY 8e): each gets its own child generator -- so the result does not depend on how many GPUs run them --
+    and, with ``use_parallel`` and more than one visible GPU, they are dealt round-robin to one context (and one
+    host thread) per GPU, like the fits of the k-sweep."""
     if number_biclusters(results) == 0:
         print("No biclusters detected!")
         return results
+    from .device import device_contexts
+
     k = int(np.atleast_1d(k)[0])
     n_views = len(data)
     dim_1 = data[0].shape
+    n_rep = int(n_stability)
+    rng = np.random.default_rng() if rng is None else rng
+    child_rngs = rng.spawn(n_rep)
+    contexts = device_contexts(ctx) if (use_parallel and ctx is not None) else [ctx]
+    reps = [None] * n_rep
+
+    def run_rank(r):
+        for i in range(r, n_rep, len(contexts)):
+            reps[i] = stability_repeat(results, data, dim_1, k, phi, xi, psi, n_iters, num_repeats, distance, spurious,
+                                       n_views, sample_rate, child_rngs[i], contexts[r])
+
+    if len(contexts) == 1 or n_rep <= 1:
+        contexts = contexts[:1]
+        run_rank(0)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=len(contexts)) as pool:  # ctypes releases the GIL inside the library
+            list(pool.map(run_rank, range(len(contexts))))
     relevance = np.zeros((n_views, k))
-    for _ in range(int(n_stability)):
-        rep = stability_repeat(results, data, dim_1, k, phi, xi, psi, n_iters, num_repeats, distance, spurious,
-                               n_views, sample_rate, rng, ctx)
+    for rep in reps:  # in repeat order, as the reference accumulates them
         if not rep["stability_performed"]:
             return results
         relevance = relevance + rep["relevance"]

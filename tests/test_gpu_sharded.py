@@ -111,3 +111,23 @@ def test_k_sweep_placed_on_two_gpus_equals_serial_sweep():
         for a, b in zip(par[key], ser[key]):
             assert np.array_equal(a, b), key
     assert par["bisil"] == ser["bisil"]
+
+
+@pytest.mark.skipif(L.device_count() < WORLD, reason="needs 2 GPUs")
+def test_stability_repeats_placed_on_two_gpus_equal_serial():
+    """The n_stability resample fits of apply_resnmtf (R/stability_analysis.r:302-338) dealt to one context per
+    GPU give exactly the single-GPU result (per-repeat child generators): same surviving biclusters."""
+    from resnmtf_b200 import synth
+    from resnmtf_b200.api import apply_resnmtf
+    from resnmtf_b200.device import Context
+
+    views, _ = synth.block_views(2, seed=33)
+    ctx = Context(0)
+    kw = dict(k_val=3, spurious=True, stability=True, n_stability=4, ctx=ctx, max_iters=500)
+    par = apply_resnmtf(views, use_parallel=True, rng=np.random.default_rng(11), **kw)
+    ser = apply_resnmtf(views, use_parallel=False, rng=np.random.default_rng(11), **kw)
+    for key in ("output_f", "row_clusters", "col_clusters"):
+        for a, b in zip(par[key], ser[key]):
+            assert np.array_equal(a, b), key
+    for v in range(2):
+        assert sorted(par["row_clusters"][v].sum(axis=0).tolist()) == [60.0, 60.0, 60.0]
