@@ -55,8 +55,9 @@ extern "C" {
 #define RESNMTF_IMPL_DMMA 2 /* FP64 tensor-core mma.sync m8n8k4 (k <= 8), X loaded straight into fragments */
 #define RESNMTF_IMPL_TMA 3  /* same MMAs, X staged through a shared-memory ring by TMA bulk copies       */
 #define RESNMTF_IMPL_FUSED 4 /* one pass over X per update-iteration: 8-row groups resident in the shared memory of a
-                                CTA cluster do the F step and the G step (k <= 8, p <= 4096, one GPU per view); views
-                                that do not qualify run RESNMTF_IMPL_TMA */
+                                cluster of 1..8 CTAs do the F step and the G step (k <= 8, p <= 8064, one GPU per view,
+                                at most 7 phi partners); views that do not qualify run RESNMTF_IMPL_TMA.  This is what
+                                RESNMTF_IMPL_AUTO picks */
 
 typedef struct resnmtf_ctx resnmtf_ctx;
 typedef struct resnmtf_fit resnmtf_fit;
