@@ -39,19 +39,19 @@ def r_density(x, from_=None, to=None, n=512, cut=3.0):
     if n > 512:
         n = 2 ** int(np.ceil(np.log2(n)))
     lo, up = from_ - 4 * bw, to + 4 * bw
-    y = np.zeros(2 * n)
     delta = (up - lo) / (n - 1)
     xpos = (x - lo) / delta
     ix = np.floor(xpos).astype(np.int64)
     fx = xpos - ix
     w = 1.0 / N
     inside = (ix >= 0) & (ix <= n - 2)
-    np.add.at(y, ix[inside], w * (1 - fx[inside]))
-    np.add.at(y, ix[inside] + 1, w * fx[inside])
     left = ix == -1
-    np.add.at(y, np.zeros(left.sum(), dtype=np.int64), w * fx[left])
     right = ix == n - 1
-    np.add.at(y, ix[right], w * (1 - fx[right]))
+    # linear binning (BinDist): one ordered accumulation -- np.bincount adds in input order, i.e. exactly the sequence
+    # of four np.add.at passes this replaces (bit-identical), at a fraction of their cost
+    idx = np.concatenate([ix[inside], ix[inside] + 1, np.zeros(int(left.sum()), dtype=np.int64), ix[right]])
+    wts = np.concatenate([w * (1 - fx[inside]), w * fx[inside], w * fx[left], w * (1 - fx[right])])
+    y = np.bincount(idx, weights=wts, minlength=2 * n).astype(np.float64)
     kords = np.linspace(0, 2 * (up - lo), 2 * n)
     kords[n + 1:2 * n] = -kords[n - 1:0:-1]
     kords = np.exp(-0.5 * (kords / bw) ** 2) / (bw * np.sqrt(2 * np.pi))
