@@ -24,14 +24,32 @@ from .stability import stability_check
 # --------------------------------------------------------------------------------------------------
 
 
+_torch_lock = __import__("threading").Lock()
+_torch_warm = False
+
+
 def _torch_cuda():
     """torch with a CUDA device, or None (torch is plumbing here: device tensors + library GEMM / eigensolver for the
-    boundary inputs of a fit, never the update path)."""
+    boundary inputs of a fit, never the update path).  The first caller initialises torch's lazily loaded linear
+    algebra backend under a lock: that initialisation is not thread-safe, and the fits of a k-sweep run on one host
+    thread per GPU."""
+    global _torch_warm
     try:
         import torch
     except Exception:  # pragma: no cover - torch is part of the image
         return None
-    return torch if torch.cuda.is_available() else None
+    if not torch.cuda.is_available():
+        return None
+    if not _torch_warm:
+        with _torch_lock:
+            if not _torch_warm:
+                for dev in range(torch.cuda.device_count()):
+                    e = torch.eye(4, dtype=torch.float64, device=torch.device("cuda", dev))
+                    torch.linalg.eigh(e @ e)
+                    torch.randperm(4, device=e.device)
+                    torch.cuda.synchronize(dev)
+                _torch_warm = True
+    return torch
 
 
 def _gram_topk_torch(torch, xt, k):
