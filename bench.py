@@ -285,6 +285,12 @@ def run_gpu(args):
         # second limiter, for the record: FP64 MMA work (k padded to 8, two phases) against the DMMA rate measured by
         # tools/microbench.cu on this GPU model (18.5 T FMA/s chip-wide; DMMA and scalar FP64 share one pipe)
         fma = 2.0 * N_ROWS * N_COLS * 8 * prof_iters * len(K_SWEEP)
+        # for comparison with the two-pass formulation (SURVEY 8d B_alg: X read by the F step AND by the G step): the
+        # rate at which those bytes would have had to move to finish a launch in the same time
+        roofline["two_pass_bytes_equivalent"] = {
+            "gbs": achieved * (2.0 * N_ROWS * N_COLS) / (1.0 * N_ROWS * N_COLS), "frac_of_peak": 2.0 * achieved / peak,
+            "note": "X-dominated approximation: 2x the one-pass rate; above 1.0 means faster than any two-pass kernel "
+                    "pair could run on this HBM"}
         roofline["fp64_mma"] = {"achieved_tfma_per_s": fma / (ran[dom][1] * 1e-3) * 1e-12, "chip_peak_tfma_per_s": 18.5,
                                 "usable_fraction_of_chip": 132.0 * 3 / (148 * 4),
                                 "peak_source": "tools/microbench.cu (DESIGN.md section 4), not MEASURED_PEAKS.json"}
