@@ -109,6 +109,10 @@ int resnmtf_fit_set_data_device(resnmtf_fit* fit, int v, const double* x_dev, in
 typedef struct resnmtf_data resnmtf_data;
 int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
                         resnmtf_data** out);
+/* Same, but x is a DEVICE pointer on ctx's device: the sub-sampled views of the stability analysis
+ * (R/stability_analysis.r:215-253) are gathered on the device from the resident data and never visit the host. */
+int resnmtf_data_create_device(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x_dev, int64_t ld,
+                               resnmtf_data** out);
 int resnmtf_data_destroy(resnmtf_data* data);
 int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* data);
 
@@ -163,6 +167,21 @@ int resnmtf_fit_get_counters(resnmtf_fit* fit, resnmtf_counters* out);
  * direct residual pass, ms[4] iteration
  * bookkeeping; launches[i] is the number of timed intervals of that class. */
 int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[5], int64_t launches[5]);
+
+/* ---- post-fit reductions -------------------------------------------------------- */
+
+/* jsd_calc() of R/utils.r:95-106 for a batch of column pairs, one thread block per pair:
+ *   out[i] = JSD(density(vecs[, pair_a[i]]), density(vecs[, pair_b[i]]))
+ * with stats::density's defaults (gaussian kernel, 512 points, from = 0, to = the larger of the two column maxima,
+ * estimates zeroed above the column's own maximum) and philentropy::JSD's base-2 logarithm on the normalised
+ * estimates.  This is the inner operation of the spurious-bicluster test (calculate_f_shuffle_jsd(),
+ * R/obtain_bicl.r:55-68, and check_biclusters(), :113-133): 15 k^2 pairs per fit.
+ * vecs: n x m column-major HOST matrix (leading dimension ld) -- the factor columns; bw[j] = bw.nrd0(vecs[, j]) and
+ * vmax[j] = max(vecs[, j]) are computed by the caller once per column (O(n), need order statistics).  0-based column
+ * indices.  The sums are evaluated in a fixed order: two calls give bit-identical results. */
+int resnmtf_jsd_pairs(resnmtf_ctx* ctx, const double* vecs, int64_t n, int32_t m, int64_t ld,
+                      const double* bw, const double* vmax, const int32_t* pair_a, const int32_t* pair_b,
+                      int64_t n_pairs, double* out);
 
 /* ---- row-sharded view across ranks (one process per GPU; NCCL all-reduce of the p x k partials) ---- */
 

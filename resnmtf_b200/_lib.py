@@ -25,7 +25,8 @@ EXPORTS = (
     "resnmtf_ctx_device",
     "resnmtf_last_error", "resnmtf_version", "resnmtf_device_count",
     "resnmtf_fit_create", "resnmtf_fit_destroy", "resnmtf_fit_set_data", "resnmtf_fit_set_data_device",
-    "resnmtf_data_create", "resnmtf_data_destroy", "resnmtf_fit_attach_data",
+    "resnmtf_data_create", "resnmtf_data_create_device", "resnmtf_data_destroy", "resnmtf_fit_attach_data",
+    "resnmtf_jsd_pairs",
     "resnmtf_fit_set_factors", "resnmtf_fit_set_restrictions", "resnmtf_fit_set_shared_map",
     "resnmtf_fit_set_options", "resnmtf_fit_run", "resnmtf_fit_step", "resnmtf_fit_get_factors",
     "resnmtf_fit_normalise", "resnmtf_fit_get_errors", "resnmtf_fit_get_view_errors",
@@ -88,7 +89,9 @@ def load():
         "resnmtf_fit_set_data": (C.c_int, [vp, C.c_int, vp, i64]),
         "resnmtf_fit_set_data_device": (C.c_int, [vp, C.c_int, vp, i64]),
         "resnmtf_data_create": (C.c_int, [vp, i64, i64, vp, i64, C.POINTER(vp)]),
+        "resnmtf_data_create_device": (C.c_int, [vp, i64, i64, vp, i64, C.POINTER(vp)]),
         "resnmtf_data_destroy": (C.c_int, [vp]),
+        "resnmtf_jsd_pairs": (C.c_int, [vp, vp, i64, i32, i64, vp, vp, vp, vp, i64, vp]),
         "resnmtf_fit_attach_data": (C.c_int, [vp, C.c_int, vp]),
         "resnmtf_fit_set_factors": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
         "resnmtf_fit_set_restrictions": (C.c_int, [vp, vp, vp, vp]),

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib as L
 from . import prep, sharding
 from .bicluster import obtain_biclusters
-from .device import DeviceData, DeviceFit, default_context, device_contexts
+from .device import DeviceFit, default_context, device_contexts
 from .prep import NamedMatrix, as_named
 from .stability import stability_check
 
@@ -52,18 +52,35 @@ def _torch_cuda():
     return torch
 
 
+_TOPK_COLS = 16  # RESNMTF_MAX_K: the triplets are always computed to this width and sliced, so that a cached set (the
+                 # k-sweep fits the same data for every k) and a freshly computed one are the same numbers
+
+
+def torch_device(index):
+    """torch.device of CUDA device ``index`` (< 0 or None: the current one)."""
+    import torch
+
+    return torch.device("cuda", int(index) if index is not None and index >= 0 else torch.cuda.current_device())
+
+
 def _gram_topk_torch(torch, xt, k):
     """Top-k singular triplets of the n x p matrix whose column-major storage is the row-major p x n tensor ``xt``,
     through the Gram matrix of the smaller side.  Returns device tensors |U| (n x k), d (k), |V| (p x k)."""
+    u, d, v = _gram_triplets_torch(torch, xt)
+    return u[:, :k], d[:k], v[:, :k]
+
+
+def _gram_triplets_torch(torch, xt):
     p, n = xt.shape
+    kc = min(_TOPK_COLS, p, n)
     if p <= n:
         w, v = torch.linalg.eigh(xt @ xt.T)
-        w, v = w[-k:].flip(0), v[:, -k:].flip(1)
+        w, v = w[-kc:].flip(0), v[:, -kc:].flip(1)
         d = torch.sqrt(torch.clamp(w, min=0.0))
         u = (xt.T @ v) / d[None, :]
     else:
         w, u = torch.linalg.eigh(xt.T @ xt)
-        w, u = w[-k:].flip(0), u[:, -k:].flip(1)
+        w, u = w[-kc:].flip(0), u[:, -kc:].flip(1)
         d = torch.sqrt(torch.clamp(w, min=0.0))
         v = (xt @ u) / d[None, :]
     return u.abs(), d, v.abs()
@@ -79,7 +96,7 @@ def _svd_topk_device(x, k, device):
     torch = _torch_cuda()
     if torch is None:
         return None
-    dev = torch.device("cuda", int(device) if device is not None and device >= 0 else torch.cuda.current_device())
+    dev = torch_device(device)
     xt = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)  # p x n, row-major (== column-major n x p)
     u, d, v = _gram_topk_torch(torch, xt, k)
     return u.cpu().numpy(), d.cpu().numpy(), v.cpu().numpy()
@@ -96,51 +113,65 @@ def _init_from_svd(f, d, g, k, rng, sigma=0.05):
     return f, s, g, f.sum(axis=0), g.sum(axis=0)
 
 
-def shuffled_fits_device(data, n_clusts, num_repeats, rng, ctx, max_iters=0):
-    """obtain_shuffled_f (R/obtain_bicl.r:31-42) with every matrix-sized step on the device: per
-    repeat and view the full random permutation of the entries (shuffle_view, :11-22, incl. its rejection of all-zero
-    rows / columns), the re-normalisation apply_resnmtf applies to the shuffled data (check_inputs, R/utils.r:20-27,
-    86-88), the SVD initialisation and the fit itself; only the n x k factors come back.  The shuffle refits run
-    with phi = xi = psi = NULL (R/obtain_bicl.r:35-39), so no shared-index maps are needed.  Randomness: one seed per
-    shuffled view and the k x k initialisation noise are drawn from ``rng`` in the reference's order; the permutation
-    itself comes from a device generator keyed by that seed.  Returns None when torch / CUDA is unavailable."""
+def device_route(data):
+    """Matrix-sized views (>= 250k entries each) keep every matrix-sized step on the GPU -- initialisation, shuffles,
+    sub-samples, bisilhouette distance blocks, JSD thresholds; small ones, and hosts without torch
+    CUDA, take the reference's host route around the device loop."""
+    if min(int(np.prod(m.shape)) for m in data) < 250_000:
+        return False
+    return _torch_cuda() is not None
+
+
+def _shuffle_refit_device(torch, xts, k, rng, ctx, max_iters=0):
+    """One repeat of obtain_shuffled_f (R/obtain_bicl.r:33-40) with every matrix-sized step on the device (SURVEY 8f
+    row N2): per view the full random permutation of the entries (shuffle_view, :11-22, incl. its rejection of
+    all-zero rows / columns), the re-normalisation apply_resnmtf applies to the shuffled data (check_inputs,
+    R/utils.r:20-27, 86-88), the SVD initialisation and the fit itself; only the n x k factors come back.  The shuffle
+    refits run with phi = xi = psi = NULL (R/obtain_bicl.r:35-39), so no shared-index maps are needed.  Randomness:
+    one seed per shuffled view and the k x k initialisation noise are drawn from ``rng``; the permutation itself comes
+    from a device generator keyed by that seed."""
+    dev = xts[0].device
+    n_v = len(xts)
+    shapes = [(int(x.shape[1]), int(x.shape[0])) for x in xts]  # (n, p)
+    with torch.cuda.device(dev):
+        messed = []
+        for xd in xts:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(rng.integers(0, 2 ** 62)))
+            while True:  # the storage order of xd is R's column-major vector order
+                perm = torch.randperm(xd.numel(), generator=gen, device=dev)
+                m = xd.reshape(-1)[perm].reshape(xd.shape)
+                if not bool((m.sum(dim=0) == 0).any() or (m.sum(dim=1) == 0).any()):
+                    break
+            del perm
+            messed.append(m / m.sum(dim=1, keepdim=True))  # L1 column normalisation (columns of X = rows of m)
+        fit = DeviceFit(ctx, [s_[0] for s_ in shapes], [s_[1] for s_ in shapes], [k] * n_v)
+        try:
+            for v_, m in enumerate(messed):
+                u, d, g = _gram_topk_torch(torch, m, k)
+                f0, s0, g0, lam, mu = _init_from_svd(u.cpu().numpy(), d.cpu().numpy(), g.cpu().numpy(), k, rng)
+                torch.cuda.current_stream(dev).synchronize()  # the library reads m on its own stream
+                fit.set_data_device(v_, m.data_ptr(), shapes[v_][0])
+                fit.set_factors(v_, f0, s0, g0, lam, mu)
+            fit.run(None, 1.0e-6, max_iters)
+            fit.normalise()
+            return [fit.get_factors(v_)[0] for v_ in range(n_v)]
+        finally:
+            fit.close()
+
+
+def shuffled_fits_device(data, n_clusts, num_repeats, rng, ctx, max_iters=0, resident=None):
+    """obtain_shuffled_f (R/obtain_bicl.r:31-42) on the device, one repeat after the other: every repeat draws from its
+    own child generator of ``rng`` (the pool of apply_resnmtf runs the same repeats as independent units, possibly on
+    other GPUs, with the same generators).  Returns None when torch / CUDA is unavailable."""
     torch = _torch_cuda()
     if torch is None:
         return None
-    dev = torch.device("cuda", int(ctx.device))
-    n_v = len(data)
-    k = int(n_clusts)
-    xs = [torch.from_numpy(np.ascontiguousarray((m.x if hasattr(m, "x") else m).T)).to(dev) for m in data]
-    shapes = [(int(x.shape[1]), int(x.shape[0])) for x in xs]  # (n, p)
-    f_mess = []
-    with torch.cuda.device(dev):
-        for _ in range(int(num_repeats)):
-            messed = []
-            for xd in xs:
-                gen = torch.Generator(device=dev)
-                gen.manual_seed(int(rng.integers(0, 2 ** 62)))
-                while True:  # the storage order of xd is R's column-major vector order
-                    perm = torch.randperm(xd.numel(), generator=gen, device=dev)
-                    m = xd.reshape(-1)[perm].reshape(xd.shape)
-                    if not bool((m.sum(dim=0) == 0).any() or (m.sum(dim=1) == 0).any()):
-                        break
-                del perm
-                messed.append(m / m.sum(dim=1, keepdim=True))  # L1 column normalisation (columns of X = rows of m)
-            fit = DeviceFit(ctx, [s_[0] for s_ in shapes], [s_[1] for s_ in shapes], [k] * n_v)
-            try:
-                for v_, m in enumerate(messed):
-                    u, d, g = _gram_topk_torch(torch, m, k)
-                    f0, s0, g0, lam, mu = _init_from_svd(u.cpu().numpy(), d.cpu().numpy(), g.cpu().numpy(), k, rng)
-                    torch.cuda.current_stream().synchronize()  # the library reads m on its own stream
-                    fit.set_data_device(v_, m.data_ptr(), shapes[v_][0])
-                    fit.set_factors(v_, f0, s0, g0, lam, mu)
-                fit.run(None, 1.0e-6, max_iters)
-                fit.normalise()
-                f_mess.append([fit.get_factors(v_)[0] for v_ in range(n_v)])
-            finally:
-                fit.close()
-            del messed
-    return f_mess
+    if resident is None:
+        dev = torch_device(ctx.device)
+        resident = [torch.from_numpy(np.ascontiguousarray((m.x if hasattr(m, "x") else m).T)).to(dev) for m in data]
+    return [_shuffle_refit_device(torch, resident, int(n_clusts), r, ctx, max_iters)
+            for r in rng.spawn(int(num_repeats))]
 
 
 def _svd_topk(x, k, device=None):
@@ -199,7 +230,9 @@ def init_mats(x, n_v, k_vec, init_f, init_g, init_s, rng, device=None):
 
 
 # --------------------------------------------------------------------------------------------------
-# res_nmtf_inner
+# one fit = core (initialisation + the loop of R/main.r:50-109 on the device + normalisation) and post-processing
+# (obtain_biclusters, R/main.r:122).  The two halves are separate so that the pool can run the cores and the shuffled
+# refits of many fits side by side and the post-processing once their inputs exist.
 # --------------------------------------------------------------------------------------------------
 
 
@@ -212,31 +245,50 @@ def _names_or_default(data):
     return rn, cn
 
 
-def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, init_g=None, k_vec=None,
-                   phi=None, xi=None, psi=None, n_iters=None, num_repeats=5, spurious=True,
-                   distance="euclidean", no_clusts=False, *, rng=None, ctx=None, max_iters=0,
-                   err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO, device_data=None):
-    """R/main.r:32-140.  ``data``: list of (already prepped) views; ``row_indices`` / ``column_indices``:
-    per view a dict {other view: shared names or None}, as produced by ``prep.reorder_data``.
-    ``device_data``: optional list of ``DeviceData`` (the views already uploaded, shared between the fits of
-    one apply_resnmtf call)."""
-    rng = np.random.default_rng() if rng is None else rng
-    ctx = default_context() if ctx is None else ctx
-    data = [as_named(m) for m in data]
+def _init_resident(torch, resident, k_vec, rng, cache):
+    """init_mats_inner (R/update_steps.r:78-125) on views resident on the GPU; ``cache`` (a dict, or None) keeps the
+    triplets of data that is fitted for several k."""
+    out = [[], [], [], [], []]
+    for v, xt in enumerate(resident):
+        k = int(k_vec[v])
+        with torch.cuda.device(xt.device):
+            if cache is not None and v in cache:
+                trip = cache[v]
+            else:
+                trip = tuple(t.cpu().numpy() for t in _gram_triplets_torch(torch, xt))
+                if cache is not None:
+                    cache[v] = trip
+        u, d, g = trip
+        for lst, val in zip(out, _init_from_svd(u[:, :k], d[:k], g[:, :k], k, rng)):
+            lst.append(val)
+    return tuple(out)
+
+
+def _fit_core(data, row_indices, column_indices, init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, *, rng, ctx,
+              max_iters=0, err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO, device_data=None, resident=None, eig_cache=None):
+    """R/main.r:38-110: initial factors, the update loop (one C-ABI call), normalisation_check."""
     n_v = len(data)
-    xs = [np.asfortranarray(m.x, dtype=np.float64) for m in data]
     phi = np.zeros((n_v, n_v)) if phi is None else np.asarray(phi, dtype=np.float64)
     xi = np.zeros((n_v, n_v)) if xi is None else np.asarray(xi, dtype=np.float64)
     psi = np.zeros((n_v, n_v)) if psi is None else np.asarray(psi, dtype=np.float64)
-    cf, cs, cg, clam, cmu = init_mats(xs, n_v, k_vec, init_f, init_g, init_s, rng, device=ctx.device)
+    xs = None
+    if resident is not None and (init_f is None or init_g is None or init_s is None):
+        cf, cs, cg, clam, cmu = _init_resident(_torch_cuda(), resident, k_vec, rng, eig_cache)
+    else:
+        xs = [np.asfortranarray(m.x, dtype=np.float64) for m in data] if resident is None else None
+        cf, cs, cg, clam, cmu = init_mats(xs, n_v, k_vec, init_f, init_g, init_s, rng, device=ctx.device)
     k_used = [int(f.shape[1]) for f in cf]
-
-    fit = DeviceFit(ctx, [x.shape[0] for x in xs], [x.shape[1] for x in xs], k_used)
+    fit = DeviceFit(ctx, [m.shape[0] for m in data], [m.shape[1] for m in data], k_used)
     try:
         fit.set_options(err_mode=err_mode, impl=impl)
         for v in range(n_v):
             if device_data is not None:
                 fit.attach_data(v, device_data[v])
+            elif resident is not None:
+                import torch
+
+                torch.cuda.current_stream(resident[v].device).synchronize()  # the library reads on its own stream
+                fit.set_data_device(v, resident[v].data_ptr(), data[v].shape[0])
             else:
                 fit.set_data(v, xs[v])  # data_norms (R/main.r:48) are computed on the device
             fit.set_factors(v, cf[v], cs[v], cg[v], clam[v], cmu[v])
@@ -254,26 +306,132 @@ def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, 
         counters = fit.counters()
     finally:
         fit.close()
-    current_f = [o[0] for o in outs]
-    current_s = [o[1] for o in outs]
-    current_g = [o[2] for o in outs]
+    return {"output_f": [o[0] for o in outs], "output_s": [o[1] for o in outs], "output_g": [o[2] for o in outs],
+            "total_err": total_err, "lambda": [lm[0] for lm in lam_mu], "mu": [lm[1] for lm in lam_mu],
+            "counters": counters}
+
+
+def _fit_post(core, data, n_iters, num_repeats, spurious, distance, no_clusts, *, rng, ctx, shuffled_f=None,
+              resident=None, want_bisil=True):
+    """R/main.r:111-139: the result list of res_nmtf_inner from the normalised factors."""
     if no_clusts:
-        return {"output_f": current_f, "output_s": current_s, "output_g": current_g}
-    clusters = obtain_biclusters(data, current_f, current_g, current_s, num_repeats, spurious, distance,
-                                 rng=rng, ctx=ctx)
-    if n_iters is None:
-        error = float(np.mean(total_err[-10:]))
-    else:
-        error = float(total_err[-1])
+        return {"output_f": core["output_f"], "output_s": core["output_s"], "output_g": core["output_g"]}
+    clusters = obtain_biclusters(data, core["output_f"], core["output_g"], core["output_s"], num_repeats, spurious,
+                                 distance, rng=rng, ctx=ctx, shuffled_f=shuffled_f, resident=resident,
+                                 want_bisil=want_bisil)
+    total_err = core["total_err"]
+    error = float(np.mean(total_err[-10:])) if n_iters is None else float(total_err[-1])
     return {
-        "output_f": current_f, "output_s": current_s, "output_g": current_g,
+        "output_f": core["output_f"], "output_s": core["output_s"], "output_g": core["output_g"],
         "Error": error, "All_Error": total_err, "bisil": clusters["bisil"],
         "row_clusters": clusters["row_clustering"], "col_clusters": clusters["col_clustering"],
-        "lambda": [lm[0] for lm in lam_mu], "mu": [lm[1] for lm in lam_mu],
+        "lambda": core["lambda"], "mu": core["mu"],
         # not in the reference's list: names (R carries them as dimnames) and device counters
         "row_names": [m.rownames for m in data], "col_names": [m.colnames for m in data],
-        "counters": counters,
+        "counters": core["counters"],
     }
+
+
+def run_fits(pool, specs, phi, xi, psi, n_iters, num_repeats, spurious, distance, no_clusts, max_iters=0,
+             err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO):
+    """Runs the res_nmtf_inner calls described by ``specs`` on the pool and returns their result lists in order.
+
+    A spec: dict(key=<data key placed on the pool>, data=[views], row_indices, col_indices, k_vec, rng, and optionally
+    init_f / init_s / init_g, shared=<the data is fitted by several specs>, want_bisil).  Phase A: the cores and -- when
+    spurious biclusters are to be removed -- the ``num_repeats`` shuffled refits of every spec, all independent units
+    (R/obtain_bicl.r:31-42 runs them inside the fit; they depend on k and on the data only).  Phase B: the
+    post-processing of every spec (JSD thresholds, binarisation, bisilhouette)."""
+    need_shuffles = bool(spurious) and not no_clusts
+    tasks, slots = [], []
+    for si, sp in enumerate(specs):
+        data, key = sp["data"], sp["key"]
+        on_dev = key in pool.loaders
+        k_vec = [int(k) for k in sp["k_vec"]]
+        cost = sharding.fit_cost([m.shape for m in data], max(k_vec))
+        sp["_shuffle_rngs"] = sp["rng"].spawn(int(num_repeats)) if need_shuffles else []
+
+        def core(worker, sp=sp, data=data, key=key, on_dev=on_dev, k_vec=k_vec):
+            shared = sp.get("shared", False)
+            return _fit_core(data, sp["row_indices"], sp["col_indices"], sp.get("init_f"), sp.get("init_s"),
+                             sp.get("init_g"), k_vec, phi, xi, psi, n_iters, rng=sp["rng"], ctx=worker.ctx,
+                             max_iters=max_iters, err_mode=err_mode, impl=impl,
+                             device_data=worker.get_handles(key) if shared else None,
+                             resident=worker.get_views(key) if on_dev else None,
+                             eig_cache=worker.eig_cache(key) if (shared and on_dev) else None)
+
+        tasks.append((cost * 1.01, core))
+        slots.append((si, None))
+        for r, srng in enumerate(sp["_shuffle_rngs"]):
+            def shuffle(worker, data=data, key=key, on_dev=on_dev, srng=srng,
+                        k=k_vec[0] if sp.get("init_f") is None else int(np.asarray(sp["init_f"][0]).shape[1])):
+                from .bicluster import shuffle_refit
+
+                return shuffle_refit(data, k, srng, worker.ctx, resident=worker.get_views(key) if on_dev else None)
+
+            tasks.append((cost, shuffle))
+            slots.append((si, r))
+    done = pool.run(tasks)
+    cores = [None] * len(specs)
+    f_mess = [[None] * len(sp["_shuffle_rngs"]) for sp in specs]
+    for (si, r), res in zip(slots, done):
+        if r is None:
+            cores[si] = res
+        else:
+            f_mess[si][r] = res
+    if no_clusts:
+        return [_fit_post(cores[si], sp["data"], n_iters, num_repeats, spurious, distance, True, rng=sp["rng"], ctx=None)
+                for si, sp in enumerate(specs)]
+
+    posts = []
+    for si, sp in enumerate(specs):
+        def post(worker, si=si, sp=sp):
+            on_dev = sp["key"] in pool.loaders
+            return _fit_post(cores[si], sp["data"], n_iters, num_repeats, spurious, distance, False, rng=sp["rng"],
+                             ctx=worker.ctx, shuffled_f=f_mess[si] if need_shuffles else None,
+                             resident=worker.get_views(sp["key"]) if on_dev else None,
+                             want_bisil=sp.get("want_bisil", True))
+
+        posts.append((max(int(k) for k in sp["k_vec"]) ** 2, post))
+    return pool.run(posts)
+
+
+def _single_pool(ctx):
+    from .fitpool import FitPool
+
+    return FitPool([ctx])
+
+
+def _place(pool, key, data):
+    """Puts the views of ``data`` on every GPU of the pool (resident, for matrix-sized views) or registers them as
+    host data (small views: every fit uploads through the library)."""
+    if device_route(data):
+        pool.place_resident(key, data)
+    else:
+        pool.place_host(key, data)
+
+
+# --------------------------------------------------------------------------------------------------
+# res_nmtf_inner
+# --------------------------------------------------------------------------------------------------
+
+
+def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, init_g=None, k_vec=None,
+                   phi=None, xi=None, psi=None, n_iters=None, num_repeats=5, spurious=True,
+                   distance="euclidean", no_clusts=False, *, rng=None, ctx=None, max_iters=0,
+                   err_mode=L.ERR_AUTO, impl=L.IMPL_AUTO):
+    """R/main.r:32-140.  ``data``: list of (already prepped) views; ``row_indices`` / ``column_indices``:
+    per view a dict {other view: shared names or None}, as produced by ``prep.reorder_data``."""
+    rng = np.random.default_rng() if rng is None else rng
+    ctx = default_context() if ctx is None else ctx
+    data = [as_named(m) for m in data]
+    with _single_pool(ctx) as pool:
+        _place(pool, "data", data)
+        spec = dict(key="data", data=data, row_indices=row_indices, col_indices=column_indices, k_vec=k_vec, rng=rng,
+                    init_f=init_f, init_s=init_s, init_g=init_g)
+        if k_vec is None:  # only legal with explicit initial factors: k comes from them
+            spec["k_vec"] = [np.asarray(f).shape[1] for f in init_f]
+        return run_fits(pool, [spec], phi, xi, psi, n_iters, num_repeats, spurious, distance, no_clusts,
+                        max_iters=max_iters, err_mode=err_mode, impl=impl)[0]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -291,6 +449,8 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
                   no_clusts=False, sample_rate=0.9, n_stability=5, stability=True, stab_thres=0.4,
                   remove_unstable=True, use_parallel=True, *, rng=None, ctx=None, max_iters=0):
     """R/main.r:214-335."""
+    from .fitpool import FitPool
+
     rng = np.random.default_rng() if rng is None else rng
     ctx = default_context() if ctx is None else ctx
     if not isinstance(data, (list, tuple)):
@@ -310,75 +470,49 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
     data = prep.check_inputs(named["data"], init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_min, k_max,
                              distance, num_repeats, no_clusts, sample_rate, n_stability, stability, stab_thres,
                              remove_unstable, spurious)
-    common = dict(rng=rng, ctx=ctx, max_iters=max_iters)
-    if k_vec is not None:
-        results = res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f, init_s,
-                                 init_g, k_vec, phi, xi, psi, n_iters, num_repeats, spurious, distance,
-                                 no_clusts, **common)
-        if stability:
-            results = stability_check(data, results, k_vec, phi, xi, psi, n_iters, spurious, num_repeats,
-                                      no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng, ctx=ctx,
-                                      use_parallel=use_parallel)
-        return results
-    ks = list(range(int(k_min), int(k_max) + 1))
-    if no_clusts:
+    if k_vec is None and no_clusts:
         # the reference fails here too: results carry no bisil, which.max(NULL) is integer(0) and the
         # `while (test == max_k)` at R/main.r:307 stops with "argument is of length zero"
         raise ValueError("argument is of length zero")
-    # The fits of the sweep are independent: every k gets its own child generator -- so the result
-    # does not depend on how many GPUs run the sweep -- and, with use_parallel and more than one visible
-    # GPU, the fits are placed longest-first on one context per GPU (the reference's %dopar% intent,
-    # R/main.r:288-299, which is unreachable there).  Each device uploads the views once and shares them.
-    child_rngs = rng.spawn(len(ks))
-    contexts = [ctx]
-    if use_parallel:
-        contexts = device_contexts(ctx)
-    shapes = [m.shape for m in data]
-    where, _ = sharding.assign_fits([sharding.fit_cost(shapes, k) for k in ks], len(contexts))
-    dev_data = {}
-
-    def fit_k(i):
-        c = contexts[where[i]]
-        if where[i] not in dev_data:
-            dev_data[where[i]] = [DeviceData(c, m.x) for m in data]
-        return res_nmtf_inner(data, reordering["row_indices"], reordering["col_indices"], init_f, init_s,
-                              init_g, [ks[i]] * n_v, phi, xi, psi, n_iters, num_repeats, spurious, distance,
-                              no_clusts, rng=child_rngs[i], ctx=c, max_iters=max_iters,
-                              device_data=dev_data[where[i]])
-
-    if len(contexts) == 1:
-        res_list = [fit_k(i) for i in range(len(ks))]
-    else:
-        from concurrent.futures import ThreadPoolExecutor
-
-        res_list = [None] * len(ks)
-
-        def run_rank(r):  # one host thread per GPU; ctypes releases the GIL inside the library
-            for i in range(len(ks)):
-                if where[i] == r:
-                    res_list[i] = fit_k(i)
-
-        with ThreadPoolExecutor(max_workers=len(contexts)) as pool:
-            list(pool.map(run_rank, range(len(contexts))))
-    common["device_data"] = dev_data.get(0) or [DeviceData(ctx, m.x) for m in data]
-    err_list = extract_bisils(res_list, ks)
-    test = ks[int(np.argmax(err_list))]
-    max_k = int(k_max)
-    if k_min != k_max:
-        while test == max_k:
-            max_k += 1
-            ks.append(max_k)
-            # quirk Q3 (R/main.r:312): `reordering$column_indices` does not exist, so the extension fits run
-            # with column_indices = NULL -- nothing is overwritten in the psi coupling.  Reproduced.
-            res_list.append(res_nmtf_inner(data, reordering["row_indices"], None, init_f, init_s, init_g,
-                                           [max_k] * n_v, phi, xi, psi, n_iters, num_repeats, spurious,
-                                           distance, no_clusts, **common))
-            err_list.append(res_list[-1]["bisil"])
-            test = ks[int(np.argmax(err_list))]
-    best = int(np.argmax(err_list))
-    results = res_list[best]
-    if stability:
-        results = stability_check(data, results, ks[best], phi, xi, psi, n_iters, spurious, num_repeats,
-                                  no_clusts, distance, sample_rate, n_stability, stab_thres, remove_unstable,
-                                  rng=rng, ctx=ctx, use_parallel=use_parallel)
-    return results
+    # The fits of one call are independent units: every fit gets its own child generator -- so the result
+    # does not depend on how many GPUs run them -- and, with use_parallel and more than one visible GPU, they are
+    # spread over one context per GPU (the reference's %dopar% intent, R/main.r:288-299, which is unreachable there).
+    contexts = device_contexts(ctx) if use_parallel else [ctx]
+    fit_kw = dict(max_iters=max_iters)
+    with FitPool(contexts) as pool:
+        _place(pool, "data", data)
+        base = dict(key="data", data=data, row_indices=reordering["row_indices"], init_f=init_f, init_s=init_s,
+                    init_g=init_g, shared=True)
+        if k_vec is not None:
+            results = run_fits(pool, [dict(base, col_indices=reordering["col_indices"], k_vec=k_vec, rng=rng)], phi, xi,
+                               psi, n_iters, num_repeats, spurious, distance, no_clusts, **fit_kw)[0]
+            if stability:
+                results = stability_check(data, results, k_vec, phi, xi, psi, n_iters, spurious, num_repeats,
+                                          no_clusts, distance, sample_rate, n_stability, stab_thres, rng=rng,
+                                          pool=pool, max_iters=max_iters)
+            return results
+        ks = list(range(int(k_min), int(k_max) + 1))
+        child_rngs = rng.spawn(len(ks))
+        res_list = run_fits(pool, [dict(base, col_indices=reordering["col_indices"], k_vec=[k] * n_v, rng=child_rngs[i])
+                                   for i, k in enumerate(ks)],
+                            phi, xi, psi, n_iters, num_repeats, spurious, distance, no_clusts, **fit_kw)
+        err_list = extract_bisils(res_list, ks)
+        test = ks[int(np.argmax(err_list))]
+        max_k = int(k_max)
+        if k_min != k_max:
+            while test == max_k:
+                max_k += 1
+                ks.append(max_k)
+                # quirk Q3 (R/main.r:312): `reordering$column_indices` does not exist, so the extension fits run
+                # with column_indices = NULL -- nothing is overwritten in the psi coupling.  Reproduced.
+                res_list.append(run_fits(pool, [dict(base, col_indices=None, k_vec=[max_k] * n_v, rng=rng)], phi, xi, psi,
+                                         n_iters, num_repeats, spurious, distance, no_clusts, **fit_kw)[0])
+                err_list.append(res_list[-1]["bisil"])
+                test = ks[int(np.argmax(err_list))]
+        best = int(np.argmax(err_list))
+        results = res_list[best]
+        if stability:
+            results = stability_check(data, results, ks[best], phi, xi, psi, n_iters, spurious, num_repeats,
+                                      no_clusts, distance, sample_rate, n_stability, stab_thres, remove_unstable,
+                                      rng=rng, pool=pool, max_iters=max_iters)
+        return results

@@ -118,7 +118,7 @@ def _pairwise_torch(torch, a, b, method):
     raise ValueError("distance must be one of 'euclidean', 'manhattan' or 'cosine'.")
 
 
-def bisilhouette_device(data, row_clustering, col_clustering, method="euclidean", device=None):
+def bisilhouette_device(data, row_clustering, col_clustering, method="euclidean", device=None, xt=None):
     """``bisilhouette`` with the pairwise-distance work on the GPU: the same definition, the same
     formulas, FP64 throughout; the |R_k| x |R_l| distance blocks are Gram contractions (library GEMM through torch --
     this is post-processing of a finished fit, not the update path).  On the k-sweep of the 20000 x 4000 view the
@@ -128,8 +128,14 @@ def bisilhouette_device(data, row_clustering, col_clustering, method="euclidean"
     torch = _torch_cuda()
     if torch is None:
         return None
-    dev = torch.device("cuda", int(device) if device is not None and device >= 0 else torch.cuda.current_device())
-    x = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.float64))).to(dev)
+    if xt is not None:  # the view is already resident (p x n row-major == column-major n x p): no upload
+        dev = xt.device
+        x = xt.T
+    else:
+        from .api import torch_device
+
+        dev = torch_device(device)
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.float64))).to(dev)
     rc = np.asarray(row_clustering) > 0
     cc = np.asarray(col_clustering) > 0
     k = rc.shape[1]
@@ -220,21 +226,24 @@ def shuffle_view(x_i, rng):
             return m
 
 
-def obtain_shuffled_f(data, n_views, num_repeats, n_clusts, rng, ctx):
-    """R/obtain_bicl.r:31-42: refit on shuffled data through apply_resnmtf (k_val, no_clusts, no stability)."""
-    from .api import apply_resnmtf, shuffled_fits_device
+def shuffle_refit(data, n_clusts, rng, ctx, resident=None, max_iters=0):
+    """One repeat of obtain_shuffled_f (R/obtain_bicl.r:33-40): shuffle every view, refit with k = n_clusts and no
+    restrictions, return the F factors.  ``resident``: the views as device tensors -- then the shuffle, the
+    re-normalisation, the initialisation and the fit never leave the GPU; otherwise the reference's
+    route literally (shuffle on the host, apply_resnmtf with k_val, no_clusts, no stability)."""
+    from .api import _shuffle_refit_device, _torch_cuda, apply_resnmtf
 
-    # matrix-sized views: shuffle, re-normalise, initialise and fit without leaving the device (SURVEY 8f N2); small
-    # ones (and hosts without torch CUDA) take the reference's route literally
-    if min(int(np.prod((m.x if hasattr(m, "x") else m).shape)) for m in data) >= 250_000:
-        f_mess = shuffled_fits_device(data, n_clusts, num_repeats, rng, ctx)
-        if f_mess is not None:
-            return f_mess
-    f_mess = []
-    for _ in range(num_repeats):
-        messed = [shuffle_view(m.x if hasattr(m, "x") else m, rng) for m in data]
-        f_mess.append(apply_resnmtf(messed, k_val=n_clusts, no_clusts=True, stability=False, rng=rng, ctx=ctx)["output_f"])
-    return f_mess
+    if resident is not None:
+        return _shuffle_refit_device(_torch_cuda(), resident, int(n_clusts), rng, ctx, max_iters)
+    messed = [shuffle_view(m.x if hasattr(m, "x") else m, rng) for m in data]
+    return apply_resnmtf(messed, k_val=n_clusts, no_clusts=True, stability=False, rng=rng, ctx=ctx,
+                         use_parallel=False, max_iters=max_iters)["output_f"]
+
+
+def obtain_shuffled_f(data, n_views, num_repeats, n_clusts, rng, ctx, resident=None):
+    """R/obtain_bicl.r:31-42, one repeat after the other.  Every repeat draws from its own child generator of ``rng``;
+    apply_resnmtf's pool runs the same repeats, with the same generators, as independent units on any GPU."""
+    return [shuffle_refit(data, n_clusts, r, ctx, resident) for r in rng.spawn(int(num_repeats))]
 
 
 def calculate_f_shuffle_jsd(f_mess, i, j, num_repeats, n_clusts):
@@ -248,34 +257,76 @@ def calculate_f_shuffle_jsd(f_mess, i, j, num_repeats, n_clusts):
     return scores
 
 
-def get_thresholds(x, output_f, num_repeats, n_views, n_clusts, rng, ctx):
-    """R/obtain_bicl.r:80-102."""
-    f_mess = obtain_shuffled_f(x, n_views, num_repeats, n_clusts, rng, ctx)
-    avg_score, max_score, shuffled_f = [], [], []
+def _jsd_scores_device(f_mess, output_f_i, i, num_repeats, n_clusts, ctx):
+    """All jsd_calc values the spurious-bicluster test needs for view i -- the pairs of calculate_f_shuffle_jsd
+    (R/obtain_bicl.r:55-68, as get_thresholds loops over it, :87-92) and of check_biclusters (:122-129) -- in ONE
+    launch of the library's pair kernel (resnmtf_jsd_pairs).  Column layout of the batch: the fitted
+    factor first, then the shuffled factors repeat by repeat.  Returns (threshold scores in the reference's order,
+    scores[k] = mean JSD of fitted column k against every shuffled column)."""
+    from .device import jsd_pairs
+
+    k = int(n_clusts)
+    cols = np.concatenate([np.asarray(output_f_i, dtype=np.float64)] +
+                          [np.asarray(f_mess[r][i], dtype=np.float64) for r in range(num_repeats)], axis=1)
+    cols = np.asfortranarray(cols)
+    bw = np.array([bw_nrd0(cols[:, c]) for c in range(cols.shape[1])])
+    vmax = cols.max(axis=0)
+    col_of = lambda r, c: k + r * k + c  # noqa: E731 - column of shuffled repeat r, cluster c
+    pa, pb = [], []
+    for j in range(max(num_repeats - 1, 1)):
+        for kk in range(k):
+            for l in range(j + 1, num_repeats):
+                for m in range(k):
+                    pa.append(col_of(j, kk))
+                    pb.append(col_of(l, m))
+    n_thr = len(pa)
+    noise = [col_of(j, c) for j in range(max(num_repeats - 1, 1)) for c in range(k)]
+    noise += [col_of(num_repeats - 1, c) for c in range(k)]
+    for kk in range(k):
+        for c in noise:
+            pa.append(kk)
+            pb.append(c)
+    vals = jsd_pairs(ctx, cols, bw, vmax, pa, pb)
+    return list(vals[:n_thr]), vals[n_thr:].reshape(k, len(noise)).mean(axis=1)
+
+
+def get_thresholds(x, output_f, num_repeats, n_views, n_clusts, rng, ctx, shuffled_f=None, resident=None):
+    """R/obtain_bicl.r:80-102.  ``shuffled_f``: the shuffled refits when the caller already has them."""
+    f_mess = shuffled_f if shuffled_f is not None else obtain_shuffled_f(x, n_views, num_repeats, n_clusts, rng, ctx,
+                                                                         resident)
+    on_device = ctx is not None and resident is not None
+    avg_score, max_score, shuffled, direct = [], [], [], []
     for i in range(n_views):
         scores, cols = [], []
         for j in range(max(num_repeats - 1, 1)):
             cols.append(f_mess[j][i])
-            scores += calculate_f_shuffle_jsd(f_mess, i, j, num_repeats, n_clusts)
+            if not on_device:
+                scores += calculate_f_shuffle_jsd(f_mess, i, j, num_repeats, n_clusts)
         cols.append(f_mess[num_repeats - 1][i])
-        shuffled_f.append(np.concatenate(cols, axis=1))
+        shuffled.append(np.concatenate(cols, axis=1))
+        if on_device:
+            scores, per_cluster = _jsd_scores_device(f_mess, output_f[i], i, num_repeats, n_clusts, ctx)
+            direct.append(per_cluster)
         avg_score.append(float(np.mean(scores)))
         gx, gy = r_density(np.asarray(scores))
         max_score.append(float(gx[int(np.argmax(gy))]))
-    return {"avg_score": avg_score, "max_score": max_score, "shuffled_f": shuffled_f}
+    return {"avg_score": avg_score, "max_score": max_score, "shuffled_f": shuffled,
+            "score": np.stack(direct) if on_device else None}
 
 
-def check_biclusters(data, output_f, num_repeats, rng, ctx):
+def check_biclusters(data, output_f, num_repeats, rng, ctx, shuffled_f=None, resident=None):
     """R/obtain_bicl.r:113-133."""
     n_views = len(data)
     n_clusts = output_f[0].shape[1]
-    scores = np.zeros((n_views, n_clusts))
-    th = get_thresholds(data, output_f, num_repeats, n_views, n_clusts, rng, ctx)
-    for i in range(n_views):
-        noise = th["shuffled_f"][i]
-        for k in range(n_clusts):
-            xk = output_f[i][:, k]
-            scores[i, k] = np.mean([jsd_calc(xk, noise[:, c]) for c in range(noise.shape[1])])
+    th = get_thresholds(data, output_f, num_repeats, n_views, n_clusts, rng, ctx, shuffled_f, resident)
+    scores = th["score"]
+    if scores is None:
+        scores = np.zeros((n_views, n_clusts))
+        for i in range(n_views):
+            noise = th["shuffled_f"][i]
+            for k in range(n_clusts):
+                xk = output_f[i][:, k]
+                scores[i, k] = np.mean([jsd_calc(xk, noise[:, c]) for c in range(noise.shape[1])])
     return {"score": scores, "avg_threshold": th["avg_score"], "max_threshold": th["max_score"]}
 
 
@@ -287,10 +338,13 @@ def binarise(output_f, output_g):
 
 
 def obtain_biclusters(data, output_f, output_g, output_s, num_repeats, remove_spurious=True,
-                      distance="euclidean", rng=None, ctx=None):
-    """R/obtain_bicl.r:151-204."""
+                      distance="euclidean", rng=None, ctx=None, shuffled_f=None, resident=None, want_bisil=True):
+    """R/obtain_bicl.r:151-204.  ``shuffled_f`` / ``resident``: shuffled refits already computed by the caller / the
+    views as device tensors (both None: the reference's serial route).  ``want_bisil=False`` skips the bisilhouette
+    of callers that never read it (the resample fits of the stability analysis use the clusters only)."""
     n_views = len(output_f)
-    biclusts = check_biclusters(data, output_f, num_repeats, rng, ctx) if remove_spurious else None
+    biclusts = (check_biclusters(data, output_f, num_repeats, rng, ctx, shuffled_f, resident)
+                if remove_spurious else None)
     row_clustering, col_clustering = binarise(output_f, output_g)
     bisil = []
     for i in range(n_views):
@@ -301,9 +355,14 @@ def obtain_biclusters(data, output_f, output_g, output_s, num_repeats, remove_sp
             new_indices = indices[relations]
             row_clustering[i][:, new_indices] = 0.0
             col_clustering[i][:, new_indices] = 0.0
-        xi = data[i].x if hasattr(data[i], "x") else data[i]
+        if not want_bisil:
+            bisil.append(0.0)
+            continue
         score = None
-        if int(np.prod(xi.shape)) >= 250_000:  # matrix-sized view: distance blocks on the GPU
+        xi = data[i].x if hasattr(data[i], "x") else data[i]
+        if resident is not None:  # matrix-sized view, already on the GPU: distance blocks there
+            score = bisilhouette_device(None, row_clustering[i], col_clustering[i], method=distance, xt=resident[i])
+        elif int(np.prod(xi.shape)) >= 250_000:
             score = bisilhouette_device(xi, row_clustering[i], col_clustering[i], method=distance,
                                         device=getattr(ctx, "device", None))
         if score is None:

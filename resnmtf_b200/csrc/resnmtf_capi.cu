@@ -14,6 +14,7 @@
 #include "../../include/resnmtf_b200.h"
 #include "rn_kernels.cuh"
 #include "rn_fused.cuh"
+#include "rn_post.cuh"
 
 #include <dlfcn.h>
 
@@ -784,8 +785,8 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
 }
 
 // ---- shared device data -------------------------------------------------------------------------
-extern "C" int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
-                                   resnmtf_data** out) {
+static int data_create_common(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld, bool on_device,
+                              resnmtf_data** out) {
   RN_CHECK(ctx && x && out, RESNMTF_E_INVALID, "resnmtf_data_create: NULL argument");
   RN_CHECK(n >= 1 && p >= 1 && ld >= n, RESNMTF_E_INVALID, "resnmtf_data_create: bad shape");
   RN_CUDA(cudaSetDevice(ctx->device));
@@ -816,7 +817,7 @@ extern "C" int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const
     g.row_tiles = (int)(d->ldx / RN_ROW_TILE);
     g.X = d->X;
     g.scal = scratch;
-    rc = upload_panels(ctx, g, x, ld, false, scratch + 8, reinterpret_cast<int32_t*>(scratch + 8 + 1024),
+    rc = upload_panels(ctx, g, x, ld, on_device, scratch + 8, reinterpret_cast<int32_t*>(scratch + 8 + 1024),
                        "resnmtf_data_create");
     if (rc == RESNMTF_OK && cudaMemcpy(&d->xnorm2, scratch, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = rn_fail(RESNMTF_E_CUDA, "resnmtf_data_create: reading back ||X||^2 failed");
@@ -828,6 +829,15 @@ extern "C" int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const
   }
   *out = d;
   return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
+                                   resnmtf_data** out) {
+  return data_create_common(ctx, n, p, x, ld, false, out);
+}
+extern "C" int resnmtf_data_create_device(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x_dev, int64_t ld,
+                                          resnmtf_data** out) {
+  return data_create_common(ctx, n, p, x_dev, ld, true, out);
 }
 
 extern "C" int resnmtf_data_destroy(resnmtf_data* data) {
@@ -1621,6 +1631,52 @@ extern "C" int resnmtf_fit_get_counters(resnmtf_fit* fit, resnmtf_counters* out)
 // ------------------------------------------------------------------------------------------------
 // row-sharded path (NCCL) -- see DESIGN.md "Multi-GPU"
 // ------------------------------------------------------------------------------------------------
+// ---- post-fit reductions -----------------------------------------------------------
+extern "C" int resnmtf_jsd_pairs(resnmtf_ctx* ctx, const double* vecs, int64_t n, int32_t m, int64_t ld,
+                                 const double* bw, const double* vmax, const int32_t* pair_a,
+                                 const int32_t* pair_b, int64_t n_pairs, double* out) {
+  RN_CHECK(ctx && vecs && bw && vmax && out, RESNMTF_E_INVALID, "resnmtf_jsd_pairs: NULL argument");
+  RN_CHECK(n >= 1 && m >= 1 && ld >= n && n_pairs >= 0, RESNMTF_E_INVALID, "resnmtf_jsd_pairs: bad shape");
+  if (n_pairs == 0) return RESNMTF_OK;
+  RN_CHECK(pair_a && pair_b, RESNMTF_E_INVALID, "resnmtf_jsd_pairs: NULL pair list");
+  for (int64_t i = 0; i < n_pairs; ++i)
+    RN_CHECK(pair_a[i] >= 0 && pair_a[i] < m && pair_b[i] >= 0 && pair_b[i] < m, RESNMTF_E_INVALID,
+             "resnmtf_jsd_pairs: column index out of range");
+  RN_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  double *d_vecs = nullptr, *d_par = nullptr, *d_out = nullptr;
+  int32_t* d_pairs = nullptr;
+  cudaError_t e = rn_dev_alloc(ctx, (void**)&d_vecs, (size_t)n * m * sizeof(double));
+  if (e == cudaSuccess) e = rn_dev_alloc(ctx, (void**)&d_par, (size_t)2 * m * sizeof(double));
+  if (e == cudaSuccess) e = rn_dev_alloc(ctx, (void**)&d_pairs, (size_t)2 * n_pairs * sizeof(int32_t));
+  if (e == cudaSuccess) e = rn_dev_alloc(ctx, (void**)&d_out, (size_t)n_pairs * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(d_vecs, (size_t)n * sizeof(double), vecs, (size_t)ld * sizeof(double),
+                          (size_t)n * sizeof(double), (size_t)m, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, bw, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + m, vmax, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_pairs, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_pairs + n_pairs, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    const int64_t grid = std::min<int64_t>(n_pairs, (int64_t)ctx->sm_count * 8);
+    rn_jsd_pairs<<<(unsigned)grid, RN_KDE_N, 0, st>>>(d_vecs, n, n, d_par, d_par + m, d_pairs, d_pairs + n_pairs,
+                                                       n_pairs, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n_pairs * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  rn_dev_free(ctx, d_vecs);
+  rn_dev_free(ctx, d_par);
+  rn_dev_free(ctx, d_pairs);
+  rn_dev_free(ctx, d_out);
+  if (e != cudaSuccess)
+    return rn_fail(e == cudaErrorMemoryAllocation ? RESNMTF_E_NOMEM : RESNMTF_E_CUDA,
+                   std::string("resnmtf_jsd_pairs: ") + cudaGetErrorString(e));
+  return RESNMTF_OK;
+}
+
 extern "C" int resnmtf_comm_id_size(void) { return (int)sizeof(rn_ncclUniqueId); }
 
 extern "C" int resnmtf_comm_id_create(void* id_out) {

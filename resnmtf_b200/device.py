@@ -3,6 +3,7 @@ device-resident X, F, S, G, lambda, mu of all views of one ``res_nmtf_inner`` ca
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -85,6 +86,9 @@ def device_contexts(first):
     """One context per visible GPU, ``first`` (and its device) leading: the placement targets of the
     independent fits of an apply_resnmtf call."""
     n = L.device_count()
+    cap = int(os.environ.get("RESNMTF_MAX_GPUS", "0") or 0)  # 0: all visible GPUs
+    if cap > 0:
+        n = min(n, max(cap, first.device + 1))
     out = [first]
     for dev in range(n):
         if dev == first.device:
@@ -92,6 +96,23 @@ def device_contexts(first):
         if dev not in _device_ctx:
             _device_ctx[dev] = Context(dev)
         out.append(_device_ctx[dev])
+    return out[:cap] if cap > 0 else out
+
+
+def jsd_pairs(ctx, vecs, bw, vmax, pair_a, pair_b):
+    """jsd_calc (R/utils.r:95-106) of the column pairs (pair_a[i], pair_b[i]) of the n x m matrix ``vecs`` on the
+    GPU (``resnmtf_jsd_pairs``); ``bw`` / ``vmax``: bw.nrd0 and maximum of every column."""
+    lib = L.require_device()
+    vecs = _f64(vecs)
+    bw = np.ascontiguousarray(bw, dtype=np.float64)
+    vmax = np.ascontiguousarray(vmax, dtype=np.float64)
+    pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+    if pa.shape != pb.shape or bw.size != vecs.shape[1] or vmax.size != vecs.shape[1]:
+        raise ValueError("jsd_pairs: inconsistent arguments")
+    out = np.empty(pa.size, dtype=np.float64)
+    L.check(lib.resnmtf_jsd_pairs(ctx._h, _ptr(vecs), vecs.shape[0], vecs.shape[1], vecs.shape[0], _ptr(bw),
+                                  _ptr(vmax), _ptr(pa), _ptr(pb), pa.size, _ptr(out)))
     return out
 
 
@@ -107,6 +128,19 @@ class DeviceData:
         h = C.c_void_p()
         L.check(self._lib.resnmtf_data_create(ctx._h, x.shape[0], x.shape[1], _ptr(x), x.shape[0], C.byref(h)))
         self._h = h
+
+    @classmethod
+    def from_device(cls, ctx, dev_ptr, n, p, ld=None):
+        """The n x p column-major float64 matrix at DEVICE address ``dev_ptr`` on the context's GPU."""
+        self = cls.__new__(cls)
+        self._lib = L.require_device()
+        self.ctx = ctx
+        self.shape = (int(n), int(p))
+        h = C.c_void_p()
+        L.check(self._lib.resnmtf_data_create_device(ctx._h, int(n), int(p), C.c_void_p(int(dev_ptr)),
+                                                     int(n if ld is None else ld), C.byref(h)))
+        self._h = h
+        return self
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -1,0 +1,126 @@
+"""Host logic of the multi-GPU placement of apply_resnmtf (independent fits): the unit decomposition, the
+pool, the stability analysis over the pool and the resident-data route, run on CPU stand-ins for the device objects
+(tests/fake_device.py: the oracle's loop behind DeviceFit's interface).  What must hold: the result of a call does
+not depend on the number of GPUs, and the reference's own assertions (test-resnmtf.R:63-135) still hold."""
+import threading
+
+import numpy as np
+import pytest
+
+import fake_device
+from resnmtf_b200 import synth
+from resnmtf_b200.api import apply_resnmtf, res_nmtf_inner
+from resnmtf_b200.fitpool import FitPool
+
+
+def _same(a, b, keys=("output_f", "output_s", "output_g", "row_clusters", "col_clusters")):
+    for key in keys:
+        for x, y in zip(a[key], b[key]):
+            assert np.array_equal(x, y), key
+
+
+def test_pool_runs_every_unit_once_longest_first_and_keeps_task_order():
+    pool = FitPool([fake_device.FakeContext(d) for d in range(3)])
+    seen, lock = [], threading.Lock()
+
+    def unit(i):
+        def run(worker):
+            with lock:
+                seen.append((i, worker.index))
+            return i * i
+
+        return run
+
+    costs = [1.0, 5.0, 3.0, 5.0, 0.5, 2.0, 4.0]
+    out = pool.run([(c, unit(i)) for i, c in enumerate(costs)])
+    assert out == [i * i for i in range(len(costs))]
+    assert sorted(i for i, _ in seen) == list(range(len(costs)))
+    one = FitPool([fake_device.FakeContext(0)])
+    order = []
+    one.run([(c, (lambda w, i=i: order.append(i))) for i, c in enumerate(costs)])
+    assert order == [1, 3, 6, 2, 5, 0, 4]  # longest first, ties in task order
+
+
+def test_pool_reraises_a_unit_failure():
+    pool = FitPool([fake_device.FakeContext(d) for d in range(2)])
+
+    def bad(worker):
+        raise ValueError("unit failed")
+
+    with pytest.raises(ValueError, match="unit failed"):
+        pool.run([(1.0, lambda w: 1), (2.0, bad), (1.0, lambda w: 2)])
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_k_sweep_with_spurious_removal_is_independent_of_the_gpu_count(monkeypatch, resident):
+    """k sweep + shuffled refits (test-resnmtf.R:123-135 with the spurious-bicluster test switched on): 1 vs 3 GPUs.
+    ``resident``: 420 x 600 views (>= 250k entries) take the resident-data route -- initialisation from the resident
+    tensor, device shuffles, one JSD batch per view -- with CPU tensors standing in."""
+    block = 200 if resident else 60
+    views, _ = synth.block_views(1, block=block, n_blocks=3, seed=5)
+    if resident:
+        views = [np.asfortranarray(views[0][:420, :])]
+    kw = dict(k_min=3, k_max=4, spurious=True, stability=False, num_repeats=2, max_iters=60)
+    outs = []
+    for n_dev in (1, 3):
+        with monkeypatch.context() as mp:
+            ctxs = fake_device.install(mp, n_dev, resident=resident)
+            outs.append(apply_resnmtf(views, rng=np.random.default_rng(3), **kw))
+            assert sum(c.fits for c in ctxs) == 2 * (1 + 2)  # 2 k values x (fit + 2 shuffled refits)
+            if n_dev == 3:
+                assert all(c.fits > 0 for c in ctxs)
+    _same(outs[0], outs[1])
+    assert outs[0]["bisil"] == outs[1]["bisil"]
+    assert outs[0]["output_f"][0].shape[1] == 3  # the sweep selects the planted k
+    n_rows = views[0].shape[0]
+    sizes = sorted(outs[0]["row_clusters"][0].sum(axis=0).tolist())
+    assert sizes == sorted([float(n_rows - 2 * block), float(block), float(block)])
+    assert sorted(outs[0]["col_clusters"][0].sum(axis=0).tolist()) == [float(block)] * 3
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_stability_analysis_is_independent_of_the_gpu_count(monkeypatch, resident):
+    """Fixed k with spurious removal and stability (test-resnmtf.R:63-118): the resample fits and their shuffled
+    refits are units like any other; 1 vs 2 GPUs give the same surviving biclusters."""
+    block = 180 if resident else 60
+    views, _ = synth.block_views(2, block=block, n_blocks=3, seed=7)
+    kw = dict(k_val=3, spurious=True, stability=True, n_stability=2, num_repeats=2, max_iters=50)
+    outs = []
+    for n_dev in (1, 2):
+        with monkeypatch.context() as mp:
+            ctxs = fake_device.install(mp, n_dev, resident=resident)
+            outs.append(apply_resnmtf(views, rng=np.random.default_rng(11), **kw))
+            assert sum(c.fits for c in ctxs) == (1 + 2) + 2 * (1 + 2)
+    _same(outs[0], outs[1])
+    for v in range(2):
+        assert sorted(outs[0]["row_clusters"][v].sum(axis=0).tolist()) == [float(block)] * 3
+        assert sorted(outs[0]["col_clusters"][v].sum(axis=0).tolist()) == [float(block)] * 3
+
+
+def test_res_nmtf_inner_serial_route_equals_the_pool_route(monkeypatch):
+    """res_nmtf_inner on its own (the reference's serial order: fit, then the shuffled refits inside
+    obtain_biclusters) returns what the same fit returns as units of a 2-GPU pool."""
+    views, _ = synth.block_views(1, block=60, n_blocks=3, seed=9)
+    data = [synth.prep(views[0])]
+    from resnmtf_b200 import prep
+
+    named = prep.give_names(data, 1)
+    idx = prep.reorder_data(named["data"], 1, named["row_names"], named["col_names"])
+    outs = []
+    for n_dev in (1, 2):
+        with monkeypatch.context() as mp:
+            fake_device.install(mp, n_dev)
+            if n_dev == 1:
+                outs.append(res_nmtf_inner(named["data"], idx["row_indices"], idx["col_indices"], k_vec=[3],
+                                           num_repeats=2, rng=np.random.default_rng(21), max_iters=60))
+            else:
+                from resnmtf_b200 import api
+
+                with FitPool(api.device_contexts(None)) as pool:
+                    pool.place_host("data", named["data"])
+                    spec = dict(key="data", data=named["data"], row_indices=idx["row_indices"],
+                                col_indices=idx["col_indices"], k_vec=[3], rng=np.random.default_rng(21))
+                    outs.append(api.run_fits(pool, [spec], None, None, None, None, 2, True, "euclidean", False,
+                                             max_iters=60)[0])
+    _same(outs[0], outs[1])
+    assert outs[0]["bisil"] == outs[1]["bisil"]
