@@ -337,18 +337,18 @@ def run_fits(pool, specs, phi, xi, psi, n_iters, num_repeats, spurious, distance
     """Runs the res_nmtf_inner calls described by ``specs`` on the pool and returns their result lists in order.
 
     A spec: dict(key=<data key placed on the pool>, data=[views], row_indices, col_indices, k_vec, rng, and optionally
-    init_f / init_s / init_g, shared=<the data is fitted by several specs>, want_bisil).  Phase A: the cores and -- when
-    spurious biclusters are to be removed -- the ``num_repeats`` shuffled refits of every spec, all independent units
-    (R/obtain_bicl.r:31-42 runs them inside the fit; they depend on k and on the data only).  Phase B: the
-    post-processing of every spec (JSD thresholds, binarisation, bisilhouette)."""
+    init_f / init_s / init_g, shared=<the data is fitted by several specs>, want_bisil).  Units: the core of every spec
+    and -- when spurious biclusters are to be removed -- its ``num_repeats`` shuffled refits, all independent
+    (R/obtain_bicl.r:31-42 runs them inside the fit; they depend on k and on the data only); then, per spec, the
+    post-processing (JSD thresholds, binarisation, bisilhouette), which waits for exactly those."""
     need_shuffles = bool(spurious) and not no_clusts
-    tasks, slots = [], []
+    tasks, core_at, post_at = [], [], []
     for si, sp in enumerate(specs):
         data, key = sp["data"], sp["key"]
         on_dev = key in pool.loaders
         k_vec = [int(k) for k in sp["k_vec"]]
         cost = sharding.fit_cost([m.shape for m in data], max(k_vec))
-        sp["_shuffle_rngs"] = sp["rng"].spawn(int(num_repeats)) if need_shuffles else []
+        shuffle_rngs = sp["rng"].spawn(int(num_repeats)) if need_shuffles else []
 
         def core(worker, sp=sp, data=data, key=key, on_dev=on_dev, k_vec=k_vec):
             shared = sp.get("shared", False)
@@ -359,40 +359,33 @@ def run_fits(pool, specs, phi, xi, psi, n_iters, num_repeats, spurious, distance
                              resident=worker.get_views(key) if on_dev else None,
                              eig_cache=worker.eig_cache(key) if (shared and on_dev) else None)
 
-        tasks.append((cost * 1.01, core))
-        slots.append((si, None))
-        for r, srng in enumerate(sp["_shuffle_rngs"]):
+        core_at.append(len(tasks))
+        tasks.append((cost * 1.01, core, (), "fit"))
+        shuffle_at = []
+        for srng in shuffle_rngs:
             def shuffle(worker, data=data, key=key, on_dev=on_dev, srng=srng,
                         k=k_vec[0] if sp.get("init_f") is None else int(np.asarray(sp["init_f"][0]).shape[1])):
                 from .bicluster import shuffle_refit
 
-                return shuffle_refit(data, k, srng, worker.ctx, resident=worker.get_views(key) if on_dev else None)
+                return shuffle_refit(data, k, srng, worker.ctx, resident=worker.get_views(key) if on_dev else None,
+                                     max_iters=max_iters)
 
-            tasks.append((cost, shuffle))
-            slots.append((si, r))
-    done = pool.run(tasks)
-    cores = [None] * len(specs)
-    f_mess = [[None] * len(sp["_shuffle_rngs"]) for sp in specs]
-    for (si, r), res in zip(slots, done):
-        if r is None:
-            cores[si] = res
-        else:
-            f_mess[si][r] = res
-    if no_clusts:
-        return [_fit_post(cores[si], sp["data"], n_iters, num_repeats, spurious, distance, True, rng=sp["rng"], ctx=None)
-                for si, sp in enumerate(specs)]
+            shuffle_at.append(len(tasks))
+            tasks.append((cost, shuffle, (), "shuffled refit"))
 
-    posts = []
-    for si, sp in enumerate(specs):
-        def post(worker, si=si, sp=sp):
-            on_dev = sp["key"] in pool.loaders
-            return _fit_post(cores[si], sp["data"], n_iters, num_repeats, spurious, distance, False, rng=sp["rng"],
-                             ctx=worker.ctx, shuffled_f=f_mess[si] if need_shuffles else None,
-                             resident=worker.get_views(sp["key"]) if on_dev else None,
+        def post(worker, sp=sp, on_dev=on_dev, ci=core_at[-1], shuffle_at=tuple(shuffle_at)):
+            return _fit_post(worker.results[ci], sp["data"], n_iters, num_repeats, spurious, distance, no_clusts,
+                             rng=sp["rng"], ctx=worker.ctx,
+                             shuffled_f=[worker.results[i] for i in shuffle_at] if need_shuffles else None,
+                             resident=worker.get_views(sp["key"]) if (on_dev and not no_clusts) else None,
                              want_bisil=sp.get("want_bisil", True))
 
-        posts.append((max(int(k) for k in sp["k_vec"]) ** 2, post))
-    return pool.run(posts)
+        # the post-processing of a fit is ready as soon as its core and its shuffled refits are; it is cheap next to
+        # them but sits on the critical path of the call, so a free GPU takes it before starting another fit
+        post_at.append(len(tasks))
+        tasks.append((cost * 2.0, post, (core_at[-1],) + tuple(shuffle_at), "post-processing"))
+    done = pool.run(tasks)
+    return [done[i] for i in post_at]
 
 
 def _single_pool(ctx):
@@ -467,9 +460,10 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
     phi = prep.init_rest_mats(phi, n_v)
     psi = prep.init_rest_mats(psi, n_v)
     xi = prep.init_rest_mats(xi, n_v)
+    on_device = device_route(named["data"])  # matrix-sized views are prepped on the GPU on the way in
     data = prep.check_inputs(named["data"], init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_min, k_max,
                              distance, num_repeats, no_clusts, sample_rate, n_stability, stability, stab_thres,
-                             remove_unstable, spurious)
+                             remove_unstable, spurious, prep_values=not on_device)
     if k_vec is None and no_clusts:
         # the reference fails here too: results carry no bisil, which.max(NULL) is integer(0) and the
         # `while (test == max_k)` at R/main.r:307 stops with "argument is of length zero"
@@ -480,7 +474,13 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
     contexts = device_contexts(ctx) if use_parallel else [ctx]
     fit_kw = dict(max_iters=max_iters)
     with FitPool(contexts) as pool:
-        _place(pool, "data", data)
+        if on_device:
+            from .fitpool import ResidentMatrix
+
+            pool.place_resident("data", data, prep=True)
+            data = [ResidentMatrix(m.shape, m.rownames, m.colnames) for m in data]  # the values live on the GPUs only
+        else:
+            pool.place_host("data", data)
         base = dict(key="data", data=data, row_indices=reordering["row_indices"], init_f=init_f, init_s=init_s,
                     init_g=init_g, shared=True)
         if k_vec is not None:

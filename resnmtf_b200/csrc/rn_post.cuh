@@ -133,8 +133,10 @@ rn_jsd_pairs(const double* __restrict__ vecs, int64_t n, int64_t ld, const doubl
     const double s2 = rn_kde_block_sum(d2, sm.red);
     const double p = d1 / s1, q = d2 / s2;
     const double m = 0.5 * (p + q);
-    const double ta = p > 0.0 ? p * log2(p / m) : 0.0;
-    const double tb = q > 0.0 ? q * log2(q / m) : 0.0;
+    // m > 0: the direct sums keep the true far tail of a gaussian (down to denormals, where (p + q) / 2 can round to
+    // zero under a non-zero p); the reference's fft() floors the tails at its rounding noise and never gets there
+    const double ta = (p > 0.0 && m > 0.0) ? p * log2(p / m) : 0.0;
+    const double tb = (q > 0.0 && m > 0.0) ? q * log2(q / m) : 0.0;
     const double ja = rn_kde_block_sum(ta, sm.red);
     const double jb = rn_kde_block_sum(tb, sm.red);
     if (threadIdx.x == 0) out[pr] = 0.5 * ja + 0.5 * jb;

@@ -97,8 +97,12 @@ class FitPool:
     def place_host(self, key, data):
         self.host_data[key] = data
 
-    def place_resident(self, key, data):
-        """Uploads the host views once (to the first GPU) and copies them from there to the other GPUs."""
+    def place_resident(self, key, data, prep=False):
+        """Uploads the host views once (to the first GPU) and copies them from there to the other GPUs.  ``prep``: the
+        views are raw; make_non_neg_inner and matrix_normalisation (R/utils.r:20-27, 86-88) run on the first GPU
+        before the copies (same warning as the host version)."""
+        import warnings
+
         import torch
 
         from .api import torch_device
@@ -106,7 +110,16 @@ class FitPool:
         self.host_data[key] = data
         w0 = self.workers[0]
         dev0 = torch_device(w0.ctx.device)
-        first = [torch.from_numpy(np.ascontiguousarray(m.x.T)).to(dev0) for m in data]
+        first = []
+        for m in data:
+            xt = torch.from_numpy(np.ascontiguousarray(np.asarray(m.x, dtype=np.float64).T)).to(dev0)  # p x n
+            if prep:
+                col_min = xt.min(dim=1, keepdim=True).values
+                if bool((col_min < 0).any()):
+                    warnings.warn("Matrix is not non-negative. Has been made non-negative.")
+                xt = xt + torch.abs(torch.clamp(col_min, max=0.0))
+                xt = xt / xt.sum(dim=1, keepdim=True)
+            first.append(xt)
         w0.views[key] = first
         for w in self.workers[1:]:
             w.views[key] = [t.to(torch_device(w.ctx.device)) for t in first]
@@ -131,72 +144,99 @@ class FitPool:
 
     # ---- work ---------------------------------------------------------------------------------------
     def run(self, tasks):
-        """``tasks``: [(cost, callable(worker) -> result)].  Returns the results in task order.  Units are started
-        longest first; with one GPU they simply run one after the other on the calling thread."""
+        """``tasks``: [(cost, callable(worker) -> result)] or [(cost, callable, deps, label)] where ``deps`` lists the
+        indices of the tasks whose results must exist first (a task with deps reads them from the list this method
+        returns -- it is handed over as ``worker.results`` -- e.g. the post-processing of a fit waits for its core
+        and its shuffled refits).  Returns the results in task order.  A free GPU takes the ready task with the
+        largest cost; with one GPU the tasks simply run one after the other on the calling thread."""
+        tasks = [(t[0], t[1], tuple(t[2]) if len(t) > 2 else (), t[3] if len(t) > 3 else "unit") for t in tasks]
         order = sorted(range(len(tasks)), key=lambda i: (-float(tasks[i][0]), i))
         results = [None] * len(tasks)
-        if self.trace is not None:
-            tasks = [(c, self._timed(fn)) for c, fn in tasks]
-            t_phase = time.perf_counter()
-            try:
-                return self._run(tasks, order, results)
-            finally:
-                self.trace.append(("phase", len(tasks), time.perf_counter() - t_phase))
-        return self._run(tasks, order, results)
+        finished = [False] * len(tasks)
+        t_phase = time.perf_counter()
 
-    def _timed(self, fn):
-        def run(worker):
+        def execute(i, worker):
+            worker.results = results
             t0 = time.perf_counter()
             try:
-                return fn(worker)
+                results[i] = tasks[i][1](worker)
             finally:
-                self.trace.append(("unit", worker.index, time.perf_counter() - t0))
+                if self.trace is not None:
+                    self.trace.append(("unit", worker.index, time.perf_counter() - t0, tasks[i][3]))
 
-        return run
+        def next_ready(pending):
+            for pos, i in enumerate(pending):
+                if all(finished[d] for d in tasks[i][2]):
+                    return pending.pop(pos)
+            return None
 
-    def _run(self, tasks, order, results):
+        pending = list(order)
         n_threads = min(len(self.workers), len(tasks))
-        if n_threads <= 1:
-            for i in order:
-                results[i] = tasks[i][1](self.workers[0])
-            return results
-        lock = threading.Lock()
-        cursor = [0]
-        errors = []
+        try:
+            if n_threads <= 1:
+                while pending:
+                    i = next_ready(pending)
+                    if i is None:
+                        raise RuntimeError("FitPool.run: circular task dependencies")
+                    execute(i, self.workers[0])
+                    finished[i] = True
+                return results
+            cond = threading.Condition()
+            errors = []
+            running = [0]
 
-        def loop(worker):
-            while True:
-                with lock:
-                    if errors or cursor[0] >= len(order):
+            def loop(worker):
+                while True:
+                    with cond:
+                        while True:
+                            if errors or not pending:
+                                return
+                            i = next_ready(pending)
+                            if i is not None:
+                                running[0] += 1
+                                break
+                            if running[0] == 0:
+                                errors.append(RuntimeError("FitPool.run: circular task dependencies"))
+                                cond.notify_all()
+                                return
+                            cond.wait()
+                    try:
+                        execute(i, worker)
+                    except BaseException as exc:  # noqa: BLE001 - re-raised on the calling thread
+                        with cond:
+                            errors.append(exc)
+                            running[0] -= 1
+                            cond.notify_all()
                         return
-                    i = order[cursor[0]]
-                    cursor[0] += 1
-                try:
-                    results[i] = tasks[i][1](worker)
-                except BaseException as exc:  # noqa: BLE001 - re-raised on the calling thread
-                    with lock:
-                        errors.append(exc)
-                    return
+                    with cond:
+                        finished[i] = True
+                        running[0] -= 1
+                        cond.notify_all()
 
-        threads = [threading.Thread(target=loop, args=(w,), daemon=True) for w in self.workers[:n_threads]]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        return results
+            threads = [threading.Thread(target=loop, args=(w,), daemon=True) for w in self.workers[:n_threads]]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+            return results
+        finally:
+            if self.trace is not None:
+                self.trace.append(("phase", len(tasks), time.perf_counter() - t_phase, ""))
 
     def report(self):
-        """Per phase: wall time, number of units, busy time per GPU (RESNMTF_TRACE)."""
-        lines, busy = [], {}
-        for kind, a, b in self.trace or []:
+        """Per phase: wall time, number of units, busy time per GPU, mean unit time per kind (RESNMTF_TRACE)."""
+        lines, busy, kinds = [], {}, {}
+        for kind, a, b, label in self.trace or []:
             if kind == "unit":
                 busy[a] = busy.get(a, 0.0) + b
+                kinds.setdefault(label, []).append(b)
             else:
                 per = " ".join(f"gpu{w}={busy.get(w, 0.0):.2f}" for w in sorted(busy))
-                lines.append(f"  phase: {a:3d} units, {b:6.2f} s wall, busy {per}")
-                busy = {}
+                mean = " ".join(f"{lb}:{len(v)}x{sum(v) / len(v):.3f}s" for lb, v in sorted(kinds.items()))
+                lines.append(f"  phase: {a:3d} units, {b:6.2f} s wall, busy {per} | {mean}")
+                busy, kinds = {}, {}
         return "\n".join(lines)
 
     def close(self):

@@ -163,9 +163,11 @@ def check_restriction_mat(data, matrix, name):
 
 def check_inputs(data, init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_min, k_max, distance,
                  num_repeats, no_clusts, sample_rate, n_stability, stability, stab_thres, remove_unstable,
-                 spurious):
+                 spurious, prep_values=True):
     """R/utils.r:391-454.  ``data`` is a list of NamedMatrix; returns the prepped list (non-negative, L1
-    column-normalised float64, names kept)."""
+    column-normalised float64, names kept).  ``prep_values=False`` leaves the two matrix-sized passes (the shift to
+    non-negative values and the normalisation) to the caller, who runs them on the GPU on the way in
+    (``FitPool.place_resident``); everything else -- checks, error strings -- is unchanged."""
     data = check_lists(data, init_f, init_s, init_g)
     check_integers(n_iters, k_min, k_max, num_repeats, n_stability)
     check_boolean(no_clusts, stability, remove_unstable, spurious)
@@ -175,8 +177,11 @@ def check_inputs(data, init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_m
         warnings.warn("Data is not a double matrix. Converting to double.")
     out = []
     for m in named:
-        x = matrix_normalisation(make_non_neg_inner(m.x))
-        out.append(NamedMatrix(np.asfortranarray(x), m.rownames, m.colnames))
+        if prep_values:
+            x = np.asfortranarray(matrix_normalisation(make_non_neg_inner(m.x)))
+        else:
+            x = np.asarray(m.x, dtype=np.float64)
+        out.append(NamedMatrix(x, m.rownames, m.colnames))
     ranks = [m.shape[1] for m in out]
     if distance not in ("euclidean", "manhattan", "cosine"):
         raise ValueError("distance must be one of 'euclidean', 'manhattan' or 'cosine'.")

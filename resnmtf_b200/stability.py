@@ -177,7 +177,7 @@ def stability_check(data, results, k, phi, xi, psi, n_iters, spurious, num_repea
             sums = resident_sums(worker.get_views("data")) if on_dev else host_sums(data)
             return draw_subsample(sums, shapes, dim_1, n_views, sample_rate, child_rngs[i])
 
-        samples = pool.run([(1.0, lambda w, i=i: draw(w, i)) for i in range(n_rep)])
+        samples = pool.run([(1.0, lambda w, i=i: draw(w, i), (), "sub-sample") for i in range(n_rep)])
         if any(smp is None for smp in samples):
             return results
         specs = []
