@@ -281,13 +281,22 @@ static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, c
   cfg.blockDim = dim3(RN_FU_THREADS);
   cfg.dynamicSmemBytes = rn_fused_smem();
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)vh.d.fu_csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // Programmatic dependent launch (RESNMTF_NO_PDL=1 switches it off): this launch may be placed on the SMs while the
+  // previous kernel of the stream drains; the kernel waits (griddepcontrol.wait) before it reads anything a kernel
+  // wrote.  Captured into the iteration graph as a programmatic edge.
+  static const bool pdl = rn_env_int("RESNMTF_NO_PDL", 0) == 0;
+  if (pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaLaunchKernelEx(&cfg, fused_step_fn(vh.d.k), vh.d, ft, v, fuse);
 }
 
@@ -1300,7 +1309,12 @@ static int prepare(resnmtf_fit* fit) {
   int rc;
   if (fit->plan_dirty && (rc = build_plan(fit))) return rc;
   if (fit->meta_dirty && (rc = sync_meta(fit))) return rc;
-  if (!fit->graph_exec && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
+  // A fit whose every view runs the one-pass kernel launches straight into the stream: consecutive launches then
+  // chain through programmatic dependent launch (launch_fused), which a chain of single-iteration graph launches
+  // cannot do; one kernel per view and iteration leaves nothing for a graph to save.
+  bool chained = rn_env_int("RESNMTF_NO_PDL", 0) == 0 && fit->d.err_mode != RESNMTF_ERR_DIRECT;
+  for (int v = 0; v < fit->V; ++v) chained = chained && fit->views[v].d.fu_csize > 0;
+  if (!fit->graph_exec && !chained && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
     cudaStream_t st = fit->ctx->stream;
     RN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     fit->launches_per_iter = enqueue_iteration(fit, st, nullptr, nullptr);

@@ -178,7 +178,10 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   const int ctid = ci * 32 + lane;    // consumer thread index
   constexpr int nb = NB;              // column blocks of this consumer (uniform; the loops below allow nb < NB)
   const int boff = NB * ci;
-  if (ft.ctrl->done) return;          // uniform over the grid
+  // Programmatic dependent launch: the next launch of the stream (the next view / update-iteration) may be placed on
+  // the SMs as this grid drains -- all but the finishing CTA leave ~6 us before the grid completes -- and set itself
+  // up (barriers, first row groups of X in flight) while it waits for this grid's results (rn_griddep_wait below).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) rn_fu_stamp(vw, 0);
 
   extern __shared__ __align__(128) unsigned char rn_smem[];
@@ -234,6 +237,38 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     }
     rn_mbar_init_fence();
   }
+  __syncthreads();
+
+  // bulk copies of local row group i into its ring slots, one per consumer warp, each as soon as that warp has
+  // released the slot (executed by the whole producer warp)
+  auto produce = [&](int i) {
+    const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
+    const int gs = i % 3;
+    const uint32_t ph = (uint32_t)((i / 3) & 1);
+#pragma unroll 1
+    for (int w = 0; w < NCW; ++w) {
+      const int wnb = NB;
+      const int wboff = NB * w;
+      const int st = gs * NCW + w;
+      rn_mbar_wait(&empty[st], ph ^ 1u);
+      if (lane == 0) {
+        rn_mbar_expect_tx(&full[st], (uint32_t)wnb * 1024u);
+        rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + wboff * 1024, src + wboff * 128, (uint32_t)wnb * 1024u, &full[st]);
+      }
+      __syncwarp();
+    }
+  };
+  // X is never written by a kernel: the ring is filled before the previous launch has finished
+  const int npre = NGL < 3 ? NGL : 3;
+  if (warp == 3)
+    for (int i = 0; i < npre; ++i) produce(i);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the previous launch wrote
+  if (ft.ctrl->done) {  // uniform over the grid; the copies in flight must land before the CTA may exit
+    if (warp == 3)
+      for (int i = 0; i < npre; ++i)
+        for (int w = 0; w < NCW; ++w) rn_mbar_wait(&full[i * NCW + w], 0u);
+    return;
+  }
   if (tid < 64) {
     Ssm[tid] = (tid < KK) ? vw.S[tid] : 0.0;
     Wsm[tid] = 0.0;
@@ -266,28 +301,9 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   for (int s = 0; s < 2 * NB; ++s) tacc[s][0] = tacc[s][1] = 0.0;
   const int64_t colbase = (int64_t)rank * RN_FU_CCOLS + 16 * boff;
 
-  // bulk copies of local row group i into its ring slots, one per consumer warp, each as soon as that warp has
-  // released the slot (executed by the whole producer warp)
-  auto produce = [&](int i) {
-    const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
-    const int gs = i % 3;
-    const uint32_t ph = (uint32_t)((i / 3) & 1);
-#pragma unroll 1
-    for (int w = 0; w < NCW; ++w) {
-      const int wnb = NB;
-      const int wboff = NB * w;
-      const int st = gs * NCW + w;
-      rn_mbar_wait(&empty[st], ph ^ 1u);
-      if (lane == 0) {
-        rn_mbar_expect_tx(&full[st], (uint32_t)wnb * 1024u);
-        rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + wboff * 1024, src + wboff * 128, (uint32_t)wnb * 1024u, &full[st]);
-      }
-      __syncwarp();
-    }
-  };
   if (warp == 3) {
     // ---- producer warp -------------------------------------------------------------------------------
-    for (int i = 0; i < NGL; ++i) produce(i);
+    for (int i = npre; i < NGL; ++i) produce(i);
   } else if (warp == 11) {
     // ---- auxiliary warp: lane (g,t) <-> row g, factor columns 2t, 2t+1; runs two row groups ahead of the epilogue --
     const int V = ft.n_views;
