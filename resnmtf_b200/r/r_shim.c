@@ -150,7 +150,32 @@ SEXP C_resnmtf_fit(SEXP data, SEXP init_f, SEXP init_s, SEXP init_g, SEXP lam, S
   return out;
 }
 
-static const R_CallMethodDef call_methods[] = {{"C_resnmtf_fit", (DL_FUNC)&C_resnmtf_fit, 12}, {NULL, NULL, 0}};
+/* jsd_calc() (R/utils.r:95-106) for a batch of column pairs: cols is the n x m matrix of factor columns, bw / vmax
+ * their bw.nrd0 and maxima, pair_a / pair_b 1-based column indices.  Returns the numeric vector of JSD values in pair
+ * order (resnmtf_jsd_pairs). */
+SEXP C_resnmtf_jsd_pairs(SEXP cols, SEXP bw, SEXP vmax, SEXP pair_a, SEXP pair_b) {
+  if (!g_ctx && resnmtf_ctx_create(-1, &g_ctx) != RESNMTF_OK) Rf_error("%s", resnmtf_last_error());
+  if (!Rf_isReal(cols) || !Rf_isMatrix(cols)) Rf_error("cols must be a numeric matrix");
+  const int64_t n = Rf_nrows(cols);
+  const int m = Rf_ncols(cols);
+  const R_xlen_t np = XLENGTH(pair_a);
+  if (XLENGTH(pair_b) != np || XLENGTH(bw) != m || XLENGTH(vmax) != m) Rf_error("inconsistent argument lengths");
+  int32_t* a = (int32_t*)R_alloc((size_t)np + 1, sizeof(int32_t));
+  int32_t* b = (int32_t*)R_alloc((size_t)np + 1, sizeof(int32_t));
+  for (R_xlen_t i = 0; i < np; ++i) { /* R is 1-based */
+    a[i] = INTEGER(pair_a)[i] - 1;
+    b[i] = INTEGER(pair_b)[i] - 1;
+  }
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, np));
+  const int rc = resnmtf_jsd_pairs(g_ctx, REAL(cols), n, m, n, REAL(bw), REAL(vmax), a, b, (int64_t)np, REAL(out));
+  UNPROTECT(1);
+  if (rc != RESNMTF_OK) Rf_error("%s", resnmtf_last_error());
+  return out;
+}
+
+static const R_CallMethodDef call_methods[] = {{"C_resnmtf_fit", (DL_FUNC)&C_resnmtf_fit, 12},
+                                               {"C_resnmtf_jsd_pairs", (DL_FUNC)&C_resnmtf_jsd_pairs, 5},
+                                               {NULL, NULL, 0}};
 
 void R_init_resnmtf(DllInfo* dll) {
   R_registerRoutines(dll, NULL, call_methods, NULL, NULL);

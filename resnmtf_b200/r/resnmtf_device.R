@@ -46,3 +46,14 @@ resnmtf_device_loop <- function(data, current_f, current_s, current_g, current_l
     current_lam = out$lam, current_mu = out$mu, total_err = out$total_err
   )
 }
+
+# jsd_calc() (R/utils.r:95-106) for many column pairs at once: `cols` holds the factor columns, `pairs` is a two-column
+# integer matrix of (1-based) column indices.  calculate_f_shuffle_jsd() / check_biclusters() (R/obtain_bicl.r:55-68,
+# 113-133) keep their loops but collect the pairs and call this once per view.
+resnmtf_jsd_pairs <- function(cols, pairs) {
+  storage.mode(cols) <- "double"
+  .Call(
+    C_resnmtf_jsd_pairs, cols, apply(cols, 2, stats::bw.nrd0), apply(cols, 2, max),
+    as.integer(pairs[, 1]), as.integer(pairs[, 2])
+  )
+}

@@ -171,3 +171,32 @@ def test_device_bisilhouette_matches_host(method):
     assert len(dev["vals"]) == len(host["vals"])
     assert np.allclose(dev["vals"], host["vals"], rtol=1e-10, atol=1e-12)
     assert abs(dev["bisil"] - host["bisil"]) <= 1e-12
+
+
+def test_resident_route_with_restrictions_spurious_and_stability():
+    """Two matrix-sized views (600 x 600, the resident-data route) with partially shared rows and columns, phi and psi
+    (test-resnmtf.R:140-184 scaled up), spurious-bicluster removal and stability analysis: the sub-samples are
+    gathered on the device, their shared-name maps rebuilt from the sub-sampled names, the JSD thresholds come from
+    the pair kernel.  The planted blocks survive, shared rows end up closer than unshared ones, and the call is
+    reproducible from its seed."""
+    views, _ = synth.block_views(2, block=200, n_blocks=3, seed=41)
+    rn = [[f"row_{i}" for i in range(1, 601)],
+          [f"row_{i}" for i in range(1, 401)] + [f"row_{i}" for i in range(601, 801)]]
+    cn = [[f"col_{i}" for i in range(1, 601)],
+          [f"col_{i}" for i in range(1, 401)] + [f"col_{i}" for i in range(601, 801)]]
+    data = [NamedMatrix(x, rn[v], cn[v]) for v, x in enumerate(views)]
+    rest = np.zeros((2, 2))
+    rest[0, 1] = 1000.0
+    outs = []
+    for _ in range(2):
+        res = apply_resnmtf(data, k_val=3, phi=rest, psi=rest, spurious=True, stability=True, n_stability=3,
+                            num_repeats=3, rng=np.random.default_rng(6), max_iters=1000)
+        outs.append(res)
+        for v in range(2):
+            assert sorted(res["row_clusters"][v].sum(0)) == [200, 200, 200]
+            assert sorted(res["col_clusters"][v].sum(0)) == [200, 200, 200]
+        f = res["output_f"]
+        assert np.mean(np.abs(f[0][400:600] - f[1][400:600])) > np.mean(np.abs(f[0][:400] - f[1][:400]))
+    for key in ("output_f", "output_g", "row_clusters", "col_clusters"):
+        for a, b in zip(outs[0][key], outs[1][key]):
+            assert np.array_equal(a, b), key

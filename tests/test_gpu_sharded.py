@@ -131,3 +131,26 @@ def test_stability_repeats_placed_on_two_gpus_equal_serial():
             assert np.array_equal(a, b), key
     for v in range(2):
         assert sorted(par["row_clusters"][v].sum(axis=0).tolist()) == [60.0, 60.0, 60.0]
+
+
+@pytest.mark.skipif(L.device_count() < WORLD, reason="needs 2 GPUs")
+def test_resident_route_units_on_two_gpus_equal_one_gpu(monkeypatch):
+    """Matrix-sized view (resident-data route): k sweep + spurious removal + stability as units on 2 GPUs (views copied
+    GPU to GPU, sub-samples gathered where a unit runs) equal the 1-GPU call bit for bit."""
+    from resnmtf_b200 import synth
+    from resnmtf_b200.api import apply_resnmtf
+    from resnmtf_b200.device import Context
+
+    views, _ = synth.block_views(1, block=200, n_blocks=3, seed=43)
+    ctx = Context(0)
+    kw = dict(k_min=3, k_max=4, spurious=True, stability=True, n_stability=2, num_repeats=2, ctx=ctx, max_iters=1000)
+    outs = []
+    for cap in ("1", "2"):
+        monkeypatch.setenv("RESNMTF_MAX_GPUS", cap)
+        outs.append(apply_resnmtf(views, rng=np.random.default_rng(13), **kw))
+    assert outs[0]["output_f"][0].shape == (600, 3)
+    for key in ("output_f", "output_s", "output_g", "row_clusters", "col_clusters"):
+        for a, b in zip(outs[0][key], outs[1][key]):
+            assert np.array_equal(a, b), key
+    assert outs[0]["bisil"] == outs[1]["bisil"]
+    assert sorted(outs[0]["row_clusters"][0].sum(axis=0).tolist()) == [200.0, 200.0, 200.0]
