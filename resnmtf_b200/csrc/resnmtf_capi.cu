@@ -1675,7 +1675,11 @@ extern "C" int resnmtf_jsd_pairs(resnmtf_ctx* ctx, const double* vecs, int64_t n
     e = cudaMemcpyAsync(d_pairs + n_pairs, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
     const int64_t grid = std::min<int64_t>(n_pairs, (int64_t)ctx->sm_count * 8);
-    rn_jsd_pairs<<<(unsigned)grid, RN_KDE_N, 0, st>>>(d_vecs, n, n, d_par, d_par + m, d_pairs, d_pairs + n_pairs,
+    e = cudaFuncSetAttribute(rn_jsd_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RnKdeSmem));
+  }
+  if (e == cudaSuccess) {
+    const int64_t grid = std::min<int64_t>(n_pairs, (int64_t)ctx->sm_count * 8);
+    rn_jsd_pairs<<<(unsigned)grid, RN_KDE_N, sizeof(RnKdeSmem), st>>>(d_vecs, n, n, d_par, d_par + m, d_pairs, d_pairs + n_pairs,
                                                        n_pairs, d_out);
     e = cudaGetLastError();
   }

@@ -19,18 +19,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define RN_KDE_N 512      // grid points of density.default (n = 512) == threads per CTA
-#define RN_KDE_CHUNK 1024 // sample values staged in shared memory per binning round
+#define RN_KDE_N 512       // grid points of density.default (n = 512) == threads per CTA
+#define RN_KDE_WARPS 16    // RN_KDE_N / 32: every warp bins its own contiguous sixteenth of the sample
 
 struct RnKdeSmem {
-  int ix[RN_KDE_CHUNK];
-  double wa[RN_KDE_CHUNK];
-  double wb[RN_KDE_CHUNK];
+  double hist[RN_KDE_WARPS][RN_KDE_N];  // per-warp private bin sums (no atomics, no inter-warp conflicts)
   double y[RN_KDE_N];
   double kern[RN_KDE_N];
   double dens[RN_KDE_N];
   double red[RN_KDE_N];
 };
+static_assert(sizeof(RnKdeSmem) <= 100 * 1024, "two CTAs per SM");
 
 // Sum over the 512 threads in a fixed tree order (every thread receives the result).
 __device__ __forceinline__ double rn_kde_block_sum(double v, double* red) {
@@ -50,39 +49,63 @@ __device__ __forceinline__ double rn_kde_block_sum(double v, double* red) {
 // density(x, from = 0, to = to)$y at grid point threadIdx.x, zeroed where the grid point exceeds xmax (R/utils.r:99-103).
 __device__ double rn_kde_density(const double* __restrict__ x, int64_t n, double bw, double to, double xmax,
                                  RnKdeSmem& sm) {
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int N = RN_KDE_N;
   const double from = 0.0;
   const double lo = from - 4.0 * bw, up = to + 4.0 * bw;
   const double delta = (up - lo) / (double)(N - 1);
   const double w = 1.0 / (double)n;
-  // ---- BinDist: y[ix] += w (1 - fx), y[ix + 1] += w fx; thread t owns bin t and adds in sample order --------------
-  double acc = 0.0;
-  const int warp_bin0 = t & ~31;
-  for (int64_t c0 = 0; c0 < n; c0 += RN_KDE_CHUNK) {
-    const int cnt = (int)((n - c0) < (int64_t)RN_KDE_CHUNK ? (n - c0) : (int64_t)RN_KDE_CHUNK);
-    for (int i = t; i < cnt; i += N) {
-      const double xpos = (x[c0 + i] - lo) / delta;
-      const double fl = floor(xpos);
-      const double fx = xpos - fl;
-      int ixv = -4;  // non-finite or far outside: contributes nowhere
-      if (fl >= -1.0 && fl <= (double)(N - 1)) ixv = (int)fl;
-      sm.ix[i] = ixv;
-      sm.wa[i] = w * (1.0 - fx);
-      sm.wb[i] = w * fx;
-    }
-    __syncthreads();
-    for (int i = 0; i < cnt; ++i) {
-      const int d = sm.ix[i] - warp_bin0;  // same for the whole warp: most samples skip the warp entirely
-      if (d >= -1 && d < 32) {
-        const int mine = sm.ix[i] - t;
-        if (mine == 0) acc += sm.wa[i];
-        else if (mine == -1) acc += sm.wb[i];
+  // ---- BinDist: y[ix] += w (1 - fx), y[ix + 1] += w fx ------------------------------------------------------------------
+  // Factor columns pile most of their values into a few bins, so the bins cannot be the unit of work.  The SAMPLE is
+  // split instead: warp q bins samples [q n/16, (q+1) n/16) into its own histogram, 32 samples at a time; the lanes of
+  // a batch that hit the same bin are summed in lane order by the lowest of them, which alone touches the bin (first all
+  // left-neighbour weights of the batch, then all right-neighbour weights); at the end the 16 histograms are added in
+  // warp order.  Every sum has a fixed order: the result does not depend on the launch.
+#pragma unroll
+  for (int q = 0; q < RN_KDE_WARPS; ++q) sm.hist[q][t] = 0.0;
+  __syncthreads();
+  {
+    double* hist = sm.hist[warp];
+    const int64_t s0 = (n * warp) / RN_KDE_WARPS, s1 = (n * (warp + 1)) / RN_KDE_WARPS;
+    for (int64_t i0 = s0; i0 < s1; i0 += 32) {
+      const int64_t i = i0 + lane;
+      int ixv = -8 - lane;  // no sample / non-finite / far outside: a bin of its own, contributes nowhere
+      double wa = 0.0, wb = 0.0;
+      if (i < s1) {
+        const double xpos = (x[i] - lo) / delta;
+        const double fl = floor(xpos);
+        const double fx = xpos - fl;
+        if (fl >= -1.0 && fl <= (double)(N - 1)) {
+          ixv = (int)fl;
+          wa = w * (1.0 - fx);
+          wb = w * fx;
+        }
       }
+      const unsigned same = __match_any_sync(0xffffffffu, ixv);
+      const bool leader = (__ffs(same) - 1) == lane;
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int src = 0; src < 32; ++src) {  // lane order; all lanes run the shuffles, the members of my group count
+        const double va = __shfl_sync(0xffffffffu, wa, src);
+        const double vb = __shfl_sync(0xffffffffu, wb, src);
+        if ((same >> src) & 1u) {
+          sa += va;
+          sb += vb;
+        }
+      }
+      if (leader && ixv >= 0 && ixv < N) hist[ixv] += sa;
+      __syncwarp();
+      if (leader && ixv + 1 >= 0 && ixv + 1 < N) hist[ixv + 1] += sb;
+      __syncwarp();
     }
-    __syncthreads();
   }
-  sm.y[t] = acc;
+  __syncthreads();
+  {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < RN_KDE_WARPS; ++q) acc += sm.hist[q][t];
+    sm.y[t] = acc;
+  }
   // ---- gaussian on the lag grid seq(0, 2 (up - lo), length = 2 n): lag m sits at m * h ------------------------------
   {
     const double h = 2.0 * (up - lo) / (double)(2 * N - 1);
@@ -122,7 +145,8 @@ __global__ void __launch_bounds__(RN_KDE_N)
 rn_jsd_pairs(const double* __restrict__ vecs, int64_t n, int64_t ld, const double* __restrict__ bw,
              const double* __restrict__ vmax, const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
              int64_t n_pairs, double* __restrict__ out) {
-  __shared__ RnKdeSmem sm;
+  extern __shared__ __align__(16) unsigned char rn_kde_raw[];
+  RnKdeSmem& sm = *reinterpret_cast<RnKdeSmem*>(rn_kde_raw);
   for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
     const int a = pair_a[pr], b = pair_b[pr];
     const double ma = vmax[a], mb = vmax[b];
