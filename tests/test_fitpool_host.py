@@ -124,3 +124,45 @@ def test_res_nmtf_inner_serial_route_equals_the_pool_route(monkeypatch):
                                              max_iters=60)[0])
     _same(outs[0], outs[1])
     assert outs[0]["bisil"] == outs[1]["bisil"]
+
+
+@pytest.mark.parametrize("kind", ["planted", "shuffled", "blocks", "rank deficient"])
+def test_filtered_subspace_iteration_matches_the_dense_eigensolver(kind):
+    """api._topk_eig_filtered (the top-16 eigenpairs of a fit's Gram matrix) against numpy's dense
+    solver on the spectra the fits meet: planted blocks over a noise bulk, a shuffled view (one dominant pair, then a
+    nearly degenerate bulk edge), the reference's block test data (three nearly equal large pairs), and a matrix of
+    rank 5 (order 1050: five pairs, then the null space)."""
+    import torch
+
+    from resnmtf_b200 import api
+
+    rng = np.random.default_rng(31)
+    if kind in ("planted", "shuffled"):
+        x = synth.prep(synth.planted_view(5000, 1100, 5, rng, row_prob=0.2, col_prob=0.2, height=5.0, sigma=1.0)[0])
+        if kind == "shuffled":
+            x = rng.permutation(x.ravel()).reshape(x.shape)
+            x = x / x.sum(axis=0)[None, :]
+    elif kind == "blocks":
+        x = synth.prep(synth.block_views(1, block=350, n_blocks=3, seed=4)[0][0])
+    else:
+        x = rng.random((1500, 5)) @ rng.random((5, 1050))
+    gram = torch.from_numpy(np.ascontiguousarray(x.T @ x))
+    w, v = np.linalg.eigh(gram.numpy())
+    w, v = w[::-1][:16], v[:, ::-1][:, :16]
+    out = api._topk_eig_filtered(torch, gram, 16)
+    if kind == "rank deficient":  # the five non-zero pairs are found; the rest of the block lies in the null space
+        wt, vt = api._topk_eigh(torch, gram, 16)
+        assert np.allclose(wt.numpy()[:5], w[:5], rtol=1e-12)
+        assert np.max(np.abs(wt.numpy()[5:])) <= 1e-12 * w[0]
+        assert np.max(np.abs(np.abs(vt.numpy()[:, :5]) - np.abs(v[:, :5]))) <= 1e-10
+        return
+    assert out is not None
+    wi, vi = out[0].numpy(), out[1].numpy()
+    assert np.max(np.abs(wi - w) / w[0]) <= 1e-14
+    # residual at the rounding level of the matrix norm, like the dense solver's; orthonormal to rounding
+    assert np.max(np.linalg.norm(gram.numpy() @ vi - vi * wi[None, :], axis=0)) <= 5e-15 * w[0]
+    assert np.max(np.abs(vi.T @ vi - np.eye(16))) <= 1e-13
+    # the vectors themselves agree as far as their conditioning (rounding level of the norm over the gap) allows
+    gaps = np.minimum(np.abs(np.diff(w, prepend=np.inf)), np.abs(np.diff(np.append(w, w[-1] - (w[-2] - w[-1])))))
+    bound = 200 * np.finfo(float).eps * w[0] / gaps
+    assert np.all(np.max(np.abs(np.abs(vi) - np.abs(v)), axis=0) <= np.maximum(bound, 1e-12))

@@ -200,3 +200,23 @@ def test_resident_route_with_restrictions_spurious_and_stability():
     for key in ("output_f", "output_g", "row_clusters", "col_clusters"):
         for a, b in zip(outs[0][key], outs[1][key]):
             assert np.array_equal(a, b), key
+
+
+def test_device_svd_initialisation_filtered_route_matches_lapack():
+    """Gram matrices of order >= 1024 take the Chebyshev-filtered subspace iteration (api._topk_eig_filtered) instead
+    of the dense eigensolver.  Against LAPACK's full svd of the view itself (what the reference calls,
+    R/update_steps.r:92): singular values to 1e-11, |U_k| and |V_k| to 1e-9 -- the Gram route squares the condition of
+    the bulk vectors whichever solver reads the Gram matrix -- on a planted and on a shuffled spectrum."""
+    from resnmtf_b200 import api
+
+    rng = np.random.default_rng(19)
+    x = synth.prep(synth.planted_view(2600, 1100, 4, rng, row_prob=0.2, col_prob=0.2, height=5.0, sigma=1.0)[0])
+    shuffled = rng.permutation(x.ravel()).reshape(x.shape)
+    shuffled = shuffled / shuffled.sum(axis=0)[None, :]
+    for m in (x, shuffled):
+        out = api._svd_topk_device(np.asfortranarray(m), 6, -1)
+        assert out is not None
+        u, d, vt = np.linalg.svd(m, full_matrices=False)
+        assert rel_err(out[1], d[:6]) <= 1e-11
+        assert np.max(np.abs(out[0] - np.abs(u[:, :6]))) <= 1e-9
+        assert np.max(np.abs(out[2] - np.abs(vt[:6].T))) <= 1e-9

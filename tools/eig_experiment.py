@@ -14,7 +14,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from resnmtf_b200 import synth  # noqa: E402
+from resnmtf_b200 import api, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 p = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
@@ -81,3 +81,15 @@ for name, m in (("planted", xt), ("shuffled", xs)):
     print(f"{name:9s} eigh {['%.1f' % (1e3 * t) for t in t_full]} ms | syevdx top-{KC} {['%.1f' % (1e3 * t) for t in t_top]} ms | "
           f"rel dW {rel_w:.2e}  max d|V| {dv:.2e}  max d|U| {du:.2e}  residual {resid:.2e}  orth {orth:.2e}")
     print("   top eigenvalues:", [f"{float(v):.6e}" for v in wf[:8]])
+    out, t_f = timed(lambda: api._topk_eig_filtered(torch, gram, KC))
+    if out is None:
+        print(f"   filtered subspace iteration: NOT CONVERGED ({['%.1f' % (1e3 * t) for t in t_f]} ms)")
+        continue
+    w_i, v_i = out
+    u_i = (m.T @ v_i) / torch.sqrt(w_i)
+    print(f"   filtered subspace iteration {['%.1f' % (1e3 * t) for t in t_f]} ms | rel dW "
+          f"{float(((w_i - wf).abs() / wf.abs()).max()):.2e}  max d|V| {float((v_i.abs() - vf.abs()).abs().max()):.2e}  "
+          f"max d|U| {float((u_i.abs() - u_full.abs()).abs().max()):.2e}  residual/lambda_max "
+          f"{float((gram @ v_i - v_i * w_i).norm(dim=0).max() / wf[0]):.2e} (eigh: "
+          f"{float((gram @ vf - vf * wf).norm(dim=0).max() / wf[0]):.2e})  orth "
+          f"{float((v_i.T @ v_i - torch.eye(KC, dtype=torch.float64, device=dev)).abs().max()):.2e}")
