@@ -89,7 +89,7 @@ def _topk_eig_filtered(torch, gram, kc, guard=48, tol=1.0e-15, max_outer=40):
     gen = torch.Generator(device=dev)
     gen.manual_seed(20260000)
     q, _ = torch.linalg.qr(torch.randn((m, b), generator=gen, device=dev, dtype=dt))
-    work = gram  # deflated copy once something is locked
+    work = gram  # deflated copy once something is locked: locked pairs then sit at eigenvalue 0, inside the damped range
     vlock = torch.empty((m, 0), device=dev, dtype=dt)
     lam_lock = []
 
@@ -98,12 +98,13 @@ def _topk_eig_filtered(torch, gram, kc, guard=48, tol=1.0e-15, max_outer=40):
 
     for _ in range(max_outer):
         aq = off_locked(work @ q)
-        h = q.T @ aq
-        theta, y = torch.linalg.eigh(0.5 * (h + h.T))
-        theta, y = theta.flip(0), y.flip(1)
+        h = (q.T @ aq).cpu().numpy()  # Rayleigh-Ritz on the host: the b x b problem is too small for the GPU
+        th, y = np.linalg.eigh(0.5 * (h + h.T))
+        th, y = th[::-1].copy(), np.ascontiguousarray(y[:, ::-1])
+        y = torch.from_numpy(y).to(dev)
+        theta = torch.from_numpy(th).to(dev)
         q, aq = q @ y, aq @ y
-        th = theta.cpu().numpy()
-        rs = (aq - q * theta[None, :]).norm(dim=0).cpu().numpy()
+        rs = torch.linalg.vector_norm(aq - q * theta[None, :], dim=0).cpu().numpy()
         scale = max(abs(float(th[0])), lam_lock[0] if lam_lock else 0.0)
         n_new = 0  # leading pairs only, in order: nothing above a locked pair is still moving
         while n_new < len(th) and len(lam_lock) + n_new < kc and rs[n_new] <= tol * scale:
@@ -114,7 +115,7 @@ def _topk_eig_filtered(torch, gram, kc, guard=48, tol=1.0e-15, max_outer=40):
             lam_lock += [float(v) for v in th[:n_new]]
             if work is gram:
                 work = gram.clone()
-            work -= (vn * theta[:n_new][None, :]) @ vn.T
+            work.addmm_(vn * theta[:n_new][None, :], vn.T, alpha=-1.0)
             q, th = q[:, n_new:], th[n_new:]
         if len(lam_lock) >= kc:
             return torch.tensor(lam_lock, device=dev, dtype=dt), vlock
@@ -125,12 +126,14 @@ def _topk_eig_filtered(torch, gram, kc, guard=48, tol=1.0e-15, max_outer=40):
         t_max = max((2.0 * float(th[0]) - c) / c, 1.0 + 1.0e-12)
         deg = int(min(40, max(2, math.floor(23.0 / math.acosh(t_max)))))
         e = 0.5 * c
-        y0, y1 = q, off_locked((work @ q - e * q) / e)
+        # T_j((W - e I) / e) q by the three-term recurrence, one fused GEMM per degree on the shifted matrix
+        shifted = work.clone()
+        shifted.diagonal().sub_(e)
+        y0, y1 = q, (shifted @ q) / e
         for _ in range(2, deg + 1):
-            y0, y1 = y1, off_locked((work @ y1 - e * y1) * (2.0 / e) - y0)
-        q, _ = torch.linalg.qr(y1)
-        if vlock.shape[1]:  # once more: keeps the block orthogonal to the locked vectors to rounding
-            q, _ = torch.linalg.qr(off_locked(q))
+            y0, y1 = y1, torch.addmm(y0, shifted, y1, beta=-1.0, alpha=2.0 / e)
+        del shifted
+        q, _ = torch.linalg.qr(off_locked(y1))
     return None
 
 
