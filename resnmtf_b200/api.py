@@ -440,7 +440,7 @@ def run_fits(pool, specs, phi, xi, psi, n_iters, num_repeats, spurious, distance
                              eig_cache=worker.eig_cache(key) if (shared and on_dev) else None)
 
         core_at.append(len(tasks))
-        tasks.append((cost * 1.01, core, (), "fit"))
+        tasks.append((cost * 1.01, core, (), "fit", key if sp.get("shared", False) else None))
         shuffle_at = []
         for srng in shuffle_rngs:
             def shuffle(worker, data=data, key=key, on_dev=on_dev, srng=srng,

@@ -121,11 +121,14 @@ class FitPool:
                 xt = xt / xt.sum(dim=1, keepdim=True)
             first.append(xt)
         w0.views[key] = first
-        for w in self.workers[1:]:
-            w.views[key] = [t.to(torch_device(w.ctx.device)) for t in first]
-        for w in self.workers:
-            torch.cuda.synchronize(w.views[key][0].device)
-        self.loaders[key] = lambda worker: worker.views[key]
+        torch.cuda.synchronize(dev0)
+
+        def copy_from_first(worker):  # runs on the worker's own thread, so the GPU-to-GPU copies overlap
+            out = [t.to(torch_device(worker.ctx.device)) for t in first]
+            torch.cuda.synchronize(out[0].device)
+            return out
+
+        self.loaders[key] = copy_from_first
 
     def place_gather(self, key, base_key, rows, cols):
         """Views of ``key`` = rows / columns ``rows[v]`` / ``cols[v]`` of the resident views of ``base_key``, gathered
@@ -144,12 +147,13 @@ class FitPool:
 
     # ---- work ---------------------------------------------------------------------------------------
     def run(self, tasks):
-        """``tasks``: [(cost, callable(worker) -> result)] or [(cost, callable, deps, label)] where ``deps`` lists the
+        """``tasks``: [(cost, callable(worker) -> result)] or [(cost, callable, deps, label[, affinity])] where ``deps`` lists the
         indices of the tasks whose results must exist first (a task with deps reads them from the list this method
         returns -- it is handed over as ``worker.results`` -- e.g. the post-processing of a fit waits for its core
         and its shuffled refits).  Returns the results in task order.  A free GPU takes the ready task with the
         largest cost; with one GPU the tasks simply run one after the other on the calling thread."""
-        tasks = [(t[0], t[1], tuple(t[2]) if len(t) > 2 else (), t[3] if len(t) > 3 else "unit") for t in tasks]
+        tasks = [(t[0], t[1], tuple(t[2]) if len(t) > 2 else (), t[3] if len(t) > 3 else "unit",
+                  t[4] if len(t) > 4 else None) for t in tasks]
         order = sorted(range(len(tasks)), key=lambda i: (-float(tasks[i][0]), i))
         results = [None] * len(tasks)
         finished = [False] * len(tasks)
@@ -164,10 +168,26 @@ class FitPool:
                 if self.trace is not None:
                     self.trace.append(("unit", worker.index, time.perf_counter() - t0, tasks[i][3]))
 
-        def next_ready(pending):
+        owner = {}  # affinity key -> index of the worker that took the first task of that key
+
+        def next_ready(pending, worker):
+            """Highest-priority ready task for this worker.  Tasks that share an affinity key (the fits of one data
+            set: whoever runs the first of them builds the library-layout copy of the views and the SVD triplets on
+            its GPU) go to the worker that owns the key as long as it is busy with them; another worker takes one
+            only when nothing else is ready for it."""
+            fallback = None
             for pos, i in enumerate(pending):
-                if all(finished[d] for d in tasks[i][2]):
+                if not all(finished[d] for d in tasks[i][2]):
+                    continue
+                key = tasks[i][4]
+                if key is None or owner.get(key, worker.index) == worker.index:
+                    if key is not None:
+                        owner[key] = worker.index
                     return pending.pop(pos)
+                if fallback is None:
+                    fallback = pos
+            if fallback is not None:
+                return pending.pop(fallback)
             return None
 
         pending = list(order)
@@ -175,7 +195,7 @@ class FitPool:
         try:
             if n_threads <= 1:
                 while pending:
-                    i = next_ready(pending)
+                    i = next_ready(pending, self.workers[0])
                     if i is None:
                         raise RuntimeError("FitPool.run: circular task dependencies")
                     execute(i, self.workers[0])
@@ -191,7 +211,7 @@ class FitPool:
                         while True:
                             if errors or not pending:
                                 return
-                            i = next_ready(pending)
+                            i = next_ready(pending, worker)
                             if i is not None:
                                 running[0] += 1
                                 break

@@ -166,3 +166,31 @@ def test_filtered_subspace_iteration_matches_the_dense_eigensolver(kind):
     gaps = np.minimum(np.abs(np.diff(w, prepend=np.inf)), np.abs(np.diff(np.append(w, w[-1] - (w[-2] - w[-1])))))
     bound = 200 * np.finfo(float).eps * w[0] / gaps
     assert np.all(np.max(np.abs(np.abs(vi) - np.abs(v)), axis=0) <= np.maximum(bound, 1e-12))
+
+
+def test_pool_keeps_tasks_of_one_affinity_key_on_one_gpu_and_lets_idle_gpus_steal():
+    """The fits of one data set share what the first of them builds on its GPU (library-layout copy, SVD triplets):
+    they stay on the GPU that took the first one while the others have other work; a GPU with nothing else to do
+    takes one rather than idle."""
+    import time
+
+    ran, lock = [], threading.Lock()
+
+    def unit(name, seconds):
+        def run(worker):
+            time.sleep(seconds)
+            with lock:
+                ran.append((name, worker.index))
+
+        return run
+
+    pool = FitPool([fake_device.FakeContext(d) for d in range(3)])
+    tasks = [(2.0, unit(f"fit{i}", 0.03), (), "fit", "data") for i in range(4)]
+    tasks += [(1.0, unit(f"refit{i}", 0.03), (), "shuffled refit") for i in range(24)]
+    pool.run(tasks)
+    assert len(ran) == 28
+    assert len({w for name, w in ran if name.startswith("fit")}) == 1
+    # nothing but affinity tasks: the other GPUs take them instead of waiting for the owner
+    ran.clear()
+    pool.run([(1.0, unit(f"fit{i}", 0.05), (), "fit", "data") for i in range(6)])
+    assert len({w for _, w in ran}) == 3
