@@ -15,7 +15,7 @@ from . import _lib as L
 from . import prep, sharding
 from .bicluster import obtain_biclusters
 from .device import DeviceFit, default_context, device_contexts
-from .prep import NamedMatrix, as_named
+from .prep import as_named
 from .stability import stability_check
 
 

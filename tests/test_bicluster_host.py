@@ -85,3 +85,51 @@ def test_binarise_thresholds_and_relations():
     rows, cols = B.binarise([f], [g])
     assert np.array_equal(rows[0], [[1, 0], [0, 1], [0, 1]])
     assert np.array_equal(cols[0], np.zeros((2, 2)))
+
+
+def test_bw_nrd0_of_all_columns_at_once_equals_the_per_column_function():
+    from resnmtf_b200 import bicluster as B
+
+    rng = np.random.default_rng(3)
+    cols = np.abs(rng.standard_normal((5000, 7))) ** 3
+    cols[:, 4] = 0.25            # constant column: sd = IQR = 0 -> |x[1]|
+    cols[:, 5] = 0.0             # all zero -> 1
+    cols[2500:, 6] = 0.0         # IQR = 0 but sd > 0 -> sd
+    want = np.array([B.bw_nrd0(cols[:, c]) for c in range(7)])
+    assert np.array_equal(B.bw_nrd0_columns(cols), want)
+
+
+def test_draw_subsample_drops_empty_rows_and_columns_and_reuses_view_one_sample():
+    """The sampling loop of stability_repeat (R/stability_analysis.r:222-253) through the sums-only interface: rows and
+    columns that are all zero inside the sub-sample are dropped, views with view 1's dimensions reuse its sample, a
+    view of other dimensions draws its own, and the final sub-samples have no all-zero row or column."""
+    from resnmtf_b200.prep import NamedMatrix
+
+    rng = np.random.default_rng(5)
+    a = rng.random((60, 40)) + 0.1
+    a[7, :] = 0.0                      # an all-zero row: dropped whenever it is drawn
+    a[:, 11] = 0.0                     # an all-zero column
+    b = a.copy()
+    c = rng.random((50, 30)) + 0.1     # other dimensions: its own sample
+    data = [NamedMatrix(x, [f"r{i}" for i in range(x.shape[0])], [f"c{j}" for j in range(x.shape[1])])
+            for x in (a, b, c)]
+    shapes = [m.shape for m in data]
+    out = S.draw_subsample(S.host_sums(data), shapes, shapes[0], 3, 0.9, np.random.default_rng(1))
+    assert out is not None
+    rows, cols = out
+    assert np.array_equal(rows[0], rows[1]) and np.array_equal(cols[0], cols[1])
+    assert 7 not in rows[0] and 11 not in cols[0]
+    assert len(rows[2]) == 45 and len(cols[2]) == 27
+    for v in range(3):
+        sub = data[v].x[np.ix_(rows[v], cols[v])]
+        assert not (sub.sum(0) == 0).any() and not (sub.sum(1) == 0).any()
+
+
+def test_resident_matrix_has_shape_and_names_but_no_host_values():
+    from resnmtf_b200.fitpool import ResidentMatrix
+    from resnmtf_b200.prep import as_named
+
+    m = ResidentMatrix((5, 3), ["a", "b", "c", "d", "e"], ["x", "y", "z"])
+    assert m.shape == (5, 3) and m.x is None and m.rownames[4] == "e"
+    cp = as_named(m)
+    assert isinstance(cp, ResidentMatrix) and cp.shape == (5, 3) and cp.colnames == ["x", "y", "z"]
