@@ -30,7 +30,11 @@ def bw_nrd0_columns(cols):
     cols = np.asarray(cols, dtype=np.float64)
     n = cols.shape[0]
     hi = np.std(cols, axis=0, ddof=1) if n > 1 else np.zeros(cols.shape[1])
-    q75, q25 = np.percentile(cols, [75, 25], axis=0)
+    # along the contiguous axis of the column-major matrix: same values, half the time of axis=0 on this layout
+    if cols.flags.f_contiguous:
+        q75, q25 = np.percentile(cols.T, [75, 25], axis=1)
+    else:
+        q75, q25 = np.percentile(cols, [75, 25], axis=0)
     lo = np.minimum(hi, (q75 - q25) / 1.34)
     first = np.abs(cols[0, :])
     lo = np.where(lo != 0, lo, np.where(hi != 0, hi, np.where(first != 0, first, 1.0)))
