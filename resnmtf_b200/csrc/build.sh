@@ -1,14 +1,23 @@
 #!/usr/bin/env bash
-# Builds the C-ABI shared library in-tree for sm_100a (nvcc cross-compiles without a GPU).
+# Builds the C-ABI shared library in-tree for sm_100a (nvcc cross-compiles without a GPU).  Every *.cu of this
+# directory is one translation unit; they are compiled in parallel and linked into one libresnmtf_b200.so.
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${RESNMTF_OUT:-$here/../libresnmtf_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 -shared)
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2)
 if [[ "${RESNMTF_VERBOSE_PTXAS:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
 if [[ -n "${RESNMTF_DEFS:-}" ]]; then FLAGS+=(${RESNMTF_DEFS}); fi
-if [[ "${RESNMTF_WITH_NCCL:-0}" == "1" && -f /usr/include/nccl.h ]]; then
-  FLAGS+=(-DRESNMTF_WITH_NCCL -lnccl)
-fi
-"$NVCC" "${FLAGS[@]}" -o "$out" "$here/resnmtf_capi.cu"
+obj="$(mktemp -d "${TMPDIR:-/tmp}/resnmtf_obj.XXXXXX")"
+trap 'rm -rf "$obj"' EXIT
+pids=()
+objs=()
+for src in "$here"/*.cu; do
+  o="$obj/$(basename "${src%.cu}").o"
+  objs+=("$o")
+  "$NVCC" "${FLAGS[@]}" -c -o "$o" "$src" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$out" "${objs[@]}" -lpthread
 echo "built $out"

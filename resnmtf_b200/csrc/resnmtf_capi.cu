@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -11,215 +12,10 @@
 #include <string>
 #include <vector>
 
-#include "../../include/resnmtf_b200.h"
+#include "rn_host.h"
 #include "rn_kernels.cuh"
 #include "rn_fused.cuh"
 #include "rn_post.cuh"
-
-#include <dlfcn.h>
-
-// NCCL is only needed by the row-sharded path, so it is resolved lazily with dlopen (no link-time
-// dependency): the handful of types / enum values used here are ABI-stable across NCCL 2.x.
-typedef struct rn_nccl_comm* rn_ncclComm_t;
-typedef struct { char internal[128]; } rn_ncclUniqueId;
-enum { RN_NCCL_SUCCESS = 0, RN_NCCL_SUM = 0, RN_NCCL_INT64 = 4, RN_NCCL_FLOAT64 = 8 };
-struct RnNccl {
-  void* handle = nullptr;
-  int (*GetUniqueId)(rn_ncclUniqueId*) = nullptr;
-  int (*CommInitRank)(rn_ncclComm_t*, int, rn_ncclUniqueId, int) = nullptr;
-  int (*CommDestroy)(rn_ncclComm_t) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, rn_ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-  bool ok = false;
-};
-static RnNccl& rn_nccl() {
-  static RnNccl api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nm : names) {
-      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-      if (api.handle) break;
-    }
-    if (api.handle) {
-      api.GetUniqueId = (int (*)(rn_ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
-      api.CommInitRank = (int (*)(rn_ncclComm_t*, int, rn_ncclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
-      api.CommDestroy = (int (*)(rn_ncclComm_t))dlsym(api.handle, "ncclCommDestroy");
-      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, rn_ncclComm_t, cudaStream_t))dlsym(
-          api.handle, "ncclAllReduce");
-      api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
-      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
-    }
-  }
-  return api;
-}
-
-// ------------------------------------------------------------------------------------------------
-// error plumbing
-// ------------------------------------------------------------------------------------------------
-static thread_local std::string g_err = "";
-
-static int rn_fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-
-#define RN_CUDA(expr)                                                                         \
-  do {                                                                                        \
-    cudaError_t e__ = (expr);                                                                 \
-    if (e__ != cudaSuccess)                                                                   \
-      return rn_fail(e__ == cudaErrorMemoryAllocation ? RESNMTF_E_NOMEM : RESNMTF_E_CUDA,     \
-                     std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
-  } while (0)
-
-#define RN_NCCL(expr)                                                                                   \
-  do {                                                                                                  \
-    int r__ = (expr);                                                                                   \
-    if (r__ != RN_NCCL_SUCCESS)                                                                         \
-      return rn_fail(RESNMTF_E_COMM, std::string(#expr) + ": " + rn_nccl().GetErrorString(r__));        \
-  } while (0)
-
-#define RN_CHECK(cond, code, msg) \
-  do {                            \
-    if (!(cond)) return rn_fail(code, msg); \
-  } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// handles
-// ------------------------------------------------------------------------------------------------
-struct resnmtf_ctx {
-  int device = 0;
-  int sm_count = 148;
-  size_t l2_persist_bytes = 0;  // persisting-L2 carve-out granted to this device (0: unavailable / disabled)
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int rank = 0, n_ranks = 1;
-  rn_ncclComm_t comm = nullptr;
-  // Device memory comes from the stream-ordered pool of the device with an unlimited release threshold: after the
-  // first fit the create / destroy path of a fit never reaches the driver's allocator (measured: cudaMalloc +
-  // cudaFree cost 3 ms per fit on one box and 15 ms on another -- more than the upload of the factors).
-  bool pooled = false;
-  // host -> device upload pipeline (two staging buffers, copy stream, events), created on first use and kept
-  double* stage[2] = {nullptr, nullptr};
-  size_t stage_bytes = 0;
-  cudaStream_t copy_st = nullptr;
-  cudaEvent_t copied[2] = {nullptr, nullptr}, tiled[2] = {nullptr, nullptr};
-};
-
-static cudaError_t rn_dev_alloc(resnmtf_ctx* ctx, void** p, size_t bytes) {
-  if (ctx->pooled) return cudaMallocAsync(p, bytes, ctx->stream);
-  return cudaMalloc(p, bytes);
-}
-static cudaError_t rn_dev_free(resnmtf_ctx* ctx, void* p) {
-  if (!p) return cudaSuccess;
-  if (ctx->pooled) return cudaFreeAsync(p, ctx->stream);
-  return cudaFree(p);
-}
-
-// A view's X in the device layout, shareable between fits (the k-sweep of apply_resnmtf fits the same
-// data for every k, R/main.r:279-287): reference-counted, freed when the last holder lets go.
-struct resnmtf_data {
-  resnmtf_ctx* ctx = nullptr;
-  int64_t n = 0, p = 0, ldx = 0, pp = 0;
-  double* X = nullptr;
-  double* X8 = nullptr;  // 8-row-group copy for the one-pass fused kernel (built on demand by the first plan)
-  int64_t pp8 = 0;
-  double xnorm2 = 0.0;
-  int refs = 1;
-};
-
-static void rn_data_release(resnmtf_data* d) {
-  if (d && --d->refs == 0) {
-    rn_dev_free(d->ctx, d->X);
-    rn_dev_free(d->ctx, d->X8);
-    delete d;
-  }
-}
-
-struct ViewHost {
-  RnView d;  // device pointers + geometry (passed by value to the kernels)
-  resnmtf_data* shared = nullptr;  // non-null: X belongs to a shared data handle
-  size_t l2_window = 0;            // bytes at the head of X pinned in L2 (persisting access-policy window)
-  int impl = RESNMTF_IMPL_TMA;     // kernel family this view runs (a fit may mix FUSED and TMA views)
-  double* x8_own = nullptr;        // X8 owned by the fit (views without a shared data handle)
-  bool has_data = false, has_factors = false;
-  std::vector<int32_t*> rowmaps, colmaps;  // [V] device maps of this view into view w (or null)
-  double* xpart = nullptr;                 // ||X||^2 partials
-  int32_t* xticket = nullptr;
-};
-
-struct resnmtf_fit {
-  resnmtf_ctx* ctx = nullptr;
-  int V = 0;
-  std::vector<ViewHost> views;
-  std::vector<void*> allocs;
-  RnFit d;               // passed by value to the kernels
-  RnView* d_views = nullptr;
-  RnCtrl* d_ctrl = nullptr;
-  double *d_phi = nullptr, *d_xi = nullptr, *d_psi = nullptr;
-  const int32_t** d_rowmap = nullptr;
-  const int32_t** d_colmap = nullptr;
-  int8_t *d_rowmode = nullptr, *d_colmode = nullptr;
-  std::vector<const int32_t*> h_rowmap, h_colmap;
-  std::vector<int8_t> h_rowmode, h_colmode;
-  std::vector<double> h_phi, h_xi, h_psi;
-  double* d_hist = nullptr;
-  int64_t hist_cap = 4096;
-  std::vector<double> errors;  // All_Error
-  int err_mode = RESNMTF_ERR_AUTO;
-  int impl_req = RESNMTF_IMPL_AUTO;
-  int impl = RESNMTF_IMPL_TMA;
-  bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
-  bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
-  bool auto_direct = false; // AUTO error mode has handed over to the direct residual pass
-  int comm_rc = 0;          // first NCCL failure seen while enqueueing (row-sharded path)
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  int64_t launches_per_iter = 0;
-  resnmtf_counters counters{};
-  RnCtrl h_ctrl{};
-};
-
-template <typename T>
-static int rn_alloc(resnmtf_fit* f, T** out, size_t count, bool zero = true) {
-  void* p = nullptr;
-  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  RN_CUDA(rn_dev_alloc(f->ctx, &p, bytes));
-  f->allocs.push_back(p);
-  if (zero) RN_CUDA(cudaMemsetAsync(p, 0, bytes, f->ctx->stream));
-  *out = static_cast<T*>(p);
-  return RESNMTF_OK;
-}
-
-static int rn_free(resnmtf_fit* f, void* p) {
-  if (!p) return RESNMTF_OK;
-  auto it = std::find(f->allocs.begin(), f->allocs.end(), p);
-  if (it != f->allocs.end()) f->allocs.erase(it);
-  RN_CUDA(rn_dev_free(f->ctx, p));
-  return RESNMTF_OK;
-}
-
-static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
-
-static int rn_env_int(const char* name, int dflt) {
-  const char* s = std::getenv(name);
-  return (s && *s) ? std::atoi(s) : dflt;
-}
-
-// in-place sum over the ranks of a row-sharded context, on the context's stream (graph-capturable)
-static int rn_allreduce(resnmtf_ctx* ctx, void* buf, size_t count, bool is_int64 = false) {
-  if (ctx->n_ranks <= 1) return RESNMTF_OK;
-  RN_NCCL(rn_nccl().AllReduce(buf, buf, count, is_int64 ? RN_NCCL_INT64 : RN_NCCL_FLOAT64, RN_NCCL_SUM, ctx->comm,
-                              ctx->stream));
-  return RESNMTF_OK;
-}
-
-// host twin of rn_fidx (rn_kernels.cuh): position of F[r, c] in the swizzled 64-row panel layout
-static inline int64_t rn_fidx_host(int64_t r, int c, int kp) {
-  const int sigma = ((c & 1) << 2) | (c & 2);
-  return ((r >> 6) * kp + c) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ sigma) + (r & 1);
-}
 
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch on k
@@ -303,8 +99,8 @@ static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, c
 // Cluster size of the fused path for a view, 0 when it does not qualify: k <= 8, not row-sharded, p within
 // 8 x 1008 columns and not padded by more than RESNMTF_FUSED_MAX_PAD percent (default 135: the one-pass kernel
 // costs ~0.68 of the two-pass pair per padded column).
-static int fused_csize(const RnView& d, int n_ranks) {
-  if (d.k > 8 || n_ranks > 1) return 0;
+static int fused_csize(const RnView& d, bool sharded) {
+  if (d.k > 8 || sharded) return 0;
   const double max_pad = rn_env_int("RESNMTF_FUSED_MAX_PAD", 135) / 100.0;
   for (int c = 1; c <= RN_FU_MAXC; ++c)
     if ((int64_t)c * RN_FU_CCOLS >= d.p) return ((double)c * RN_FU_CCOLS <= max_pad * (double)d.p) ? c : 0;
@@ -406,13 +202,13 @@ static int ff_contributors(const RnView& d) {
   return (int)(u < cut ? u / (q + 1) : rem + (u - cut) / q) + 1;
 }
 
-// G step of one view: returns the number of kernels launched.  `ctx` is non-null with n_ranks > 1 for a
+// G step of one view: returns the number of kernels launched.  `ctx` has joined a communicator for a
 // row-sharded view: the stream kernel then stops after T, [T | F'F | colSums(F)] is all-reduced over the ranks
 // and the stand-alone epilogue finishes the view on every rank redundantly (no broadcast needed).
 static int launch_g_step(const ViewHost& vh, const RnFit& ft, int v, int impl, int fuse, cudaStream_t st,
                          resnmtf_ctx* ctx, int* comm_rc) {
   const int K = vh.d.k;
-  const bool sharded = ctx && ctx->n_ranks > 1;
+  const bool sharded = ctx && ctx->comm;
   if (use_mma(vh, impl) && !sharded) {
     if (impl != RESNMTF_IMPL_DMMA)
       launch_windowed(g_step_tma_fn(K), vh.d.g_ctas, RN_TMA_THREADS, rn_g_tma_smem(K), st, vh.d.X, vh.l2_window,
@@ -484,7 +280,7 @@ static void launch_residual_kernel(const ViewHost& vh, const RnFit& ft, int forc
 static int launch_residual(const ViewHost& vh, const RnFit& ft, int force, cudaStream_t st, resnmtf_ctx* ctx,
                            int* comm_rc) {
   launch_residual_kernel(vh, ft, force, st);
-  if (!(ctx && ctx->n_ranks > 1)) return 1;
+  if (!(ctx && ctx->comm)) return 1;
   const int rc = rn_allreduce(ctx, vh.d.scal + 3, 1);
   if (rc && comm_rc) *comm_rc = rc;
   rn_residual_scale<<<1, 1, 0, st>>>(vh.d, ft, force);
@@ -494,7 +290,11 @@ static int launch_residual(const ViewHost& vh, const RnFit& ft, int force, cudaS
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-extern "C" const char* resnmtf_last_error(void) { return g_err.c_str(); }
+std::string& rn_err_slot() {
+  static thread_local std::string g_err = "";
+  return g_err;
+}
+extern "C" const char* resnmtf_last_error(void) { return rn_err_slot().c_str(); }
 extern "C" const char* resnmtf_version(void) { return "resnmtf_b200 0.1.0 (sm_100a)"; }
 
 extern "C" int resnmtf_device_count(void) {
@@ -538,11 +338,22 @@ extern "C" int resnmtf_ctx_create(int device, resnmtf_ctx** out) {
   RN_CUDA(cudaEventCreate(&c->ev1));
   if (rn_env_int("RESNMTF_NO_POOL", 0) == 0) {
     int pools = 0;
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools &&
-        cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools) {
+      cudaMemPoolProps props;
+      std::memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
       uint64_t keep = UINT64_MAX;
-      if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) c->pooled = true;
+      if (cudaMemPoolCreate(&c->pool, &props) == cudaSuccess) {
+        if (cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) {
+          c->pooled = true;
+        } else {
+          cudaMemPoolDestroy(c->pool);
+          c->pool = nullptr;
+        }
+      }
     }
     cudaGetLastError();
   }
@@ -550,26 +361,26 @@ extern "C" int resnmtf_ctx_create(int device, resnmtf_ctx** out) {
   return RESNMTF_OK;
 }
 
-extern "C" int resnmtf_ctx_destroy(resnmtf_ctx* ctx) {
-  if (!ctx) return RESNMTF_OK;
+void rn_ctx_release(resnmtf_ctx* ctx) {
+  if (!ctx || ctx->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(ctx->device);
-  if (ctx->comm) rn_nccl().CommDestroy(ctx->comm);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) rn_nccl().CommDestroy(ctx->comm);
   for (int b = 0; b < 2; ++b) {
     if (ctx->stage[b]) cudaFree(ctx->stage[b]);
     if (ctx->copied[b]) cudaEventDestroy(ctx->copied[b]);
     if (ctx->tiled[b]) cudaEventDestroy(ctx->tiled[b]);
   }
   if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
-  if (ctx->pooled) {  // give the cached blocks back to the device
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // every block of the private pool goes back to the device
   delete ctx;
+}
+
+extern "C" int resnmtf_ctx_destroy(resnmtf_ctx* ctx) {
+  rn_ctx_release(ctx);  // fits / data handles still alive keep the context until the last of them is destroyed
   return RESNMTF_OK;
 }
 
@@ -602,6 +413,7 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
   resnmtf_fit* f = new (std::nothrow) resnmtf_fit();
   RN_CHECK(f != nullptr, RESNMTF_E_NOMEM, "resnmtf_fit_create: out of host memory");
   f->ctx = ctx;
+  ctx->refs.fetch_add(1);
   f->V = n_views;
   f->views.resize(n_views);
   int rc = RESNMTF_OK;
@@ -621,7 +433,7 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
     vh.d.ldx = rn_round_up(n[v], RN_ROW_TILE);
     vh.d.pp = rn_round_up(p[v], 32);
     vh.d.row_tiles = (int)(vh.d.ldx / RN_ROW_TILE);
-    vh.d.sharded = ctx->n_ranks > 1 ? 1 : 0;
+    vh.d.sharded = ctx->comm ? 1 : 0;
     vh.rowmaps.assign(V, nullptr);
     vh.colmaps.assign(V, nullptr);
     const int K = k[v], KP = vh.d.kp;
@@ -665,7 +477,7 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
   f->h_psi.assign((size_t)V * V, 0.0);
   std::memset(&f->d, 0, sizeof(RnFit));
   std::memset(&f->h_ctrl, 0, sizeof(RnCtrl));
-  if (ctx->n_ranks > 1) {  // row-sharded views: n is local, the coupling weights need the global row count
+  if (ctx->comm) {  // row-sharded views: n is local, the coupling weights need the global row count
     int64_t* d_n = nullptr;
     if ((rc = rn_alloc(f, &d_n, (size_t)V))) return fail(rc);
     std::vector<int64_t> hn(n, n + V);
@@ -691,7 +503,9 @@ extern "C" int resnmtf_fit_destroy(resnmtf_fit* fit) {
   if (fit->graph) cudaGraphDestroy(fit->graph);
   for (void* p : fit->allocs) rn_dev_free(fit->ctx, p);
   for (ViewHost& vh : fit->views) rn_data_release(vh.shared);
+  resnmtf_ctx* ctx = fit->ctx;
   delete fit;
+  rn_ctx_release(ctx);
   return RESNMTF_OK;
 }
 
@@ -802,6 +616,7 @@ static int data_create_common(resnmtf_ctx* ctx, int64_t n, int64_t p, const doub
   resnmtf_data* d = new (std::nothrow) resnmtf_data();
   RN_CHECK(d != nullptr, RESNMTF_E_NOMEM, "resnmtf_data_create: out of host memory");
   d->ctx = ctx;
+  ctx->refs.fetch_add(1);
   d->n = n;
   d->p = p;
   d->ldx = rn_round_up(n, RN_ROW_TILE);
@@ -871,7 +686,7 @@ extern "C" int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* da
     if (rc) return rc;
   }
   vh.shared = data;
-  data->refs += 1;
+  data->refs.fetch_add(1);
   vh.d.X = data->X;
   if (vh.d.X8) fit->plan_dirty = true;
   vh.d.X8 = nullptr;
@@ -936,6 +751,10 @@ extern "C" int resnmtf_fit_set_restrictions(resnmtf_fit* fit, const double* phi,
     for (size_t i = 0; i < VV; ++i) {
       const double x = src ? src[i] : 0.0;
       RN_CHECK(!(x < 0.0), RESNMTF_E_INVALID, std::string(name) + " must be a non-negative matrix");
+      // init_rest_mats() (R/update_steps.r:19-22) zeroes the diagonal before it symmetrises; a view coupled to itself
+      // would read its own factor rows while they are overwritten in place
+      RN_CHECK(!(x != 0.0 && i % ((size_t)fit->V + 1) == 0), RESNMTF_E_INVALID,
+               std::string(name) + " must have a zero diagonal (init_rest_mats, R/update_steps.r:12-24)");
       dst[i] = x;
     }
     return RESNMTF_OK;
@@ -1033,7 +852,7 @@ static int build_plan(resnmtf_fit* fit) {
     RnView& d = vh.d;
     // the one-pass fused kernel serves the views that qualify (fused_csize); the others of the fit run the
     // two-pass TMA kernels
-    int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->n_ranks) : 0;
+    int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->comm != nullptr) : 0;
     if (csz) {  // the fused kernel prefetches the phi gathers of at most RN_FU_MAXPART partner views
       int partners = 0;
       for (int w = 0; w < fit->V; ++w) {
@@ -1072,6 +891,7 @@ static int build_plan(resnmtf_fit* fit) {
       if (rn_env_int("RESNMTF_FU_TIMELINE", 0) && !d.fu_timeline) {
         if ((rc = rn_alloc(fit, &d.fu_timeline, (size_t)sms * 12))) return rc;
         if ((rc = rn_alloc(fit, &d.fu_trace, (size_t)((d.n + 7) / 8 + 8) * 32))) return rc;
+        if ((rc = rn_alloc(fit, &d.fu_waits, (size_t)sms * RN_FU_NCW * 2))) return rc;
       }
       if (!d.X8) {  // second copy of X in the 8-row-group layout (shared by every fit attached to the same data)
         const size_t x8_count = (size_t)d.ldx * d.pp8;
@@ -1079,13 +899,15 @@ static int build_plan(resnmtf_fit* fit) {
         if (vh.shared) {
           if (vh.shared->X8 && vh.shared->pp8 == d.pp8) {
             convert = false;
-          } else {
-            rn_dev_free(fit->ctx, vh.shared->X8);
-            vh.shared->X8 = nullptr;
+            d.X8 = vh.shared->X8;
+          } else if (!vh.shared->X8) {
             RN_CUDA(rn_dev_alloc(fit->ctx, (void**)&vh.shared->X8, x8_count * sizeof(double)));
             vh.shared->pp8 = d.pp8;
+            d.X8 = vh.shared->X8;
+          } else {  // the handle's copy has another width and other fits may be running on it: this fit keeps its own
+            if (!vh.x8_own && (rc = rn_alloc(fit, &vh.x8_own, x8_count, false))) return rc;
+            d.X8 = vh.x8_own;
           }
-          d.X8 = vh.shared->X8;
         } else {
           if (!vh.x8_own && (rc = rn_alloc(fit, &vh.x8_own, x8_count, false))) return rc;
           d.X8 = vh.x8_own;
@@ -1403,56 +1225,10 @@ static int handle_pause(resnmtf_fit* fit) {
   return prepare(fit);
 }
 
-extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, int64_t max_iters,
-                               int64_t* iters_done) {
-  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_run: fit is NULL");
-  int rc;
-  if ((rc = prepare(fit))) return rc;
-  cudaStream_t st = fit->ctx->stream;
-  const bool conv = n_iters < 0;
-  fit->h_ctrl.done = 0;
-  fit->h_ctrl.conv_mode = conv ? 1 : 0;
-  fit->h_ctrl.tol = tol;
-  fit->h_ctrl.hist_count = 0;
-  fit->h_ctrl.direct_passes = 0;
-  fit->h_ctrl.want_direct = 0;
-  if ((rc = push_ctrl(fit))) return rc;
-  fit->counters.kernel_launches = 0;
-  const int64_t it0 = fit->h_ctrl.iters;
-  RN_CUDA(cudaEventRecord(fit->ctx->ev0, st));
-  // sweeps enqueued between two reads of the device-side stop flag: a read costs a stream synchronisation (~30 us), a
-  // sweep launched after the flag fired returns at once (~3 us)
-  const int64_t conv_batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 32));
-  for (;;) {
-    const int64_t donei = fit->h_ctrl.iters - it0;
-    int64_t b;
-    if (!conv) {
-      b = std::min<int64_t>(n_iters - donei, fit->hist_cap);
-    } else {
-      b = conv_batch;
-      if (max_iters > 0) b = std::min(b, max_iters - donei);
-    }
-    if (b <= 0) break;
-    if ((rc = run_batch(fit, b))) return rc;
-    // fixed mode without AUTO hand-over pending needs no read-back until the end
-    if ((rc = pull_ctrl(fit))) return rc;
-    if (fit->h_ctrl.done == 3) {
-      if ((rc = handle_pause(fit))) return rc;
-    }
-    if (fit->h_ctrl.done == 1 || fit->h_ctrl.done == 2) break;
-  }
-  RN_CUDA(cudaEventRecord(fit->ctx->ev1, st));
-  if ((rc = pull_ctrl(fit))) return rc;
-  float ms = 0.f;
-  RN_CUDA(cudaEventElapsedTime(&ms, fit->ctx->ev0, fit->ctx->ev1));
-  fit->counters.device_ms = ms;
-  fit->counters.iterations = fit->h_ctrl.iters;
-  fit->counters.converged = fit->h_ctrl.done == 1;
-  fit->counters.impl = fit->impl;
-  fit->counters.direct_error_passes = fit->h_ctrl.direct_passes;
-  fit->counters.alg_bytes_per_iter = alg_bytes_per_iter(fit);
-  if (iters_done) *iters_done = fit->h_ctrl.iters - it0;
-  for (int v = 0; v < fit->V; ++v) {  // developer timeline of the last fused launch (RESNMTF_FU_TIMELINE=1)
+// Developer timeline of the last fused launch (RESNMTF_FU_TIMELINE=1): per-CTA stamps, the per-row-group trace of CTA 0
+// and the cycles every consumer warp spent waiting for X and for F_new, to stderr.  A no-op without the switch.
+static int rn_print_fused_timeline(resnmtf_fit* fit) {
+  for (int v = 0; v < fit->V; ++v) {
     const RnView& d = fit->views[v].d;
     if (!d.fu_timeline || !d.fu_csize) continue;
     const int grid = d.fu_clusters * d.fu_csize;
@@ -1516,7 +1292,75 @@ extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, in
                      cnt, period / cnt, wait_x / cnt, f_ph / cnt, wait_f / cnt, g_ph / cnt, pub2in / cnt, ep_exch / cnt,
                      ep_math / cnt, early / cnt);
     }
+    if (d.fu_waits) {  // cycles per row group a consumer warp waited for X (ring) and for F_new (epilogue), mean over CTAs
+      std::vector<long long> wt((size_t)grid * RN_FU_NCW * 2);
+      RN_CUDA(cudaMemcpy(wt.data(), d.fu_waits, wt.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      const double groups_per_cluster = (double)((d.n + 7) / 8) / d.fu_clusters;
+      std::fprintf(stderr, "  cycles per row group waited for X | for F_new, per consumer warp (mean over the %d CTAs):\n   ", grid);
+      for (int w = 0; w < RN_FU_NCW; ++w) {
+        double sx = 0, sf = 0;
+        for (int b = 0; b < grid; ++b) {
+          sx += (double)wt[((size_t)b * RN_FU_NCW + w) * 2];
+          sf += (double)wt[((size_t)b * RN_FU_NCW + w) * 2 + 1];
+        }
+        std::fprintf(stderr, " w%d %.0f|%.0f", w, sx / grid / groups_per_cluster, sf / grid / groups_per_cluster);
+      }
+      std::fprintf(stderr, "\n");
+    }
   }
+  return RESNMTF_OK;
+}
+
+extern "C" int resnmtf_fit_run(resnmtf_fit* fit, int64_t n_iters, double tol, int64_t max_iters,
+                               int64_t* iters_done) {
+  RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_run: fit is NULL");
+  int rc;
+  if ((rc = prepare(fit))) return rc;
+  cudaStream_t st = fit->ctx->stream;
+  const bool conv = n_iters < 0;
+  fit->h_ctrl.done = 0;
+  fit->h_ctrl.conv_mode = conv ? 1 : 0;
+  fit->h_ctrl.tol = tol;
+  fit->h_ctrl.hist_count = 0;
+  fit->h_ctrl.direct_passes = 0;
+  fit->h_ctrl.want_direct = 0;
+  if ((rc = push_ctrl(fit))) return rc;
+  fit->counters.kernel_launches = 0;
+  const int64_t it0 = fit->h_ctrl.iters;
+  RN_CUDA(cudaEventRecord(fit->ctx->ev0, st));
+  // sweeps enqueued between two reads of the device-side stop flag: a read costs a stream synchronisation (~30 us), a
+  // sweep launched after the flag fired returns at once (~3 us)
+  const int64_t conv_batch = std::max(1, rn_env_int("RESNMTF_CONV_BATCH", 32));
+  for (;;) {
+    const int64_t donei = fit->h_ctrl.iters - it0;
+    int64_t b;
+    if (!conv) {
+      b = std::min<int64_t>(n_iters - donei, fit->hist_cap);
+    } else {
+      b = conv_batch;
+      if (max_iters > 0) b = std::min(b, max_iters - donei);
+    }
+    if (b <= 0) break;
+    if ((rc = run_batch(fit, b))) return rc;
+    // fixed mode without AUTO hand-over pending needs no read-back until the end
+    if ((rc = pull_ctrl(fit))) return rc;
+    if (fit->h_ctrl.done == 3) {
+      if ((rc = handle_pause(fit))) return rc;
+    }
+    if (fit->h_ctrl.done == 1 || fit->h_ctrl.done == 2) break;
+  }
+  RN_CUDA(cudaEventRecord(fit->ctx->ev1, st));
+  if ((rc = pull_ctrl(fit))) return rc;
+  float ms = 0.f;
+  RN_CUDA(cudaEventElapsedTime(&ms, fit->ctx->ev0, fit->ctx->ev1));
+  fit->counters.device_ms = ms;
+  fit->counters.iterations = fit->h_ctrl.iters;
+  fit->counters.converged = fit->h_ctrl.done == 1;
+  fit->counters.impl = fit->impl;
+  fit->counters.direct_error_passes = fit->h_ctrl.direct_passes;
+  fit->counters.alg_bytes_per_iter = alg_bytes_per_iter(fit);
+  if (iters_done) *iters_done = fit->h_ctrl.iters - it0;
+  if (int trc = rn_print_fused_timeline(fit)) return trc;  // developer switch RESNMTF_FU_TIMELINE=1, else a no-op
   if (conv && fit->h_ctrl.done == 2)
     return rn_fail(RESNMTF_E_NAN, "mean error is NaN: missing value where TRUE/FALSE needed (R/main.r:55)");
   return RESNMTF_OK;

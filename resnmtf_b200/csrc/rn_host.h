@@ -1,0 +1,234 @@
+// Host-side declarations shared by the translation units of libresnmtf_b200.so: handles behind the C ABI
+// (include/resnmtf_b200.h), error plumbing, device allocation from the context's private pool, lazy NCCL binding.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/resnmtf_b200.h"
+#include "rn_types.h"
+
+#include <dlfcn.h>
+
+// NCCL is only needed by the row-sharded path, so it is resolved lazily with dlopen (no link-time
+// dependency): the handful of types / enum values used here are ABI-stable across NCCL 2.x.
+typedef struct rn_nccl_comm* rn_ncclComm_t;
+typedef struct { char internal[128]; } rn_ncclUniqueId;
+enum { RN_NCCL_SUCCESS = 0, RN_NCCL_SUM = 0, RN_NCCL_INT64 = 4, RN_NCCL_FLOAT64 = 8 };
+struct RnNccl {
+  void* handle = nullptr;
+  int (*GetUniqueId)(rn_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(rn_ncclComm_t*, int, rn_ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(rn_ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, rn_ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+inline RnNccl& rn_nccl() {
+  static RnNccl api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.GetUniqueId = (int (*)(rn_ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(rn_ncclComm_t*, int, rn_ncclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(rn_ncclComm_t))dlsym(api.handle, "ncclCommDestroy");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, rn_ncclComm_t, cudaStream_t))dlsym(
+          api.handle, "ncclAllReduce");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    }
+  }
+  return api;
+}
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+// thread-local message behind resnmtf_last_error() (defined in resnmtf_capi.cu)
+std::string& rn_err_slot();
+inline int rn_fail(int code, const std::string& msg) {
+  rn_err_slot() = msg;
+  return code;
+}
+
+#define RN_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return rn_fail(e__ == cudaErrorMemoryAllocation ? RESNMTF_E_NOMEM : RESNMTF_E_CUDA,     \
+                     std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+#define RN_NCCL(expr)                                                                                   \
+  do {                                                                                                  \
+    int r__ = (expr);                                                                                   \
+    if (r__ != RN_NCCL_SUCCESS)                                                                         \
+      return rn_fail(RESNMTF_E_COMM, std::string(#expr) + ": " + rn_nccl().GetErrorString(r__));        \
+  } while (0)
+
+#define RN_CHECK(cond, code, msg) \
+  do {                            \
+    if (!(cond)) return rn_fail(code, msg); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct resnmtf_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t l2_persist_bytes = 0;  // persisting-L2 carve-out granted to this device (0: unavailable / disabled)
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int rank = 0, n_ranks = 1;
+  rn_ncclComm_t comm = nullptr;  // non-null: every view of every fit on this context is ROW-SHARDED over the communicator's
+                                 // ranks -- also for a communicator of ONE rank, which runs the whole sharded code path
+                                 // (pack -> all-reduce -> stand-alone G epilogue) on a single GPU
+  // Device memory comes from the stream-ordered pool of the device with an unlimited release threshold: after the
+  // first fit the create / destroy path of a fit never reaches the driver's allocator (measured: cudaMalloc +
+  // cudaFree cost 3 ms per fit on one box and 15 ms on another -- more than the upload of the factors).
+  bool pooled = false;
+  cudaMemPool_t pool = nullptr;  // PRIVATE to this context (never the device's default pool, which other users of the
+                                 // process -- torch's cudaMallocAsync backend, other contexts -- share)
+  // The context outlives every fit / data handle created on it: they hold a reference, resnmtf_ctx_destroy only drops
+  // the creator's, and the last one out tears the context down.
+  std::atomic<int> refs{1};
+  // host -> device upload pipeline (two staging buffers, copy stream, events), created on first use and kept
+  double* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaStream_t copy_st = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, tiled[2] = {nullptr, nullptr};
+};
+
+inline cudaError_t rn_dev_alloc(resnmtf_ctx* ctx, void** p, size_t bytes) {
+  if (ctx->pooled) return cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+  return cudaMalloc(p, bytes);
+}
+inline cudaError_t rn_dev_free(resnmtf_ctx* ctx, void* p) {
+  if (!p) return cudaSuccess;
+  if (ctx->pooled) return cudaFreeAsync(p, ctx->stream);
+  return cudaFree(p);
+}
+
+// A view's X in the device layout, shareable between fits (the k-sweep of apply_resnmtf fits the same
+// data for every k, R/main.r:279-287): reference-counted, freed when the last holder lets go.
+struct resnmtf_data {
+  resnmtf_ctx* ctx = nullptr;
+  int64_t n = 0, p = 0, ldx = 0, pp = 0;
+  double* X = nullptr;
+  double* X8 = nullptr;  // 8-row-group copy for the one-pass fused kernel (built on demand by the first plan)
+  int64_t pp8 = 0;
+  double xnorm2 = 0.0;
+  std::atomic<int> refs{1};
+};
+
+void rn_ctx_release(resnmtf_ctx* ctx);  // resnmtf_capi.cu
+
+inline void rn_data_release(resnmtf_data* d) {
+  if (d && d->refs.fetch_sub(1) == 1) {
+    resnmtf_ctx* ctx = d->ctx;
+    cudaSetDevice(ctx->device);
+    rn_dev_free(ctx, d->X);
+    rn_dev_free(ctx, d->X8);
+    delete d;
+    rn_ctx_release(ctx);
+  }
+}
+
+struct ViewHost {
+  RnView d;  // device pointers + geometry (passed by value to the kernels)
+  resnmtf_data* shared = nullptr;  // non-null: X belongs to a shared data handle
+  size_t l2_window = 0;            // bytes at the head of X pinned in L2 (persisting access-policy window)
+  int impl = RESNMTF_IMPL_TMA;     // kernel family this view runs (a fit may mix FUSED and TMA views)
+  double* x8_own = nullptr;        // X8 owned by the fit (views without a shared data handle)
+  bool has_data = false, has_factors = false;
+  std::vector<int32_t*> rowmaps, colmaps;  // [V] device maps of this view into view w (or null)
+  double* xpart = nullptr;                 // ||X||^2 partials
+  int32_t* xticket = nullptr;
+};
+
+struct resnmtf_fit {
+  resnmtf_ctx* ctx = nullptr;
+  int V = 0;
+  std::vector<ViewHost> views;
+  std::vector<void*> allocs;
+  RnFit d;               // passed by value to the kernels
+  RnView* d_views = nullptr;
+  RnCtrl* d_ctrl = nullptr;
+  double *d_phi = nullptr, *d_xi = nullptr, *d_psi = nullptr;
+  const int32_t** d_rowmap = nullptr;
+  const int32_t** d_colmap = nullptr;
+  int8_t *d_rowmode = nullptr, *d_colmode = nullptr;
+  std::vector<const int32_t*> h_rowmap, h_colmap;
+  std::vector<int8_t> h_rowmode, h_colmode;
+  std::vector<double> h_phi, h_xi, h_psi;
+  double* d_hist = nullptr;
+  int64_t hist_cap = 4096;
+  std::vector<double> errors;  // All_Error
+  int err_mode = RESNMTF_ERR_AUTO;
+  int impl_req = RESNMTF_IMPL_AUTO;
+  int impl = RESNMTF_IMPL_TMA;
+  bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
+  bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
+  bool auto_direct = false; // AUTO error mode has handed over to the direct residual pass
+  int comm_rc = 0;          // first NCCL failure seen while enqueueing (row-sharded path)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int64_t launches_per_iter = 0;
+  resnmtf_counters counters{};
+  RnCtrl h_ctrl{};
+};
+
+template <typename T>
+inline int rn_alloc(resnmtf_fit* f, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  RN_CUDA(rn_dev_alloc(f->ctx, &p, bytes));
+  f->allocs.push_back(p);
+  if (zero) RN_CUDA(cudaMemsetAsync(p, 0, bytes, f->ctx->stream));
+  *out = static_cast<T*>(p);
+  return RESNMTF_OK;
+}
+
+inline int rn_free(resnmtf_fit* f, void* p) {
+  if (!p) return RESNMTF_OK;
+  auto it = std::find(f->allocs.begin(), f->allocs.end(), p);
+  if (it != f->allocs.end()) f->allocs.erase(it);
+  RN_CUDA(rn_dev_free(f->ctx, p));
+  return RESNMTF_OK;
+}
+
+static inline int64_t rn_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+inline int rn_env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : dflt;
+}
+
+// in-place sum over the ranks of a row-sharded context, on the context's stream (graph-capturable)
+inline int rn_allreduce(resnmtf_ctx* ctx, void* buf, size_t count, bool is_int64 = false) {
+  if (!ctx->comm) return RESNMTF_OK;
+  RN_NCCL(rn_nccl().AllReduce(buf, buf, count, is_int64 ? RN_NCCL_INT64 : RN_NCCL_FLOAT64, RN_NCCL_SUM, ctx->comm,
+                              ctx->stream));
+  return RESNMTF_OK;
+}
+
+// host twin of rn_fidx (rn_kernels.cuh): position of F[r, c] in the swizzled 64-row panel layout
+static inline int64_t rn_fidx_host(int64_t r, int c, int kp) {
+  const int sigma = ((c & 1) << 2) | (c & 2);
+  return ((r >> 6) * kp + c) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ sigma) + (r & 1);
+}
+

@@ -74,9 +74,10 @@ struct RnView {
   // Tpart is then [fu_clusters][pp8][kp], FFpart [fu_clusters][k*k+k], GGpart [ceil(pp/64)][2*k*k+k]
   double* X8;
   int64_t pp8;
-  int32_t fu_csize, fu_clusters;  // CTAs per cluster (1, 2 or 4; 0: view not on the fused path), clusters in the grid
+  int32_t fu_csize, fu_clusters;  // CTAs per cluster (1..8; 0: view not on the fused path), clusters in the grid
   long long* fu_trace;            // optional [row groups of cluster 0][8] per-group stamps of CTA 0 (same switch)
   long long* fu_timeline;         // optional [grid][12] %globaltimer stamps of the last launch (RESNMTF_FU_TIMELINE=1)
+  long long* fu_waits;            // optional [grid][9 consumer warps][2] cycles waited for X / for F_new (same switch)
 };
 
 struct RnFit {

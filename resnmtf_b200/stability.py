@@ -56,8 +56,9 @@ test_cond.__test__ = False  # not a pytest test
 
 
 def number_biclusters(results):
-    """R/stability_analysis.r:94-99."""
-    return float(sum(x.sum() for x in results["row_clusters"]))
+    """R/stability_analysis.r:94-99.  With no_clusts the result list carries no row_clusters (R/main.r:115-120):
+    results$row_clusters is NULL there, lapply over NULL is empty and the count is 0."""
+    return float(sum(x.sum() for x in (results.get("row_clusters") or [])))
 
 
 def _sample(rng, n, size):

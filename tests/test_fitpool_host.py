@@ -194,3 +194,17 @@ def test_pool_keeps_tasks_of_one_affinity_key_on_one_gpu_and_lets_idle_gpus_stea
     ran.clear()
     pool.run([(1.0, unit(f"fit{i}", 0.05), (), "fit", "data") for i in range(6)])
     assert len({w for _, w in ran}) == 3
+
+
+def test_fixed_k_with_no_clusts_and_default_stability_returns_the_factors(monkeypatch, capsys):
+    """apply_resnmtf(k_val = 3, no_clusts = TRUE) with the default stability = TRUE: the no_clusts result list holds
+    only the three factor lists (R/main.r:115-120), number_biclusters() of a list without row_clusters is 0
+    (R/stability_analysis.r:94-99) and stability_check prints "No biclusters detected!" and hands the factors back
+    (:308-312) -- it must not fail on the missing key."""
+    views, _ = synth.block_views(1, block=60, n_blocks=3, seed=13)
+    with monkeypatch.context() as mp:
+        fake_device.install(mp, 1)
+        out = apply_resnmtf(views, k_val=3, no_clusts=True, rng=np.random.default_rng(4), max_iters=40)
+    assert sorted(out.keys()) == ["output_f", "output_g", "output_s"]
+    assert out["output_f"][0].shape == (180, 3)
+    assert "No biclusters detected!" in capsys.readouterr().out

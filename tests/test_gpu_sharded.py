@@ -1,5 +1,6 @@
-"""Row-sharded view over 2 GPUs (NCCL all-reduce of [X'F | F'F | colSums(F)] per sweep) against the unsharded
-oracle.  Needs >= 2 visible GPUs: run with  gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu"""
+"""Row-sharded view (NCCL all-reduce of [X'F | F'F | colSums(F)] per sweep) against the unsharded oracle: the whole
+code path on ONE GPU through a communicator of one rank, and over 2 GPUs (those tests need >= 2 visible GPUs: run with
+gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu)."""
 import os
 import socket
 import sys
@@ -79,6 +80,48 @@ def worker(rank, world, port, out_dir, impl, err_mode, k):
     np.save(os.path.join(out_dir, f"worst{rank}.npy"), np.array([worst, worst_n]))
     dist.barrier()
     dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("impl,err_mode,k", [(L.IMPL_AUTO, L.ERR_AUTO, 8), (L.IMPL_TMA, L.ERR_AUTO, 5),
+                                             (L.IMPL_DMMA, L.ERR_DIRECT, 3), (L.IMPL_DFMA, L.ERR_DIRECT, 9),
+                                             (L.IMPL_DFMA, L.ERR_ALGEBRAIC, 4)])
+def test_sharded_code_path_on_a_one_rank_communicator(impl, err_mode, k):
+    """The WHOLE row-sharded code path on a 1-GPU box: a context that joined a communicator of ONE rank runs
+    rn_g_step (T to HBM) -> rn_pack_ff -> ncclAllReduce -> stand-alone rn_g_epilogue, the all-reduced ||X||^2, column
+    sums and direct residual, exactly as an 8-rank run does -- against the oracle sweep by sweep (1e-9), and the
+    fused one-pass kernel must NOT be picked (the view is sharded)."""
+    from helpers import rel_err
+    from oracle import resnmtf_oracle as O
+    from resnmtf_b200.device import Context, DeviceFit
+
+    x, f, s, g = problem(k)
+    z = np.zeros((1, 1))
+    states = []
+    ref = O.res_nmtf_loop([x], None, None, [None], [None], [f], [s], [g], [k], z, z, z, n_iters=6,
+                          trace=lambda t, cf, cs, cg, cl, cm, er: states.append(
+                              (cf[0].copy(), cs[0].copy(), cg[0].copy(), cl[0].copy(), cm[0].copy(), er.copy())))
+    with Context(0) as ctx:
+        ctx.join(Context.comm_id_create(), 0, 1)
+        fit = DeviceFit(ctx, [x.shape[0]], [x.shape[1]], [k])
+        fit.set_options(err_mode=err_mode, impl=impl)
+        fit.set_data(0, x)
+        fit.set_factors(0, f, s, g)
+        worst = 0.0
+        for t in range(6):
+            fit.step()
+            fl, sl, gl, lam, mu = fit.get_factors(0)
+            errs, _ = fit.view_errors()
+            cf, cs, cg, cl, cm, oerr = states[t]
+            for a, r in ((fl, cf), (sl, cs), (gl, cg), (lam, cl), (mu, cm), (errs, oerr)):
+                worst = max(worst, rel_err(a, r))
+        c = fit.counters()
+        assert c["impl"] != L.IMPL_FUSED  # a sharded view never takes the one-GPU one-pass kernel
+        assert c["kernel_launches"] >= 5  # F step, G stream, pack, all-reduce, G epilogue (+ residual passes)
+        fit.normalise()
+        fn, sn, gn, _, _ = fit.get_factors(0)
+        worst_n = max(rel_err(fn, ref["output_f"][0]), rel_err(sn, ref["output_s"][0]), rel_err(gn, ref["output_g"][0]))
+        fit.close()
+    assert worst <= 1e-9 and worst_n <= 1e-9, (worst, worst_n)
 
 
 @pytest.mark.skipif(L.device_count() < WORLD, reason="needs 2 GPUs")
