@@ -116,6 +116,40 @@ int resnmtf_data_create_device(resnmtf_ctx* ctx, int64_t n, int64_t p, const dou
 int resnmtf_data_destroy(resnmtf_data* data);
 int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* data);
 
+/* ---- data handles on the device: prep, shuffles, sub-samples ------------------------------- */
+
+/* resnmtf_data_create followed by make_non_neg_inner() and matrix_normalisation() (R/utils.r:20-27, 86-88) on the device:
+ * every column is shifted by |min(0, min(column))| and divided by its sum.  *was_negative (may be NULL) is set to 1 when
+ * a negative entry was seen -- the caller then issues the reference's warning "Matrix is not non-negative. Has been made
+ * non-negative." (R/utils.r:24). */
+int resnmtf_data_create_prepped(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
+                                int32_t* was_negative, resnmtf_data** out);
+int resnmtf_data_shape(resnmtf_data* data, int64_t* n, int64_t* p);
+/* The view back on the host, column-major with leading dimension ld (e.g. the prepped data for R-side post-processing). */
+int resnmtf_data_download(resnmtf_data* data, double* x, int64_t ld);
+/* colSums (length p) and rowSums (length n) of the view; either pointer may be NULL. */
+int resnmtf_data_sums(resnmtf_data* data, double* col_sums, double* row_sums);
+/* shuffle_view() (R/obtain_bicl.r:11-22): a new handle holding matrix(sample(x), nrow, ncol) -- ALL entries permuted by
+ * a keyed bijection of the index range (a function of `seed` only; the reference draws from R's global stream) --
+ * reshuffled until no row and no column sums to zero.  renormalise != 0 applies the prep apply_resnmtf() gives the
+ * shuffled views (R/obtain_bicl.r:35 -> check_inputs).  *attempts (may be NULL) receives the number of shuffles. */
+int resnmtf_data_shuffle(resnmtf_data* src, uint64_t seed, int renormalise, int64_t* attempts, resnmtf_data** out);
+/* x[rows, cols] (0-based indices) as a new handle: the sub-samples of stability_repeat() (R/stability_analysis.r:215-253)
+ * are gathered from the resident view; no re-normalisation (the reference does none, quirk Q10). */
+int resnmtf_data_subsample(resnmtf_data* src, const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t n_cols,
+                           resnmtf_data** out);
+/* A copy of the view (and of its cached SVD triplets) on another context's GPU, device to device. */
+int resnmtf_data_copy(resnmtf_data* src, resnmtf_ctx* dst_ctx, resnmtf_data** out);
+
+/* ---- SVD initialisation ------------------------------------------------------------ */
+
+/* What init_mats_inner() (R/update_steps.r:92-95) takes from svd(x): |U[, 1:k]| (n x k), d[1:k], |V[, 1:k]| (p x k),
+ * column-major, computed on the device from the Gram matrix of the smaller side (FP64 tensor-core product), its top
+ * eigenpairs (Chebyshev-filtered subspace iteration with locking, residuals at rounding level of the matrix norm) and one
+ * more pass over the view for the other side.  Computed once per handle to width min(16, n, p) and cached: the fits of a
+ * k-sweep slice the same triplets.  Any output pointer may be NULL. */
+int resnmtf_data_svd_topk(resnmtf_data* data, int k, double* u, double* d, double* v);
+
 /* Initial factors of view v: F n x k, S k x k, G p x k, lambda k, mu k (what init_mats(),
  * R/update_steps.r:36-66, hands to the loop).  lambda / mu may be NULL: they are then set to
  * colSums(F) / colSums(G) as R/update_steps.r:53-54 does.  Resets the iteration counter. */
@@ -183,12 +217,99 @@ int resnmtf_jsd_pairs(resnmtf_ctx* ctx, const double* vecs, int64_t n, int32_t m
                       const double* bw, const double* vmax, const int32_t* pair_a, const int32_t* pair_b,
                       int64_t n_pairs, double* out);
 
+/* ---- fan-out: independent fits over the GPUs of a pool ----------------------------------- */
+
+/* One default apply_resnmtf() call is 66 convergence loops: per k of the sweep one fit and num_repeats shuffled refits
+ * (R/main.r:270-299, R/obtain_bicl.r:31-42), then per stability resample the same again
+ * (R/stability_analysis.r:302-338); the reference runs them nested and serially (its %dopar% over k is unreachable).
+ * Each of them is a UNIT below.  A pool owns one context and -- during resnmtf_batch_run -- one native worker thread per
+ * GPU; the views of a data set are uploaded once and copied GPU to GPU on first use. */
+typedef struct resnmtf_pool resnmtf_pool;
+
+/* devices == NULL: the first n_devices visible GPUs (n_devices <= 0: all of them). */
+int resnmtf_pool_create(const int* devices, int n_devices, resnmtf_pool** out);
+int resnmtf_pool_destroy(resnmtf_pool* pool);
+int resnmtf_pool_size(resnmtf_pool* pool);
+/* Context of GPU `gpu` of the pool (owned by the pool). */
+resnmtf_ctx* resnmtf_pool_ctx(resnmtf_pool* pool, int gpu);
+/* Registers the views of one data set (the `data` list of apply_resnmtf) under `key`.  _put: handles that already
+ * live on one of the pool's contexts (the pool takes its own reference); _put_host: host matrices, uploaded to the first
+ * GPU, with prep != 0 through make_non_neg_inner + matrix_normalisation (resnmtf_data_create_prepped). */
+int resnmtf_pool_put(resnmtf_pool* pool, int key, int n_views, resnmtf_data* const* views);
+int resnmtf_pool_put_host(resnmtf_pool* pool, int key, int n_views, const int64_t* n, const int64_t* p,
+                          const double* const* x, const int64_t* ld, int prep, int32_t* was_negative);
+/* View `view` of set `key` on GPU `gpu` of the pool (copied there on first use); borrowed, owned by the pool. */
+int resnmtf_pool_get(resnmtf_pool* pool, int key, int gpu, int view, resnmtf_data** out);
+int resnmtf_pool_drop(resnmtf_pool* pool, int key);
+
+#define RESNMTF_DERIVE_NONE 0
+#define RESNMTF_DERIVE_SUBSAMPLE 1 /* x[rows, cols] first (stability_repeat, R/stability_analysis.r:215-253)            */
+#define RESNMTF_DERIVE_SHUFFLE 2   /* then shuffle_view on every view (obtain_shuffled_f, R/obtain_bicl.r:31-42)        */
+
+typedef struct resnmtf_map {  /* one resnmtf_fit_set_shared_map call */
+  int32_t kind, v, w;
+  const int32_t* idx_v;
+  const int32_t* idx_w;
+  int64_t len;
+} resnmtf_map;
+
+/* One res_nmtf_inner() core: [derive the data] -> initial factors -> loop of R/main.r:50-109 -> normalisation_check.
+ * Per-view arrays have one entry per view of the data set; host buffers are borrowed until resnmtf_batch_run returns. */
+typedef struct resnmtf_unit {
+  /* ---- inputs ---- */
+  int32_t data_key;             /* data set registered with resnmtf_pool_put(_host)                                    */
+  int32_t derive;               /* RESNMTF_DERIVE_* bits                                                                */
+  const int32_t* const* rows;   /* SUBSAMPLE: per view, 0-based row / column indices and their counts                   */
+  const int64_t* n_rows;
+  const int32_t* const* cols;
+  const int64_t* n_cols;
+  uint64_t seed;                /* SHUFFLE: key of the permutation (view v uses a function of seed and v)               */
+  int32_t renormalise;          /* SHUFFLE: re-prep the shuffled views as apply_resnmtf does (R/obtain_bicl.r:35)        */
+  int32_t n_maps;
+  const int32_t* k;             /* k_vec                                                                                */
+  const double* const* init_f;  /* explicit initial factors per view (R/update_steps.r:49-60) -- all three or none:     */
+  const double* const* init_s;  /*   none = the SVD initialisation on the device (resnmtf_data_svd_topk) with ...        */
+  const double* const* init_g;
+  const double* const* noise;   /* ... per view the k x k draw abs(mvrnorm(k, 0, 0.05 I)) of R/update_steps.r:96-99      */
+                                /*   made by the caller in the reference's order (NULL: no noise term)                   */
+  const double* phi;            /* n_views x n_views, symmetrised (init_rest_mats); NULL = zero                         */
+  const double* xi;
+  const double* psi;
+  const resnmtf_map* maps;      /* shared-name index maps, n_maps of them                                               */
+  int64_t n_iters;              /* as resnmtf_fit_run                                                                   */
+  double tol;
+  int64_t max_iters;
+  int32_t err_mode, impl;       /* as resnmtf_fit_set_options                                                           */
+  /* ---- outputs (host buffers of the caller; any pointer may be NULL) ---- */
+  double* const* out_f;         /* normalised factors (normalisation_check, R/utils.r:176-195)                          */
+  double* const* out_s;
+  double* const* out_g;
+  double* const* out_lambda;    /* lambda / mu as the loop left them (R/main.r:137-138)                                 */
+  double* const* out_mu;
+  double* errors;               /* All_Error (R/main.r:134): first min(errors_cap, n_errors) values                     */
+  int64_t errors_cap;
+  int64_t n_errors;
+  int64_t iters;                /* sweeps done                                                                          */
+  int32_t status;               /* RESNMTF_OK or the RESNMTF_E_* code of this unit                                      */
+  int32_t gpu;                  /* GPU of the pool that ran it                                                          */
+  double seconds;               /* wall time of the unit on its worker thread                                           */
+  char message[200];            /* resnmtf_last_error() of the worker thread when status != 0                           */
+} resnmtf_unit;
+
+/* Runs the units, longest first, on one native worker thread per GPU of the pool (no interpreter, no host language
+ * involved), and returns when all are done: RESNMTF_OK, or the code of the first failed unit (every unit carries its
+ * own status).  What a unit returns does not depend on the GPU that ran it or on the number of GPUs. */
+int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_units);
+/* sizeof(resnmtf_unit) as this library was built: lets a binding verify its own declaration of the struct. */
+int resnmtf_unit_size(void);
+
 /* ---- row-sharded view across ranks (one process per GPU; NCCL all-reduce of the p x k partials) ---- */
 
 /* Size of the opaque NCCL unique id and its creation on rank 0 (to be broadcast by the host). */
 int resnmtf_comm_id_size(void);
 int resnmtf_comm_id_create(void* id_out);
 /* Joins the communicator (NCCL is resolved with dlopen at this point; RESNMTF_E_COMM when it is missing).
+ * n_ranks == 1 is allowed and runs the complete sharded code path on one GPU.
  * After this, every view of every fit created on ctx is treated as ROW-SHARDED: n[v] passed to fit_create
  * is the local row count (whole 64-row panels except on the last rank), F rows are local, G/S/lambda/mu
  * are replicated; per sweep [X'F | F'F | colSums(F)] is all-reduced once (p*k + k*k + k doubles) and the

@@ -27,6 +27,10 @@ EXPORTS = (
     "resnmtf_fit_create", "resnmtf_fit_destroy", "resnmtf_fit_set_data", "resnmtf_fit_set_data_device",
     "resnmtf_data_create", "resnmtf_data_create_device", "resnmtf_data_destroy", "resnmtf_fit_attach_data",
     "resnmtf_jsd_pairs",
+    "resnmtf_data_create_prepped", "resnmtf_data_shape", "resnmtf_data_download", "resnmtf_data_sums",
+    "resnmtf_data_shuffle", "resnmtf_data_subsample", "resnmtf_data_copy", "resnmtf_data_svd_topk",
+    "resnmtf_pool_create", "resnmtf_pool_destroy", "resnmtf_pool_size", "resnmtf_pool_ctx", "resnmtf_pool_put",
+    "resnmtf_pool_put_host", "resnmtf_pool_get", "resnmtf_pool_drop", "resnmtf_batch_run", "resnmtf_unit_size",
     "resnmtf_fit_set_factors", "resnmtf_fit_set_restrictions", "resnmtf_fit_set_shared_map",
     "resnmtf_fit_set_options", "resnmtf_fit_run", "resnmtf_fit_step", "resnmtf_fit_get_factors",
     "resnmtf_fit_normalise", "resnmtf_fit_get_errors", "resnmtf_fit_get_view_errors",
@@ -44,6 +48,32 @@ class Counters(C.Structure):
         ("direct_error_passes", C.c_int64),
         ("converged", C.c_int32),
         ("impl", C.c_int32),
+    ]
+
+
+DERIVE_NONE, DERIVE_SUBSAMPLE, DERIVE_SHUFFLE = 0, 1, 2
+
+
+class Map(C.Structure):
+    """resnmtf_map"""
+    _fields_ = [("kind", C.c_int32), ("v", C.c_int32), ("w", C.c_int32), ("idx_v", C.c_void_p), ("idx_w", C.c_void_p),
+                ("len", C.c_int64)]
+
+
+class Unit(C.Structure):
+    """resnmtf_unit (include/resnmtf_b200.h)"""
+    _fields_ = [
+        ("data_key", C.c_int32), ("derive", C.c_int32),
+        ("rows", C.c_void_p), ("n_rows", C.c_void_p), ("cols", C.c_void_p), ("n_cols", C.c_void_p),
+        ("seed", C.c_uint64), ("renormalise", C.c_int32), ("n_maps", C.c_int32),
+        ("k", C.c_void_p), ("init_f", C.c_void_p), ("init_s", C.c_void_p), ("init_g", C.c_void_p), ("noise", C.c_void_p),
+        ("phi", C.c_void_p), ("xi", C.c_void_p), ("psi", C.c_void_p), ("maps", C.c_void_p),
+        ("n_iters", C.c_int64), ("tol", C.c_double), ("max_iters", C.c_int64),
+        ("err_mode", C.c_int32), ("impl", C.c_int32),
+        ("out_f", C.c_void_p), ("out_s", C.c_void_p), ("out_g", C.c_void_p), ("out_lambda", C.c_void_p),
+        ("out_mu", C.c_void_p), ("errors", C.c_void_p), ("errors_cap", C.c_int64), ("n_errors", C.c_int64),
+        ("iters", C.c_int64), ("status", C.c_int32), ("gpu", C.c_int32), ("seconds", C.c_double),
+        ("message", C.c_char * 200),
     ]
 
 
@@ -93,6 +123,24 @@ def load():
         "resnmtf_data_destroy": (C.c_int, [vp]),
         "resnmtf_jsd_pairs": (C.c_int, [vp, vp, i64, i32, i64, vp, vp, vp, vp, i64, vp]),
         "resnmtf_fit_attach_data": (C.c_int, [vp, C.c_int, vp]),
+        "resnmtf_data_create_prepped": (C.c_int, [vp, i64, i64, vp, i64, pi32, C.POINTER(vp)]),
+        "resnmtf_data_shape": (C.c_int, [vp, pi64, pi64]),
+        "resnmtf_data_download": (C.c_int, [vp, vp, i64]),
+        "resnmtf_data_sums": (C.c_int, [vp, vp, vp]),
+        "resnmtf_data_shuffle": (C.c_int, [vp, C.c_uint64, C.c_int, pi64, C.POINTER(vp)]),
+        "resnmtf_data_subsample": (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(vp)]),
+        "resnmtf_data_copy": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "resnmtf_data_svd_topk": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "resnmtf_pool_create": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+        "resnmtf_pool_destroy": (C.c_int, [vp]),
+        "resnmtf_pool_size": (C.c_int, [vp]),
+        "resnmtf_pool_ctx": (vp, [vp, C.c_int]),
+        "resnmtf_pool_put": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "resnmtf_pool_put_host": (C.c_int, [vp, C.c_int, C.c_int, pi64, pi64, vp, pi64, C.c_int, pi32]),
+        "resnmtf_pool_get": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "resnmtf_pool_drop": (C.c_int, [vp, C.c_int]),
+        "resnmtf_batch_run": (C.c_int, [vp, vp, C.c_int]),
+        "resnmtf_unit_size": (C.c_int, []),
         "resnmtf_fit_set_factors": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
         "resnmtf_fit_set_restrictions": (C.c_int, [vp, vp, vp, vp]),
         "resnmtf_fit_set_shared_map": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, i64]),
@@ -113,6 +161,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.resnmtf_unit_size() != C.sizeof(Unit):
+        raise RuntimeError("resnmtf_b200: the ctypes declaration of resnmtf_unit does not match the library's")
     _lib = lib
     return lib
 

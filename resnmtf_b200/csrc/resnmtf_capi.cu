@@ -655,6 +655,59 @@ static int data_create_common(resnmtf_ctx* ctx, int64_t n, int64_t p, const doub
   return RESNMTF_OK;
 }
 
+// An empty (zeroed) view in the panel layout for the kernels of rn_native.cu to fill, and its completion:
+// data_norms = ||X||_F^2 (R/main.r:48), all-reduced when the context is row-sharded.
+int rn_data_alloc(resnmtf_ctx* ctx, int64_t n, int64_t p, resnmtf_data** out) {
+  RN_CHECK(ctx && out, RESNMTF_E_INVALID, "rn_data_alloc: NULL argument");
+  RN_CHECK(n >= 1 && p >= 1, RESNMTF_E_INVALID, "rn_data_alloc: bad shape");
+  RN_CUDA(cudaSetDevice(ctx->device));
+  resnmtf_data* d = new (std::nothrow) resnmtf_data();
+  RN_CHECK(d != nullptr, RESNMTF_E_NOMEM, "rn_data_alloc: out of host memory");
+  d->ctx = ctx;
+  ctx->refs.fetch_add(1);
+  d->n = n;
+  d->p = p;
+  d->ldx = rn_round_up(n, RN_ROW_TILE);
+  d->pp = rn_round_up(p, 32);
+  const size_t xbytes = (size_t)d->ldx * d->pp * sizeof(double);
+  cudaError_t e = rn_dev_alloc(ctx, (void**)&d->X, xbytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d->X, 0, xbytes, ctx->stream);
+  if (e != cudaSuccess) {
+    rn_data_release(d);
+    return rn_fail(e == cudaErrorMemoryAllocation ? RESNMTF_E_NOMEM : RESNMTF_E_CUDA,
+                   std::string("rn_data_alloc: ") + cudaGetErrorString(e));
+  }
+  *out = d;
+  return RESNMTF_OK;
+}
+
+int rn_data_seal(resnmtf_data* d) {
+  resnmtf_ctx* ctx = d->ctx;
+  RN_CUDA(cudaSetDevice(ctx->device));
+  double* scratch = nullptr;  // [0..7] scal, then 1024 partials, then the ticket
+  RN_CUDA(rn_dev_alloc(ctx, (void**)&scratch, (8 + 1024 + 2) * sizeof(double)));
+  RN_CUDA(cudaMemsetAsync(scratch, 0, (8 + 1024 + 2) * sizeof(double), ctx->stream));
+  RnView g;
+  std::memset(&g, 0, sizeof(g));
+  g.n = d->n;
+  g.p = d->p;
+  g.ldx = d->ldx;
+  g.pp = d->pp;
+  g.row_tiles = (int)(d->ldx / RN_ROW_TILE);
+  g.X = d->X;
+  g.scal = scratch;
+  rn_xnorm2<<<1024, 256, 0, ctx->stream>>>(g, scratch + 8, reinterpret_cast<int32_t*>(scratch + 8 + 1024));
+  cudaError_t e = cudaGetLastError();
+  int rc = e == cudaSuccess ? rn_allreduce(ctx, g.scal, 1) : RESNMTF_OK;
+  if (e == cudaSuccess && rc == RESNMTF_OK)
+    e = cudaMemcpyAsync(&d->xnorm2, scratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  rn_dev_free(ctx, scratch);
+  if (rc) return rc;
+  if (e != cudaSuccess) return rn_fail(RESNMTF_E_CUDA, std::string("rn_data_seal: ") + cudaGetErrorString(e));
+  return RESNMTF_OK;
+}
+
 extern "C" int resnmtf_data_create(resnmtf_ctx* ctx, int64_t n, int64_t p, const double* x, int64_t ld,
                                    resnmtf_data** out) {
   return data_create_common(ctx, n, p, x, ld, false, out);

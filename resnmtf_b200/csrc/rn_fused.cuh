@@ -47,28 +47,23 @@
 #define RN_FU_CBLOCKS 63                                  // 16-column blocks per CTA
 #define RN_FU_CCOLS (16 * RN_FU_CBLOCKS)                  // data columns per CTA (1008)
 #define RN_FU_GROUP_BYTES (RN_FU_CBLOCKS * 1024)          // a CTA's share of one row group (63 KB)
-// A consumer warp's share of a row group (7 blocks = 7 KB) is loaded as RN_FU_NH pieces with their own mbarrier
-// pair: a piece is released -- and its reload issued -- as soon as the G phase is through with it, which lengthens
-// the time a reload may take before the F phase three groups later stalls on it (one piece: G + F phase = 1.35 us;
-// two pieces: ~1.7 us).  Measured on C2 (per-warp wait counters, RESNMTF_FU_TIMELINE=1): the consumer warps do NOT
-// wait for X -- ~105 cycles per group, the cost of one satisfied mbarrier wait -- so every extra piece only adds such
-// a wait: 149 / 155.5 / 184 us per update-iteration with 1 / 2 / 3 pieces.  One piece is shipped.
-#ifndef RN_FU_NH
-#define RN_FU_NH 1
-#endif
-// Early probes: a satisfied mbarrier.try_wait costs ~100 cycles of latency, and the three consumer warps of a
+#define RN_FU_NSLOT (3 * RN_FU_NCW)                       // (row group in the ring, consumer warp) slots
+#define RN_FU_RING_BYTES (3 * RN_FU_GROUP_BYTES)          // 189 KB = 3 row groups
+#define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
+// Early probes: a satisfied mbarrier.try_wait still costs ~100 cycles of latency (measured: the consumer warps spend
+// ~105 cycles per row group in the wait for X although X is always there), and the three consumer warps of a
 // sub-partition reach their waits together, so the FP64 pipe idles behind them.  A non-blocking test_wait issued a few
 // MMAs before the phase boundary lets that latency pass under the MMAs; the blocking wait is only taken when the probe
-// came back negative.
+// came back negative.  (Also measured and dropped: splitting a warp's 7 KB share of a row group into 2 / 3 pieces with
+// their own barriers so that a piece is reloaded earlier -- 149 / 155.5 / 184 us per update-iteration with 1 / 2 / 3
+// pieces: nobody waits for X, every piece only adds a barrier wait -- and one producer lane per consumer warp instead
+// of the sequential producer loop: +4 %, the spinning lanes take issue slots from the epilogue warp next to them.)
 #ifndef RN_FU_PROBE
 #define RN_FU_PROBE 1
 #endif
 #ifndef RN_FU_PROBE_LEAD
-#define RN_FU_PROBE_LEAD 4  // F phase: MMA pairs (of 14) / G phase: half blocks before the phase ends
+#define RN_FU_PROBE_LEAD 4  // F phase: MMA pairs (of 14) / G phase: half as many blocks (of 7) before the phase ends
 #endif
-#define RN_FU_NSLOT (3 * RN_FU_NCW * RN_FU_NH)            // (row group in the ring, consumer warp, piece) slots
-#define RN_FU_RING_BYTES (3 * RN_FU_GROUP_BYTES)          // 189 KB = 3 row groups
-#define RN_FU_MAXC 8                                      // largest (portable) cluster: columns <= 8064
 
 // doubles of shared memory behind the ring (see the carve-up in the kernel)
 #define RN_FU_MAXPART 7                                   // most phi partners of a view on the fused path
@@ -78,14 +73,6 @@
    3 * RN_FU_MAXPART * 64 + 4 * 64)
 static inline size_t rn_fused_smem() {
   return (size_t)RN_FU_RING_BYTES + (size_t)RN_FU_AUX_DOUBLES * 8 + (2 * RN_FU_NSLOT + 6 + 8) * 8 + 16;
-}
-
-// first block and number of blocks of piece h of a warp's 7-block share
-__host__ __device__ constexpr int rn_fu_hb(int h) {
-  return RN_FU_NH == 1 ? 0 : RN_FU_NH == 2 ? (h == 0 ? 0 : 4) : (h == 0 ? 0 : h == 1 ? 3 : 5);
-}
-__host__ __device__ constexpr int rn_fu_hn(int h) {
-  return RN_FU_NH == 1 ? 7 : RN_FU_NH == 2 ? (h == 0 ? 4 : 3) : (h == 0 ? 3 : 2);
 }
 
 // position (in doubles) of X[r][j] in the X8 layout with pp8 (even) columns
@@ -152,18 +139,18 @@ __device__ __forceinline__ void rn_mbar_wait_cluster(uint64_t* bar, uint32_t par
       "r"(parity)
       : "memory");
 }
-// non-blocking probe of an mbarrier phase (acquire at CTA scope like the blocking wait)
-__device__ __forceinline__ bool rn_mbar_test(uint64_t* bar, uint32_t parity) {
+// Non-blocking probe of an mbarrier phase.  Deliberately NOT volatile and without a memory clobber: the compiler
+// and ptxas may schedule it among the MMAs around it, and the predicate is only consumed at the phase boundary.  The
+// caller orders the reads that depend on a positive probe behind an explicit compiler barrier.
+__device__ __forceinline__ bool rn_mbar_probe(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n"
+  asm("{\n"
       ".reg .pred p;\n"
       "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(rn_smem_u32(bar)), "r"(parity)
-      : "memory");
+      : "r"(rn_smem_u32(bar)), "r"(parity));
   return ok != 0;
 }
 __device__ __forceinline__ void rn_cp_async8(void* dst, const void* src) {
@@ -280,22 +267,23 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   }
   __syncthreads();
 
-  // bulk copies of local row group i into its ring slots.  Lane l of the producer warp owns piece l % NH of consumer
-  // warp l / NH for the whole kernel: it waits for that piece's release and re-arms it on its own, so no piece waits
-  // behind another warp's (the consumer warps drift up to ~0.9 us apart).
-  constexpr int NH = RN_FU_NH;
-  const int pw_w = lane / NH, pw_h = lane % NH;
-  const int pw_hb = rn_fu_hb(pw_h), pw_hn = rn_fu_hn(pw_h);
+  // bulk copies of local row group i into its ring slots, one per consumer warp, each as soon as that warp has
+  // released the slot (executed by the whole producer warp)
   auto produce = [&](int i) {
-    if (lane < NCW * NH) {
-      const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
-      const int gs = i % 3;
-      const uint32_t ph = (uint32_t)((i / 3) & 1);
-      const int blk = NB * pw_w + pw_hb;
-      const int st = (gs * NCW + pw_w) * NH + pw_h;
+    const double* src = vw.X8 + (((g0 + i) * qrow + (int64_t)rank * (RN_FU_CCOLS / 2)) << 4);
+    const int gs = i % 3;
+    const uint32_t ph = (uint32_t)((i / 3) & 1);
+#pragma unroll 1
+    for (int w = 0; w < NCW; ++w) {
+      const int wnb = NB;
+      const int wboff = NB * w;
+      const int st = gs * NCW + w;
       rn_mbar_wait(&empty[st], ph ^ 1u);
-      rn_mbar_expect_tx(&full[st], (uint32_t)pw_hn * 1024u);
-      rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + blk * 1024, src + blk * 128, (uint32_t)pw_hn * 1024u, &full[st]);
+      if (lane == 0) {
+        rn_mbar_expect_tx(&full[st], (uint32_t)wnb * 1024u);
+        rn_bulk_g2s(ring + gs * RN_FU_GROUP_BYTES + wboff * 1024, src + wboff * 128, (uint32_t)wnb * 1024u, &full[st]);
+      }
+      __syncwarp();
     }
   };
   // X is never written by a kernel: the ring is filled before the previous launch has finished
@@ -304,8 +292,9 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     for (int i = 0; i < npre; ++i) produce(i);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the previous launch wrote
   if (ft.ctrl->done) {  // uniform over the grid; the copies in flight must land before the CTA may exit
-    if (warp == 3 && lane < NCW * NH)
-      for (int i = 0; i < npre; ++i) rn_mbar_wait(&full[(i * NCW + pw_w) * NH + pw_h], 0u);
+    if (warp == 3)
+      for (int i = 0; i < npre; ++i)
+        for (int w = 0; w < NCW; ++w) rn_mbar_wait(&full[i * NCW + w], 0u);
     return;
   }
   if (tid < 64) {
@@ -583,24 +572,26 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     double pe0 = 0.0, pe1 = 0.0, po0 = 0.0, po1 = 0.0;  // two accumulator chains: even / odd column of a pair
     const bool tr_waits = vw.fu_waits != nullptr;        // developer switch: cycles this warp waited for X / F_new
     long long wait_x = 0, wait_f = 0;
-    bool x_ready = false, fn_ready = false;  // outcome of the early probes (RN_FU_PROBE)
+    bool x_ready = false, fn_ready = false;              // outcome of the early probes (RN_FU_PROBE)
     auto f_phase = [&](int i) {
       const int gs = i % 3;
       if (tid == 0) rn_fu_trace(vw, i, 0);
+      {
+        long long c0_ = 0;
+        if (tr_waits) c0_ = clock64();
+        if (!(RN_FU_PROBE && x_ready)) rn_mbar_wait(&full[gs * NCW + ci], (uint32_t)((i / 3) & 1));
+        asm volatile("" ::: "memory");  // nothing below is read before the (probed or awaited) phase completion
+        if (tr_waits) wait_x += clock64() - c0_;
+      }
+      if (tid == 0) rn_fu_trace(vw, i, 7);
       const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024 + off1;
       pe0 = pe1 = po0 = po1 = 0.0;
 #pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        long long c0_ = 0;
-        if (tr_waits) c0_ = clock64();
-        if (!(RN_FU_PROBE && NH == 1 && x_ready)) rn_mbar_wait(&full[(gs * NCW + ci) * NH + h], (uint32_t)((i / 3) & 1));
-        if (tr_waits) wait_x += clock64() - c0_;
-        if (h == 0 && tid == 0) rn_fu_trace(vw, i, 7);
-#pragma unroll
-        for (int s = 2 * rn_fu_hb(h); s < 2 * (rn_fu_hb(h) + rn_fu_hn(h)); ++s) {
-          // F_new of the group whose G phase follows this F phase (group i - 1): probed RN_FU_PROBE_LEAD MMA pairs early
-          if (RN_FU_PROBE && s == 2 * NB - RN_FU_PROBE_LEAD)
-            fn_ready = i >= 1 && rn_mbar_test(&fp_full[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
+      for (int s = 0; s < 2 * NB; ++s) {
+        // F_new of the group whose G phase follows this F phase (group i - 1), probed a few MMAs early
+        if (RN_FU_PROBE && s == 2 * NB - RN_FU_PROBE_LEAD)
+          fn_ready = i >= 1 && rn_mbar_probe(&fp_full[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
+        if (s < 2 * nb) {  // uniform over the warp
           const double2 x = *reinterpret_cast<const double2*>(xs + s * 512);
           rn_dmma(pe0, pe1, x.x, gfr[s][0]);
           rn_dmma(po0, po1, x.y, gfr[s][1]);
@@ -620,6 +611,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
         long long c0_ = 0;
         if (tr_waits) c0_ = clock64();
         if (!(RN_FU_PROBE && fn_ready)) rn_mbar_wait(&fp_full[i & 1], (uint32_t)((i >> 1) & 1));
+        asm volatile("" ::: "memory");
         fn_ready = false;
         if (tr_waits) wait_f += clock64() - c0_;
       }
@@ -629,12 +621,11 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       const double fb = Fp[(i & 1) * 64 + rb * 8 + g];
       const unsigned char* xs = ring + gs * RN_FU_GROUP_BYTES + boff * 1024;
 #pragma unroll
-      for (int h = 0; h < NH; ++h) {
-#pragma unroll
-        for (int b = rn_fu_hb(h); b < rn_fu_hb(h) + rn_fu_hn(h); ++b) {
-          // X of the group whose F phase follows this G phase (group i + 2): probed early (one piece per warp only)
-          if (RN_FU_PROBE && NH == 1 && b == NB - (RN_FU_PROBE_LEAD + 1) / 2)
-            x_ready = i + 2 < NGL && rn_mbar_test(&full[(((i + 2) % 3) * NCW + ci) * NH], (uint32_t)(((i + 2) / 3) & 1));
+      for (int b = 0; b < NB; ++b) {
+        // X of the group whose F phase follows this G phase (group i + 2), probed early
+        if (RN_FU_PROBE && b == NB - (RN_FU_PROBE_LEAD + 1) / 2)
+          x_ready = i + 2 < NGL && rn_mbar_probe(&full[((i + 2) % 3) * NCW + ci], (uint32_t)(((i + 2) / 3) & 1));
+        if (b < nb) {  // uniform over the warp
           const double2 xa = *reinterpret_cast<const double2*>(xs + off2a + b * 1024);
           const double2 xb = *reinterpret_cast<const double2*>(xs + off2b + b * 1024);
           rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xa.x, fa);
@@ -642,9 +633,9 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
           rn_dmma(tacc[2 * b][0], tacc[2 * b][1], xb.x, fb);
           rn_dmma(tacc[2 * b + 1][0], tacc[2 * b + 1][1], xb.y, fb);
         }
-        __syncwarp();  // the piece is released (and reloaded) while the warp is still in the rest of its G phase
-        if (lane == 0) rn_mbar_arrive(&empty[(gs * NCW + ci) * NH + h]);
       }
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&empty[gs * NCW + ci]);
       if (tid == 0) rn_fu_trace(vw, i, 3);
     };
     if (NGL > 0) {

@@ -133,6 +133,11 @@ struct resnmtf_data {
   int64_t pp8 = 0;
   double xnorm2 = 0.0;
   std::atomic<int> refs{1};
+  // |U| (n x svd_kc), d, |V| (p x svd_kc) of the view, svd_kc = min(16, n, p): computed by the first fit that asks for
+  // the SVD initialisation (init_mats_inner, R/update_steps.r:92-95) and shared by every fit of this data -- the
+  // k-sweep slices the same triplets for every k.  Host copies, column-major.
+  std::vector<double> svd_u, svd_d, svd_v;
+  int svd_kc = 0;
 };
 
 void rn_ctx_release(resnmtf_ctx* ctx);  // resnmtf_capi.cu
@@ -232,3 +237,8 @@ static inline int64_t rn_fidx_host(int64_t r, int c, int kp) {
   return ((r >> 6) * kp + c) * RN_ROW_TILE + 2 * ((int)((r & 63) >> 1) ^ sigma) + (r & 1);
 }
 
+// resnmtf_capi.cu: an empty (zeroed) view in the panel layout, and its completion (||X||_F^2 into the handle)
+int rn_data_alloc(resnmtf_ctx* ctx, int64_t n, int64_t p, resnmtf_data** out);
+int rn_data_seal(resnmtf_data* d);
+// rn_native.cu: fills the handle's cache of top singular triplets (no-op when it is there)
+int rn_data_svd(resnmtf_data* data);

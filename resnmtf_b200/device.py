@@ -142,6 +142,73 @@ class DeviceData:
         self._h = h
         return self
 
+    @classmethod
+    def _wrap(cls, ctx, handle, shape):
+        self = cls.__new__(cls)
+        self._lib = L.require_device()
+        self.ctx = ctx
+        self.shape = (int(shape[0]), int(shape[1]))
+        self._h = handle
+        return self
+
+    @classmethod
+    def prepped(cls, ctx, x):
+        """Upload + make_non_neg_inner + matrix_normalisation (R/utils.r:20-27, 86-88) on the device.  Returns
+        (handle, was_negative)."""
+        lib = L.require_device()
+        x = _f64(x)
+        h, neg = C.c_void_p(), C.c_int32(0)
+        L.check(lib.resnmtf_data_create_prepped(ctx._h, x.shape[0], x.shape[1], _ptr(x), x.shape[0], C.byref(neg),
+                                                C.byref(h)))
+        return cls._wrap(ctx, h, x.shape), bool(neg.value)
+
+    def download(self):
+        out = np.empty(self.shape, dtype=np.float64, order="F")
+        L.check(self._lib.resnmtf_data_download(self._h, _ptr(out), self.shape[0]))
+        return out
+
+    def sums(self):
+        """(colSums, rowSums) of the view."""
+        cs = np.empty(self.shape[1], dtype=np.float64)
+        rs = np.empty(self.shape[0], dtype=np.float64)
+        L.check(self._lib.resnmtf_data_sums(self._h, _ptr(cs), _ptr(rs)))
+        return cs, rs
+
+    def shuffle(self, seed, renormalise=True):
+        """shuffle_view (R/obtain_bicl.r:11-22) on the device: a new handle with all entries permuted (keyed by
+        ``seed``), reshuffled until no row / column is all zero; ``renormalise``: the prep apply_resnmtf applies to
+        the shuffled data."""
+        h, tries = C.c_void_p(), C.c_int64(0)
+        L.check(self._lib.resnmtf_data_shuffle(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(bool(renormalise)),
+                                               C.byref(tries), C.byref(h)))
+        out = DeviceData._wrap(self.ctx, h, self.shape)
+        out.attempts = int(tries.value)
+        return out
+
+    def subsample(self, rows, cols):
+        """x[rows, cols] as a new handle (0-based indices), gathered on the device."""
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        c = np.ascontiguousarray(cols, dtype=np.int32)
+        h = C.c_void_p()
+        L.check(self._lib.resnmtf_data_subsample(self._h, _ptr(r), r.size, _ptr(c), c.size, C.byref(h)))
+        return DeviceData._wrap(self.ctx, h, (r.size, c.size))
+
+    def copy_to(self, ctx):
+        """The view (and its cached SVD triplets) on another context's GPU, device to device."""
+        h = C.c_void_p()
+        L.check(self._lib.resnmtf_data_copy(self._h, ctx._h, C.byref(h)))
+        return DeviceData._wrap(ctx, h, self.shape)
+
+    def svd_topk(self, k):
+        """|U[:, :k]|, d[:k], |V[:, :k]| of the view (what init_mats_inner takes from svd(x), R/update_steps.r:92-95),
+        computed on the device and cached on the handle."""
+        k = int(k)
+        u = np.empty((self.shape[0], k), dtype=np.float64, order="F")
+        d = np.empty(k, dtype=np.float64)
+        v = np.empty((self.shape[1], k), dtype=np.float64, order="F")
+        L.check(self._lib.resnmtf_data_svd_topk(self._h, k, _ptr(u), _ptr(d), _ptr(v)))
+        return u, d, v
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.resnmtf_data_destroy(self._h)
