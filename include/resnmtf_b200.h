@@ -217,6 +217,21 @@ int resnmtf_jsd_pairs(resnmtf_ctx* ctx, const double* vecs, int64_t n, int32_t m
                       const double* bw, const double* vmax, const int32_t* pair_a, const int32_t* pair_b,
                       int64_t n_pairs, double* out);
 
+/* ---- bisilhouette distance blocks ------------------------------------------------------------- */
+
+#define RESNMTF_DIST_EUCLIDEAN 0
+#define RESNMTF_DIST_MANHATTAN 1
+#define RESNMTF_DIST_COSINE 2
+
+/* bisilhouette::bisilhouette() as obtain_biclusters() calls it per view (R/obtain_bicl.r:190-199) on the resident view:
+ * for every non-empty bicluster (R_j, C_j) the mean silhouette of the rows of R_j, distances taken on the columns C_j
+ * only, against the other row clusters (rows of R_j excluded) or -- when there is none -- against all other rows.
+ * row_cl (n x k) / col_cl (p x k): column-major, non-zero = member.  vals[j] (may be NULL) receives the per-bicluster
+ * value (0 for empty ones), *bisil their mean over the non-empty biclusters.  The package is not in the reference tree:
+ * restated from its published definition, parity unpinned. */
+int resnmtf_data_bisil(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method, double* vals,
+                       double* bisil);
+
 /* ---- fan-out: independent fits over the GPUs of a pool ----------------------------------- */
 
 /* One default apply_resnmtf() call is 66 convergence loops: per k of the sweep one fit and num_repeats shuffled refits

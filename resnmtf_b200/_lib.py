@@ -29,6 +29,7 @@ EXPORTS = (
     "resnmtf_jsd_pairs",
     "resnmtf_data_create_prepped", "resnmtf_data_shape", "resnmtf_data_download", "resnmtf_data_sums",
     "resnmtf_data_shuffle", "resnmtf_data_subsample", "resnmtf_data_copy", "resnmtf_data_svd_topk",
+    "resnmtf_data_bisil",
     "resnmtf_pool_create", "resnmtf_pool_destroy", "resnmtf_pool_size", "resnmtf_pool_ctx", "resnmtf_pool_put",
     "resnmtf_pool_put_host", "resnmtf_pool_get", "resnmtf_pool_drop", "resnmtf_batch_run", "resnmtf_unit_size",
     "resnmtf_fit_set_factors", "resnmtf_fit_set_restrictions", "resnmtf_fit_set_shared_map",
@@ -52,6 +53,7 @@ class Counters(C.Structure):
 
 
 DERIVE_NONE, DERIVE_SUBSAMPLE, DERIVE_SHUFFLE = 0, 1, 2
+DISTANCES = {"euclidean": 0, "manhattan": 1, "cosine": 2}
 
 
 class Map(C.Structure):
@@ -131,6 +133,7 @@ def load():
         "resnmtf_data_subsample": (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(vp)]),
         "resnmtf_data_copy": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "resnmtf_data_svd_topk": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "resnmtf_data_bisil": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, pd]),
         "resnmtf_pool_create": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "resnmtf_pool_destroy": (C.c_int, [vp]),
         "resnmtf_pool_size": (C.c_int, [vp]),

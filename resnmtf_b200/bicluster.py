@@ -107,11 +107,14 @@ def jsd_calc(x1, x2):
 
 
 def _pairwise(a, b, method):
-    if method == "euclidean":
-        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * (a @ b.T)
-        return np.sqrt(np.maximum(d2, 0.0))
+    if method == "euclidean":  # the direct form sqrt(sum (a - b)^2), as stats::dist computes it (no Gram-form cancellation)
+        from scipy.spatial.distance import cdist
+
+        return cdist(a, b, "euclidean")
     if method == "manhattan":
-        return np.abs(a[:, None, :] - b[None, :, :]).sum(-1)
+        from scipy.spatial.distance import cdist
+
+        return cdist(a, b, "cityblock")
     if method == "cosine":
         na = np.linalg.norm(a, axis=1)[:, None]
         nb = np.linalg.norm(b, axis=1)[None, :]

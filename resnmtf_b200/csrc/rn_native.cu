@@ -5,6 +5,7 @@
 // (R/update_steps.r:92-95).  Kernels: rn_data.cuh, rn_linalg.cuh.  No cuBLAS / cuSOLVER, no CPU fallback.
 #include "rn_host.h"
 #include "rn_linalg.cuh"
+#include "rn_bisil.cuh"
 #include "rn_dense.h"
 
 namespace {
@@ -686,5 +687,121 @@ extern "C" int resnmtf_data_svd_topk(resnmtf_data* data, int k, double* u, doubl
   if (u) std::memcpy(u, data->svd_u.data(), (size_t)data->n * k * sizeof(double));
   if (d) std::memcpy(d, data->svd_d.data(), (size_t)k * sizeof(double));
   if (v) std::memcpy(v, data->svd_v.data(), (size_t)data->p * k * sizeof(double));
+  return RESNMTF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bisilhouette
+// ------------------------------------------------------------------------------------------------------------------
+
+// Bisilhouette score of one view's biclustering (as obtain_biclusters() asks for it, R/obtain_bicl.r:190-199): for every
+// non-empty bicluster (R_j, C_j) the silhouette of the rows of R_j computed on the columns C_j only, against the other
+// row clusters R_l \ R_j (or, when there is none, against the rows outside R_j); vals[j] = mean row silhouette (0 for
+// empty biclusters), *bisil = mean over the non-empty ones.  row_cl n x k, col_cl p x k: column-major, non-zero = member.
+extern "C" int resnmtf_data_bisil(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method,
+                                  double* vals, double* bisil) {
+  RN_CHECK(data && row_cl && col_cl && bisil, RESNMTF_E_INVALID, "resnmtf_data_bisil: NULL argument");
+  RN_CHECK(k >= 1 && k <= 64, RESNMTF_E_INVALID, "resnmtf_data_bisil: k out of range");
+  RN_CHECK(method >= 0 && method <= 2, RESNMTF_E_INVALID,
+           "distance must be one of 'euclidean', 'manhattan' or 'cosine'.");
+  resnmtf_ctx* ctx = data->ctx;
+  RN_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = data->n, p = data->p;
+  std::vector<std::vector<int32_t>> R((size_t)k), Cc((size_t)k);
+  for (int j = 0; j < k; ++j) {
+    for (int64_t i = 0; i < n; ++i)
+      if (row_cl[(size_t)i + (size_t)j * n] > 0.0) R[j].push_back((int32_t)i);
+    for (int64_t i = 0; i < p; ++i)
+      if (col_cl[(size_t)i + (size_t)j * p] > 0.0) Cc[j].push_back((int32_t)i);
+  }
+  std::vector<int> live;
+  for (int j = 0; j < k; ++j)
+    if (!R[j].empty() && !Cc[j].empty()) live.push_back(j);
+  if (vals)
+    for (int j = 0; j < k; ++j) vals[j] = 0.0;
+  double total = 0.0;
+  for (int j : live) {
+    // segments: R_j, then R_l \ R_j for every other live l (non-empty ones), else the complement of R_j
+    std::vector<std::vector<int32_t>> seg;
+    seg.push_back(R[j]);
+    std::vector<char> in_j((size_t)n, 0);
+    for (int32_t r : R[j]) in_j[r] = 1;
+    for (int l : live) {
+      if (l == j) continue;
+      std::vector<int32_t> g;
+      for (int32_t r : R[l])
+        if (!in_j[r]) g.push_back(r);
+      if (!g.empty()) seg.push_back(g);
+    }
+    if (seg.size() == 1) {
+      std::vector<int32_t> g;
+      for (int64_t r = 0; r < n; ++r)
+        if (!in_j[r]) g.push_back((int32_t)r);
+      if (!g.empty()) seg.push_back(g);
+    }
+    if (seg.size() == 1) continue;  // no other rows at all: the bicluster scores 0
+    RN_CHECK(seg.size() <= 17, RESNMTF_E_UNSUPPORTED, "resnmtf_data_bisil: more than 16 other row clusters");
+    const int n_seg = (int)seg.size();
+    std::vector<int32_t> slots, seg_of_tile;
+    for (int sg = 0; sg < n_seg; ++sg) {
+      for (int32_t r : seg[sg]) slots.push_back(r);
+      while (slots.size() % 64) slots.push_back(-1);
+      while (seg_of_tile.size() < slots.size() / 64) seg_of_tile.push_back(sg);
+    }
+    const int a_tiles = (int)((seg[0].size() + 63) / 64), b_tiles = (int)(slots.size() / 64);
+    const int m = (int)Cc[j].size(), ldy = (m + 15) / 16 * 16;
+    int splits = std::max(1, std::min(b_tiles, (4 * ctx->sm_count + a_tiles - 1) / a_tiles));
+    DevBuf d_slots, d_cols, d_segt, d_Y, d_norms, d_part;
+    RN_CUDA(d_slots.alloc(ctx, slots.size() * sizeof(int32_t), false));
+    RN_CUDA(d_cols.alloc(ctx, (size_t)m * sizeof(int32_t), false));
+    RN_CUDA(d_segt.alloc(ctx, seg_of_tile.size() * sizeof(int32_t), false));
+    RN_CUDA(d_Y.alloc(ctx, slots.size() * (size_t)ldy * sizeof(double), false));
+    RN_CUDA(d_norms.alloc(ctx, slots.size() * sizeof(double), false));
+    const size_t part_count = (size_t)splits * n_seg * a_tiles * 64;
+    RN_CUDA(d_part.alloc(ctx, part_count * sizeof(double), false));
+    RN_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    RN_CUDA(cudaMemcpyAsync(d_cols.p, Cc[j].data(), (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    RN_CUDA(cudaMemcpyAsync(d_segt.p, seg_of_tile.data(), seg_of_tile.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    rn_bisil_gather<<<(unsigned)((slots.size() + 7) / 8), 256, 0, ctx->stream>>>(
+        data->X, data->pp, static_cast<const int32_t*>(d_slots.p), (int64_t)slots.size(),
+        static_cast<const int32_t*>(d_cols.p), m, ldy, d_Y.d(), d_norms.d());
+    RnBisil a;
+    a.Y = d_Y.d();
+    a.norms = method == RN_DIST_COSINE ? d_norms.d() : nullptr;
+    a.rows = static_cast<const int32_t*>(d_slots.p);
+    a.ldy = ldy;
+    a.a_tiles = a_tiles;
+    a.b_tiles = b_tiles;
+    a.seg_of_tile = static_cast<const int32_t*>(d_segt.p);
+    a.n_seg = n_seg;
+    a.splits = splits;
+    a.part = d_part.d();
+    dim3 grid((unsigned)a_tiles, (unsigned)splits);
+    if (method == RN_DIST_EUCLIDEAN) rn_bisil_dist<RN_DIST_EUCLIDEAN><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (method == RN_DIST_MANHATTAN) rn_bisil_dist<RN_DIST_MANHATTAN><<<grid, 256, 0, ctx->stream>>>(a);
+    else rn_bisil_dist<RN_DIST_COSINE><<<grid, 256, 0, ctx->stream>>>(a);
+    RN_CUDA(cudaGetLastError());
+    std::vector<double> part(part_count);
+    RN_CUDA(cudaMemcpyAsync(part.data(), d_part.d(), part_count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    RN_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t na = seg[0].size(), stride = (size_t)a_tiles * 64;
+    double sil_sum = 0.0;
+    for (size_t i = 0; i < na; ++i) {
+      double own = 0.0, best = INFINITY;
+      for (int sg = 0; sg < n_seg; ++sg) {
+        double s = 0.0;
+        for (int q = 0; q < splits; ++q) s += part[((size_t)q * n_seg + sg) * stride + i];
+        if (sg == 0) own = na > 1 ? s / (double)std::max<size_t>(na - 1, 1) : 0.0;
+        else best = std::min(best, s / (double)seg[sg].size());
+      }
+      const double den = std::max(own, best);
+      sil_sum += den > 0.0 ? (best - own) / den : 0.0;
+    }
+    const double val = sil_sum / (double)na;
+    if (vals) vals[j] = val;
+    total += val;
+  }
+  *bisil = live.empty() ? 0.0 : total / (double)live.size();
   return RESNMTF_OK;
 }

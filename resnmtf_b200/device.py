@@ -209,6 +209,21 @@ class DeviceData:
         L.check(self._lib.resnmtf_data_svd_topk(self._h, k, _ptr(u), _ptr(d), _ptr(v)))
         return u, d, v
 
+    def bisil(self, row_clustering, col_clustering, method="euclidean"):
+        """Bisilhouette score of this view's biclustering with the distance blocks on the GPU (resnmtf_data_bisil).
+        Returns dict(bisil=..., vals=[per bicluster that is non-empty])."""
+        if method not in L.DISTANCES:
+            raise ValueError("distance must be one of 'euclidean', 'manhattan' or 'cosine'.")
+        rc = _f64(np.asarray(row_clustering) > 0)
+        cc = _f64(np.asarray(col_clustering) > 0)
+        k = rc.shape[1]
+        vals = np.zeros(k, dtype=np.float64)
+        out = C.c_double(0.0)
+        L.check(self._lib.resnmtf_data_bisil(self._h, _ptr(rc), _ptr(cc), k, L.DISTANCES[method], _ptr(vals),
+                                             C.byref(out)))
+        live = [j for j in range(k) if rc[:, j].any() and cc[:, j].any()]
+        return {"bisil": float(out.value), "vals": [float(vals[j]) for j in live]}
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.resnmtf_data_destroy(self._h)

@@ -149,3 +149,50 @@ def test_device_to_device_copy_carries_the_view_and_its_triplets(ctx):
         assert np.array_equal(u2, u) and np.array_equal(dv2, dv) and np.array_equal(v2, v)
         c.close()
     d.close()
+
+
+@pytest.mark.parametrize("method", ["euclidean", "manhattan", "cosine"])
+@pytest.mark.parametrize("n,p,k", [(400, 150, 5), (1000, 333, 8), (130, 70, 3)])
+def test_bisilhouette_on_the_resident_view_matches_the_host_restatement(ctx, method, n, p, k):
+    """resnmtf_data_bisil (distance blocks of bisilhouette on the device) against the host restatement of
+    the same definition (scipy's direct-difference distances): overlapping clusters, an empty cluster, a single-row
+    cluster, all three distances, ragged sizes (tiles of 64 rows / 16 columns are padded)."""
+    from resnmtf_b200 import bicluster as B
+
+    rng = np.random.default_rng(23)
+    x = synth.prep(synth.planted_view(n, p, 3, rng, row_prob=0.3, col_prob=0.3)[0])
+    rc = (rng.random((n, k)) < 0.25).astype(float)
+    cc = (rng.random((p, k)) < 0.3).astype(float)
+    if k >= 5:
+        rc[:, 3] = 0.0            # empty row cluster
+        rc[:, 4] = 0.0
+        rc[17, 4] = 1.0           # single-row cluster
+    d = DeviceData(ctx, x)
+    host = B.bisilhouette(x, rc, cc, method=method)
+    dev = d.bisil(rc, cc, method=method)
+    assert len(dev["vals"]) == len(host["vals"])
+    np.testing.assert_allclose(dev["vals"], host["vals"], rtol=1e-10, atol=1e-12)
+    assert abs(dev["bisil"] - host["bisil"]) <= 1e-12
+    again = d.bisil(rc, cc, method=method)
+    assert again == dev           # fixed summation order: bit-identical
+    d.close()
+
+
+def test_bisilhouette_single_cluster_scores_against_the_rows_outside(ctx):
+    """One non-empty bicluster only: the comparison group is the complement of its rows; all rows in it: score 0."""
+    from resnmtf_b200 import bicluster as B
+
+    rng = np.random.default_rng(5)
+    x = synth.prep(synth.planted_view(300, 90, 3, rng, row_prob=0.3, col_prob=0.3)[0])
+    rc = np.zeros((300, 3))
+    cc = np.zeros((90, 3))
+    rc[:120, 1] = 1.0
+    cc[10:50, 1] = 1.0
+    d = DeviceData(ctx, x)
+    host = B.bisilhouette(x, rc, cc)
+    dev = d.bisil(rc, cc)
+    np.testing.assert_allclose(dev["vals"], host["vals"], rtol=1e-10, atol=1e-12)
+    rc[:, 1] = 1.0
+    assert d.bisil(rc, cc)["bisil"] == 0.0 == B.bisilhouette(x, rc, cc)["bisil"]
+    assert d.bisil(np.zeros((300, 3)), cc)["bisil"] == 0.0
+    d.close()
