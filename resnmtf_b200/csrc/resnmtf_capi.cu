@@ -15,6 +15,7 @@
 #include "rn_host.h"
 #include "rn_kernels.cuh"
 #include "rn_fused.cuh"
+#include "rn_fused2.cuh"
 #include "rn_post.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -60,7 +61,15 @@ static GStepSkFn g_step_tma_fn(int K) {
   return nullptr;
 }
 
-static GStepSkFn fused_step_fn(int K) {
+static GStepSkFn fused_step_fn(int K, int kind) {
+  if (kind == 2) {
+    switch (K) {
+#define X(KC) case KC: return rn_fused2_step<KC>;
+      RN_K_CASES_LE8(X)
+#undef X
+    }
+    return nullptr;
+  }
   switch (K) {
 #define X(KC) case KC: return rn_fused_step<KC>;
     RN_K_CASES_LE8(X)
@@ -68,14 +77,16 @@ static GStepSkFn fused_step_fn(int K) {
   }
   return nullptr;
 }
+static inline size_t fused_smem(int kind) { return kind == 2 ? rn_fused2_smem() : rn_fused_smem(); }
+static inline int fused_threads(int kind) { return kind == 2 ? RN_F2_THREADS : RN_FU_THREADS; }
 
 // One-pass fused update of a view: cluster launch (fu_csize CTAs per cluster, fu_clusters clusters).
 static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(vh.d.fu_clusters * vh.d.fu_csize));
-  cfg.blockDim = dim3(RN_FU_THREADS);
-  cfg.dynamicSmemBytes = rn_fused_smem();
+  cfg.blockDim = dim3((unsigned)fused_threads(vh.d.fu_kind));
+  cfg.dynamicSmemBytes = fused_smem(vh.d.fu_kind);
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -93,7 +104,7 @@ static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, c
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  cudaLaunchKernelEx(&cfg, fused_step_fn(vh.d.k), vh.d, ft, v, fuse);
+  cudaLaunchKernelEx(&cfg, fused_step_fn(vh.d.k, vh.d.fu_kind), vh.d, ft, v, fuse);
 }
 
 // Cluster size of the fused path for a view, 0 when it does not qualify: k <= 8, not row-sharded, p within
@@ -108,17 +119,17 @@ static int fused_csize(const RnView& d, bool sharded) {
 }
 
 // Most clusters of `csz` CTAs of the fused kernel the device keeps resident at once (0: the cluster does not fit).
-static int fused_max_clusters(int K, int csz, int sms) {
-  GStepSkFn fn = fused_step_fn(K);
-  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rn_fused_smem()) != cudaSuccess) {
+static int fused_max_clusters(int K, int csz, int sms, int kind) {
+  GStepSkFn fn = fused_step_fn(K, kind);
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem(kind)) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(csz * sms));
-  cfg.blockDim = dim3(RN_FU_THREADS);
-  cfg.dynamicSmemBytes = rn_fused_smem();
+  cfg.blockDim = dim3((unsigned)fused_threads(kind));
+  cfg.dynamicSmemBytes = fused_smem(kind);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)csz;
@@ -905,25 +916,56 @@ static int build_plan(resnmtf_fit* fit) {
     RnView& d = vh.d;
     // the one-pass fused kernel serves the views that qualify (fused_csize); the others of the fit run the
     // two-pass TMA kernels
-    int csz = (impl_fit == RESNMTF_IMPL_FUSED) ? fused_csize(d, fit->ctx->comm != nullptr) : 0;
-    if (csz) {  // the fused kernel prefetches the phi gathers of at most RN_FU_MAXPART partner views
-      int partners = 0;
-      for (int w = 0; w < fit->V; ++w) {
-        const size_t slot = (size_t)w + (size_t)v * fit->V;
-        if (w != v && fit->h_phi[slot] != 0.0 && fit->h_rowmode[slot] != RN_MODE_NA) ++partners;
-      }
-      if (partners > RN_FU_MAXPART || (partners > 0 && rn_env_int("RESNMTF_FUSED_PHI", 1) == 0)) csz = 0;
-    }
+    // Two generations of the one-pass kernel.  rn_fused_step (kind 1: 1008 columns per CTA, 9 consumer warps on three
+    // sub-partitions) is the faster one at the bench shape (143 vs 146 us per update-iteration at 20000 x 4000) and is
+    // preferred whenever its fixed CTA width fits the view: p <= 8064 and at most RESNMTF_FUSED2_PAD percent (default
+    // 108) of padded columns.  rn_fused2_step (kind 2: <= 42 blocks of 16 columns per CTA dealt evenly, no padding, 12
+    // consumer warps on all four sub-partitions; p <= 8 x 672) takes the widths kind 1 would pad heavily and the narrow
+    // views (p < 747) that kind 1 does not accept at all.  RESNMTF_FUSED_KIND=1 / 2 forces one of them (A/B runs, parity
+    // tests of both).
     const int K = d.k, KP = d.kp;
-    // the persistent cluster grid must be resident at once; a cluster shape that strands too many SMs loses to the
-    // two-pass kernels, which use all of them
-    const int max_clusters = csz ? fused_max_clusters(K, csz, sms) : 0;
-    if (csz && (max_clusters < 1 || max_clusters * csz * 100 < sms * rn_env_int("RESNMTF_FUSED_MIN_SM_PCT", 70))) csz = 0;
+    const bool sharded = fit->ctx->comm != nullptr;
+    int partners = 0;  // the fused kernels prefetch the phi gathers of at most RN_FU_MAXPART partner views
+    for (int w = 0; w < fit->V; ++w) {
+      const size_t slot = (size_t)w + (size_t)v * fit->V;
+      if (w != v && fit->h_phi[slot] != 0.0 && fit->h_rowmode[slot] != RN_MODE_NA) ++partners;
+    }
+    const bool phi_ok = partners <= RN_FU_MAXPART && !(partners > 0 && rn_env_int("RESNMTF_FUSED_PHI", 1) == 0);
+    const int kind_req = rn_env_int("RESNMTF_FUSED_KIND", 0);
+    const int min_pct = rn_env_int("RESNMTF_FUSED_MIN_SM_PCT", 70);
+    int csz = 0, kind = 0, max_clusters = 0;
+    if (impl_fit == RESNMTF_IMPL_FUSED && phi_ok && K <= 8 && !sharded) {
+      // the persistent cluster grid must be resident at once; a cluster shape that strands too many SMs loses to the
+      // two-pass kernels, which use all of them
+      int c1 = 0, mc1 = 0, c2 = 0, mc2 = 0;
+      if (kind_req != 2) {
+        c1 = fused_csize(d, sharded);
+        mc1 = c1 ? fused_max_clusters(K, c1, sms, 1) : 0;
+        if (!(c1 && mc1 >= 1 && mc1 * c1 * 100 >= sms * min_pct)) c1 = 0;
+      }
+      if (kind_req != 1) {
+        const int64_t blocks = d.pp / 16;
+        c2 = (int)((blocks + RN_F2_MAXB - 1) / RN_F2_MAXB);
+        if (c2 < 1 || c2 > RN_FU_MAXC) c2 = 0;
+        mc2 = c2 ? fused_max_clusters(K, c2, sms, 2) : 0;
+        if (!(c2 && mc2 >= 1 && mc2 * c2 * 100 >= sms * min_pct)) c2 = 0;
+      }
+      const bool tight1 = c1 && (int64_t)c1 * RN_FU_CCOLS * 100 <= (int64_t)d.p * rn_env_int("RESNMTF_FUSED2_PAD", 108);
+      if (c1 && (tight1 || !c2)) {
+        csz = c1;
+        kind = 1;
+        max_clusters = mc1;
+      } else if (c2) {
+        csz = c2;
+        kind = 2;
+        max_clusters = mc2;
+      }
+    }
     const int impl = (impl_fit == RESNMTF_IMPL_FUSED && !csz) ? RESNMTF_IMPL_TMA : impl_fit;
     vh.impl = impl;
     const bool mma = use_mma(vh, impl);
     size_t n_ppart, n_tpart, n_ffpart, n_ggpart;
-    d.fu_csize = d.fu_clusters = 0;
+    d.fu_csize = d.fu_clusters = d.fu_kind = 0;
     if (csz) {
       any_fused = true;
       const int64_t groups = (d.n + 7) / 8;
@@ -931,7 +973,10 @@ static int build_plan(resnmtf_fit* fit) {
       nc = std::max(1, std::min(nc, rn_env_int("RESNMTF_FU_CLUSTERS", nc)));
       d.fu_csize = csz;
       d.fu_clusters = nc;
-      d.pp8 = (int64_t)csz * RN_FU_CCOLS;
+      d.fu_kind = kind;
+      const int64_t pp8_new = kind == 2 ? d.pp : (int64_t)csz * RN_FU_CCOLS;
+      if (d.X8 && d.pp8 != pp8_new) d.X8 = nullptr;  // the copy at hand has the other kernel's width
+      d.pp8 = pp8_new;
       d.col_groups = (int)((d.pp + RN_COL_GROUP - 1) / RN_COL_GROUP);
       d.cs = d.rs = 1;
       d.nff = 0;
@@ -1302,7 +1347,7 @@ static int rn_print_fused_timeline(resnmtf_fit* fit) {
       }
       std::fprintf(stderr, "  %-22s %8lld %8lld\n", nm[sidx], lo, hi);
     }
-    if (d.fu_trace) {  // per-row-group trace of CTA 0 (cluster 0): averages over its groups, ns
+    if (d.fu_trace && d.fu_kind == 1) {  // per-row-group trace of CTA 0 (cluster 0): averages over its groups, ns
       const int64_t groups = (d.n + 7) / 8;
       const int ngl = (int)(groups / d.fu_clusters + (groups % d.fu_clusters ? 1 : 0));
       std::vector<long long> tr((size_t)ngl * 32);
@@ -1345,7 +1390,32 @@ static int rn_print_fused_timeline(resnmtf_fit* fit) {
                      cnt, period / cnt, wait_x / cnt, f_ph / cnt, wait_f / cnt, g_ph / cnt, pub2in / cnt, ep_exch / cnt,
                      ep_math / cnt, early / cnt);
     }
-    if (d.fu_waits) {  // cycles per row group a consumer warp waited for X (ring) and for F_new (epilogue), mean over CTAs
+    if (d.fu_trace && d.fu_kind == 2) {  // rn_fused2_step: per-group stamps of CTA 0, ns relative to warp 0's publication
+      const int64_t groups = (d.n + 7) / 8;
+      const int ngl = (int)(groups / d.fu_clusters + (groups % d.fu_clusters ? 1 : 0));
+      std::vector<long long> tr((size_t)ngl * 32);
+      RN_CUDA(cudaMemcpy(tr.data(), d.fu_trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      static const char* nm2[32] = {"w0 F phase asks X", "w0 X(A) there", "w0 published", "w0 G phase asks F_new",
+                                    "w0 F_new there", "w0 G phase done", "", "", "E starts", "E old F rows there",
+                                    "E warp partials in", "E partial sent", "E cluster partials in", "E F_new out",
+                                    "E done", "", "pub w0", "pub w1", "pub w2", "pub w3", "pub w4", "pub w5", "pub w6",
+                                    "pub w7", "pub w8", "pub w9", "pub w10", "pub w11", "", "", "", ""};
+      double mean[32] = {0}, period = 0;
+      int cnt = 0;
+      for (int i = 6; i + 4 < ngl; ++i) {
+        const long long* a = &tr[(size_t)i * 32];
+        for (int q = 0; q < 32; ++q) mean[q] += (double)(a[q] - a[2]);
+        period += (double)(tr[(size_t)(i + 1) * 32 + 2] - a[2]);
+        ++cnt;
+      }
+      if (cnt > 0) {
+        std::fprintf(stderr, "  per row group (CTA 0, %d groups): period %.0f ns; stamps relative to warp 0's publication:\n", cnt,
+                     period / cnt);
+        for (int q = 0; q < 28; ++q)
+          if (nm2[q][0]) std::fprintf(stderr, "    %-24s %8.0f\n", nm2[q], mean[q] / cnt);
+      }
+    }
+    if (d.fu_waits && d.fu_kind == 1) {  // cycles per row group a consumer warp waited for X (ring) and for F_new (epilogue), mean over CTAs
       std::vector<long long> wt((size_t)grid * RN_FU_NCW * 2);
       RN_CUDA(cudaMemcpy(wt.data(), d.fu_waits, wt.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       const double groups_per_cluster = (double)((d.n + 7) / 8) / d.fu_clusters;

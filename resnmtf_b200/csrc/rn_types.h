@@ -70,11 +70,12 @@ struct RnView {
   int32_t gepi_ctas;           // G-epilogue grid
   int32_t resid_cs;            // residual grid y
   int32_t sharded;             // 1: rows are sharded over ranks (epilogue scalars come from all-reduce)
-  // one-pass fused path (rn_fused.cuh): second copy of X in the 8-row-group layout, pp8 = fu_csize * 1024 columns;
+  // one-pass fused path (rn_fused.cuh): second copy of X in the 8-row-group layout, pp8 = fu_csize * 1008 (kind 1) or pp (kind 2) columns;
   // Tpart is then [fu_clusters][pp8][kp], FFpart [fu_clusters][k*k+k], GGpart [ceil(pp/64)][2*k*k+k]
   double* X8;
   int64_t pp8;
   int32_t fu_csize, fu_clusters;  // CTAs per cluster (1..8; 0: view not on the fused path), clusters in the grid
+  int32_t fu_kind, fu_pad_;       // 1: rn_fused_step (1008 columns per CTA), 2: rn_fused2_step (<= 672, rn_fused2.cuh)
   long long* fu_trace;            // optional [row groups of cluster 0][8] per-group stamps of CTA 0 (same switch)
   long long* fu_timeline;         // optional [grid][12] %globaltimer stamps of the last launch (RESNMTF_FU_TIMELINE=1)
   long long* fu_waits;            // optional [grid][9 consumer warps][2] cycles waited for X / for F_new (same switch)

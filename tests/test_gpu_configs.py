@@ -45,12 +45,13 @@ def test_c2_full_size_two_sweeps_vs_oracle_and_paths_agree(ctx):
     np.testing.assert_allclose(ref[0][2].sum(0), np.ones(k), rtol=0, atol=1e-12)
 
 
-@pytest.fixture(params=["default kernels", "fused kernel"])
+@pytest.fixture(params=["two-pass kernels", "fused kernel"])
 def kernel_family(request, monkeypatch):
-    """The reduced-size views are narrower than the fused kernel's padding rule admits, so they default to the
-    two-pass kernels; the second pass of each structure test lifts the rule (the full-size configs run fused)."""
-    if request.param == "fused kernel":
-        monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
+    """The reduced-size views take the one-pass kernel by default (rn_fused2_step deals their columns without padding;
+    the full-size configs run rn_fused_step); the other pass of each structure test sends them through the two-pass
+    TMA kernels, which serve the views the one-pass kernels do not take (p > 8064, row-sharded, k > 8)."""
+    if request.param == "two-pass kernels":
+        monkeypatch.setenv("RESNMTF_IMPL", str(L.IMPL_TMA))
     return request.param
 
 

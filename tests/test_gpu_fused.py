@@ -1,6 +1,8 @@
-"""Parity of the one-pass fused kernel (RESNMTF_IMPL_FUSED, rn_fused.cuh: one read of X per update-iteration,
-8-row groups resident in the shared memory of a 1/2/4-CTA cluster) against the CPU oracle, sweep by sweep,
-through the C ABI.  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+"""Parity of the one-pass fused kernels (RESNMTF_IMPL_FUSED: one read of X per update-iteration, 8-row groups resident
+in the shared memory of a CTA cluster) against the CPU oracle, sweep by sweep, through the C ABI.  Every test runs three
+times: with the library's own choice between the two kernel generations, with rn_fused_step forced (rn_fused.cuh, 1008
+columns per CTA) and with rn_fused2_step forced (rn_fused2.cuh, <= 672 columns per CTA, no column padding).
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
 import numpy as np
 import pytest
 
@@ -10,6 +12,17 @@ from resnmtf_b200 import synth
 from test_gpu_parity import single_view_problem, two_view_problem
 
 pytestmark = pytest.mark.gpu
+
+KIND2_MAX_COLS = 8 * 42 * 16  # widest view rn_fused2_step takes (8-CTA cluster, 42 blocks of 16 columns per CTA)
+
+
+@pytest.fixture(autouse=True, params=["auto", "kind1", "kind2"])
+def kernel_generation(request, monkeypatch):
+    if request.param == "auto":
+        monkeypatch.delenv("RESNMTF_FUSED_KIND", raising=False)
+    else:
+        monkeypatch.setenv("RESNMTF_FUSED_KIND", request.param[-1])
+    return request.param
 
 
 @pytest.fixture
@@ -146,8 +159,10 @@ def test_fused_convergence_rule(ctx, any_width):
 
 
 @pytest.mark.parametrize("p,k", [(2100, 3), (5000, 5), (5900, 4), (7000, 8), (8064, 6)])
-def test_fused_odd_cluster_sizes(ctx, p, k, monkeypatch):
+def test_fused_odd_cluster_sizes(ctx, p, k, monkeypatch, kernel_generation):
     """Clusters of 3, 5, 6, 7 and 8 CTAs (p up to 8 x 1008 columns)."""
+    if kernel_generation == "kind2" and p > KIND2_MAX_COLS:
+        pytest.skip("wider than rn_fused2_step's 8 x 672 columns")
     monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
     monkeypatch.setenv("RESNMTF_FUSED_MIN_SM_PCT", "1")
     prob = single_view_problem(150, p, k, seed=900 + p, n_planted=4)

@@ -34,11 +34,15 @@ def test_fixed_sweeps_match_golden(ctx, name, impl, monkeypatch):
         fit.close()
 
 
-@pytest.mark.parametrize("family", ["default kernels", "fused kernel"])
+@pytest.mark.parametrize("family", ["default kernels", "two-pass kernels", "first one-pass kernel"])
 @pytest.mark.parametrize("name", CASES)
 def test_converged_run_matches_golden(ctx, name, family, monkeypatch):
-    if family == "fused kernel":
+    """Default for these narrow views: rn_fused2_step; then the two-pass TMA kernels and rn_fused_step forced."""
+    if family == "two-pass kernels":
+        monkeypatch.setenv("RESNMTF_IMPL", str(L.IMPL_TMA))
+    elif family == "first one-pass kernel":
         monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
+        monkeypatch.setenv("RESNMTF_FUSED_KIND", "1")
     prob, z, V = load(name)
     fit = prob.device_fit(ctx)
     try:
