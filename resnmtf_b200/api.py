@@ -172,7 +172,22 @@ def _svd_topk_device(x, k, device):
     boundary input of a fit, not the update path.  The reference's full svd(x) (LAPACK,
     R/update_steps.r:92) is what dominates the wall time of apply_resnmtf once the loop runs on the device (host
     profile on 4000 x 1500: 33 of 45 s); the Gram route agrees with it to ~1e-14 on planted and on shuffled (nearly
-    degenerate) spectra.  Returns None when torch / CUDA is unavailable."""
+    degenerate) spectra.  Returns None when torch / CUDA is unavailable.
+    Default (native route): the library's own resnmtf_data_svd_topk on a temporary data handle -- hand-written FP64
+    tensor-core Gram / projection kernels and a filtered subspace iteration on the device, no torch."""
+    if native_route():
+        if L.device_count() <= 0:
+            return None
+        from .device import Context, DeviceData
+
+        ctx = default_context() if device is None or device < 0 or device == default_context().device else Context(device)
+        h = DeviceData(ctx, np.asfortranarray(x, dtype=np.float64))
+        try:
+            return h.svd_topk(k)
+        finally:
+            h.close()
+            if ctx is not default_context():
+                ctx.close()
     torch = _torch_cuda()
     if torch is None:
         return None
@@ -193,13 +208,36 @@ def _init_from_svd(f, d, g, k, rng, sigma=0.05):
     return f, s, g, f.sum(axis=0), g.sum(axis=0)
 
 
+def native_route():
+    """The matrix-sized steps run on the library alone (native_route.py) unless RESNMTF_ROUTE=torch asks for the first
+    version of these steps (library GEMM / eigensolver / gathers through torch; kept for comparison runs)."""
+    import os
+
+    return os.environ.get("RESNMTF_ROUTE", "native") != "torch"
+
+
 def device_route(data):
     """Matrix-sized views (>= 250k entries each) keep every matrix-sized step on the GPU -- initialisation, shuffles,
-    sub-samples, bisilhouette distance blocks, JSD thresholds; small ones, and hosts without torch
-    CUDA, take the reference's host route around the device loop."""
+    sub-samples, bisilhouette distance blocks, JSD thresholds, all behind the C ABI
+    (native_route.py); small ones take the reference's host route around the device loop."""
     if min(int(np.prod(m.shape)) for m in data) < 250_000:
         return False
+    if native_route():
+        return L.device_count() > 0
     return _torch_cuda() is not None
+
+
+def _pool_devices(ctx, use_parallel):
+    """GPUs of a call: the context's GPU first, then -- with use_parallel -- the other visible ones, at most
+    RESNMTF_MAX_GPUS (0: all)."""
+    import os
+
+    if not use_parallel:
+        return [ctx.device]
+    n = L.device_count()
+    cap = int(os.environ.get("RESNMTF_MAX_GPUS", "0") or 0)
+    devs = [ctx.device] + [d for d in range(n) if d != ctx.device]
+    return devs[:cap] if cap > 0 else devs
 
 
 def _shuffle_refit_device(torch, xts, k, rng, ctx, max_iters=0):
@@ -497,6 +535,15 @@ def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, 
     rng = np.random.default_rng() if rng is None else rng
     ctx = default_context() if ctx is None else ctx
     data = [as_named(m) for m in data]
+    if native_route() and device_route(data):
+        from .native_route import NativeRunner
+
+        with NativeRunner(devices=[ctx.device]) as runner:
+            runner.put(data, prep_values=False)
+            spec = dict(data=data, row_indices=row_indices, col_indices=column_indices, k_vec=k_vec, rng=rng,
+                        init_f=init_f, init_s=init_s, init_g=init_g)
+            return runner.run_fits([spec], phi, xi, psi, n_iters, num_repeats, spurious, distance, no_clusts,
+                                   max_iters=max_iters, err_mode=err_mode, impl=impl)[0]
     with _single_pool(ctx) as pool:
         _place(pool, "data", data)
         spec = dict(key="data", data=data, row_indices=row_indices, col_indices=column_indices, k_vec=k_vec, rng=rng,
@@ -510,6 +557,46 @@ def res_nmtf_inner(data, row_indices, column_indices, init_f=None, init_s=None, 
 # --------------------------------------------------------------------------------------------------
 # apply_resnmtf
 # --------------------------------------------------------------------------------------------------
+
+
+def _apply_native(data, reordering, init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_min, k_max, distance, spurious,
+                  num_repeats, no_clusts, sample_rate, n_stability, stability, stab_thres, remove_unstable, devices, rng,
+                  max_iters):
+    """R/main.r:258-334 for matrix-sized views on the native pool (native_route.py): the raw views go to the first GPU
+    once (prepped there), every convergence loop of the call is a unit of resnmtf_batch_run."""
+    from .native_route import NativeRunner, ResidentView
+
+    n_v = len(data)
+    with NativeRunner(devices=devices) as runner:
+        runner.put(data, prep_values=True)
+        data = [ResidentView(m.shape, m.rownames, m.colnames) for m in data]  # the values live on the GPUs only
+        base = dict(data=data, row_indices=reordering["row_indices"], init_f=init_f, init_s=init_s, init_g=init_g)
+        run = lambda specs: runner.run_fits(specs, phi, xi, psi, n_iters, num_repeats, spurious, distance, no_clusts,  # noqa: E731
+                                            max_iters=max_iters)
+        stab = lambda results, k: runner.stability_check(data, results, k, phi, xi, psi, n_iters, spurious, num_repeats,  # noqa: E731
+                                                         no_clusts, distance, sample_rate, n_stability, stab_thres,
+                                                         remove_unstable, rng=rng, max_iters=max_iters)
+        if k_vec is not None:
+            results = run([dict(base, col_indices=reordering["col_indices"], k_vec=k_vec, rng=rng)])[0]
+            return stab(results, k_vec) if stability else results
+        ks = list(range(int(k_min), int(k_max) + 1))
+        child_rngs = rng.spawn(len(ks))
+        res_list = run([dict(base, col_indices=reordering["col_indices"], k_vec=[k] * n_v, rng=child_rngs[i])
+                        for i, k in enumerate(ks)])
+        err_list = extract_bisils(res_list, ks)
+        test = ks[int(np.argmax(err_list))]
+        max_k = int(k_max)
+        if k_min != k_max:
+            while test == max_k:
+                max_k += 1
+                ks.append(max_k)
+                # quirk Q3 (R/main.r:312): the extension fits run with column_indices = NULL.  Reproduced.
+                res_list.append(run([dict(base, col_indices=None, k_vec=[max_k] * n_v, rng=rng)])[0])
+                err_list.append(res_list[-1]["bisil"])
+                test = ks[int(np.argmax(err_list))]
+        best = int(np.argmax(err_list))
+        results = res_list[best]
+        return stab(results, ks[best]) if stability else results
 
 
 def extract_bisils(res_list, k_vec):
@@ -551,6 +638,10 @@ def apply_resnmtf(data, init_f=None, init_s=None, init_g=None, k_val=None, phi=N
     # The fits of one call are independent units: every fit gets its own child generator -- so the result
     # does not depend on how many GPUs run them -- and, with use_parallel and more than one visible GPU, they are
     # spread over one context per GPU (the reference's %dopar% intent, R/main.r:288-299, which is unreachable there).
+    if on_device and native_route():
+        return _apply_native(data, reordering, init_f, init_s, init_g, k_vec, phi, xi, psi, n_iters, k_min, k_max, distance,
+                             spurious, num_repeats, no_clusts, sample_rate, n_stability, stability, stab_thres,
+                             remove_unstable, _pool_devices(ctx, use_parallel), rng, max_iters)
     contexts = device_contexts(ctx) if use_parallel else [ctx]
     fit_kw = dict(max_iters=max_iters)
     with FitPool(contexts) as pool:

@@ -379,9 +379,12 @@ def obtain_biclusters(data, output_f, output_g, output_s, num_repeats, remove_sp
             continue
         score = None
         xi = data[i].x if hasattr(data[i], "x") else data[i]
-        if resident is not None:  # matrix-sized view, already on the GPU: distance blocks there
+        if resident is not None and hasattr(resident[i], "bisil"):
+            # matrix-sized view resident in the library's layout: distance blocks by resnmtf_data_bisil
+            score = resident[i].bisil(row_clustering[i], col_clustering[i], method=distance)
+        elif resident is not None and resident[i] is not None:  # first version: a torch tensor of the view
             score = bisilhouette_device(None, row_clustering[i], col_clustering[i], method=distance, xt=resident[i])
-        elif int(np.prod(xi.shape)) >= 250_000:
+        elif xi is not None and int(np.prod(xi.shape)) >= 250_000:
             score = bisilhouette_device(xi, row_clustering[i], col_clustering[i], method=distance,
                                         device=getattr(ctx, "device", None))
         if score is None:

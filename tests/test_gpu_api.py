@@ -220,3 +220,45 @@ def test_device_svd_initialisation_filtered_route_matches_lapack():
         assert rel_err(out[1], d[:6]) <= 1e-11
         assert np.max(np.abs(out[0] - np.abs(u[:, :6]))) <= 1e-9
         assert np.max(np.abs(out[2] - np.abs(vt[:6].T))) <= 1e-9
+
+
+def test_matrix_sized_route_runs_without_torch():
+    """The default route of apply_resnmtf on matrix-sized views -- prep, SVD initialisation, shuffles, sub-samples, the
+    fits, JSD thresholds, bisilhouette -- goes through the C ABI only: a fresh interpreter finishes the reference's
+    default call (k sweep + spurious-bicluster removal + stability analysis) without ever importing torch."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from resnmtf_b200 import synth\n"
+        "from resnmtf_b200.api import apply_resnmtf\n"
+        "views, _ = synth.block_views(1, block=200, n_blocks=3, seed=5)\n"
+        "res = apply_resnmtf(views, k_min=3, k_max=4, num_repeats=3, n_stability=3, rng=np.random.default_rng(9),\n"
+        "                    max_iters=600)\n"
+        "assert 'torch' not in sys.modules, 'torch was imported on the default route'\n"
+        "sizes = res['row_clusters'][0].sum(0)\n"
+        "assert set(sizes) <= {0.0, 200.0} and (sizes == 200).sum() >= 3, sizes  # planted blocks, whatever k was selected\n"
+        "print('selected k', res['output_f'][0].shape[1], 'bisil', res['bisil'])\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "selected k" in out.stdout
+
+
+def test_native_route_is_reproducible_and_matches_the_first_version_statistically(monkeypatch):
+    """Same seed, same result (every unit has its own generator and the library's sums have fixed orders); the first
+    version of the matrix-sized steps (RESNMTF_ROUTE=torch: other permutation generator, library eigensolver) finds the
+    same biclusters on planted data."""
+    views, _ = synth.block_views(1, block=200, n_blocks=3, seed=6)
+    a = apply_resnmtf(views, k_val=3, num_repeats=3, n_stability=3, rng=np.random.default_rng(3), max_iters=800)
+    b = apply_resnmtf(views, k_val=3, num_repeats=3, n_stability=3, rng=np.random.default_rng(3), max_iters=800)
+    for key in ("output_f", "output_g", "output_s", "row_clusters", "col_clusters"):
+        assert np.array_equal(a[key][0], b[key][0])
+    assert a["bisil"] == b["bisil"]
+    monkeypatch.setenv("RESNMTF_ROUTE", "torch")
+    c = apply_resnmtf(views, k_val=3, num_repeats=3, n_stability=3, rng=np.random.default_rng(3), max_iters=800)
+    assert sorted(c["row_clusters"][0].sum(0)) == sorted(a["row_clusters"][0].sum(0)) == [200, 200, 200]
+    assert abs(c["bisil"] - a["bisil"]) < 1e-6
