@@ -42,6 +42,12 @@
 #ifndef RN_F2_PROBE
 #define RN_F2_PROBE 0                                    // 1: early non-blocking probes of the next phase's barrier
 #endif
+#ifndef RN_F2_SKEW
+#define RN_F2_SKEW 0                                     // 1: fewer blocks on the sub-partitions of the epilogue warps
+#endif
+#ifndef RN_F2_EPRE
+#define RN_F2_EPRE 1                                     // 1: epilogue warps form a group's denominator reciprocal one group early
+#endif
 #ifndef RN_F2_PF
 #define RN_F2_PF 4                                       // L2 prefetch distance in row groups (ahead of the ring copy)
 #endif
@@ -63,7 +69,13 @@ __device__ __forceinline__ void rn_f2_share(int total, int w, bool half_b, int& 
   const int base = total / RN_F2_NCW, extra = total % RN_F2_NCW;
   // position of every warp in the priority list (4 bits each): A = 0,2,4,6,8,10,1,3,5,7,9,11; B = 11,9,7,0,2,4,6,1,3,8,10,5
   const unsigned long long pos_a = 0xB5A493827160ull;  // nibble w = position of warp w in list A
+#if RN_F2_SKEW
+  // list B = 0,2,4,6,8,10,7,11,9,1,3,5: a CTA with 42 blocks carries 12 / 9 / 12 / 9 (the epilogue warps' sub-partitions
+  // keep more of their FP64 pipe)
+  const unsigned long long pos_b = 0x758463B2A190ull;
+#else
   const unsigned long long pos_b = 0x0A1926B58473ull;  // nibble w = position of warp w in list B
+#endif
   const unsigned long long pos = half_b ? pos_b : pos_a;
   nb = base + ((int)((pos >> (4 * w)) & 15) < extra ? 1 : 0);
   off = base * w;
@@ -413,24 +425,40 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
       if (!coupled && isnan(ratio)) ratio = 1.0;
       return fabs(f * ratio);
     };
+    // Everything of a group that does not depend on its partials -- old F rows, denominator, coupling sum, and the
+    // reciprocal (six dependent FP64 instructions) -- is formed for this warp's NEXT group (i + 2) in the shadow of the
+    // cluster exchange of group i, after the partial has been sent: off the chain "warp partials in -> F_new out" and
+    // off the warp's serial time per group (RN_F2_EPRE; measured before: 0.4 us of every 2.2 us group).
+    double2 fmine, den, pcn = make_double2(0.0, 0.0);
+    double w0 = 0.0, w1 = 0.0;
+    bool safe0 = false, safe1 = false;
+    auto prework = [&](int i) {
+      RN_F2_TR(lane == 0, i, 8);
+      // old F rows, denominators (+ coupling sum) of this group are in shared memory -- in particular before any peer
+      // can be released to overwrite those rows in HBM (this warp's partial of the group is sent after this point)
+      rn_mbar_wait(&aux_full[i & 3], (uint32_t)((i >> 2) & 1));
+      RN_F2_TR(lane == 0, i, 9);
+      fmine = *reinterpret_cast<const double2*>(Fo + (i & 3) * 64 + g * 8 + c0);
+      den = *reinterpret_cast<const double2*>(Dn + (i & 3) * 64 + g * 8 + c0);
+      if (coupled) pcn = *reinterpret_cast<const double2*>(Pcn + (i & 3) * 64 + g * 8 + c0);
+      w0 = fmine.x * recip(v0 ? den.x : 1.0, safe0);
+      w1 = fmine.y * recip(v1 ? den.y : 1.0, safe1);
+      __syncwarp();
+      if (lane == 0) rn_mbar_arrive(&aux_empty[i & 3]);
+    };
+#if RN_F2_EPRE
+    if (ew < NGL) prework(ew);
+#endif
     for (int i = ew; i < NGL; i += 2) {
       const int s3 = i % NPW, s4 = i & (NPEX - 1);
       const uint32_t ph3 = (uint32_t)((i / NPW) & 1), ph4 = (uint32_t)((i >> 2) & 1);
       if (lane == 0) rn_mbar_expect_tx(&pex_full[s4], csize * 512u);
-      RN_F2_TR(lane == 0, i, 8);
-      // old F rows, denominators (+ coupling sum) of this group are in shared memory -- in particular before any peer
-      // can be released to overwrite those rows in HBM
-      rn_mbar_wait(&aux_full[i & 3], ph4);
-      RN_F2_TR(lane == 0, i, 9);
-      const double2 fmine = *reinterpret_cast<const double2*>(Fo + (i & 3) * 64 + g * 8 + c0);
-      const double2 den = *reinterpret_cast<const double2*>(Dn + (i & 3) * 64 + g * 8 + c0);
-      double2 pcn = make_double2(0.0, 0.0);
-      if (coupled) pcn = *reinterpret_cast<const double2*>(Pcn + (i & 3) * 64 + g * 8 + c0);
-      bool safe0, safe1;
-      const double w0 = fmine.x * recip(v0 ? den.x : 1.0, safe0);
-      const double w1 = fmine.y * recip(v1 ? den.y : 1.0, safe1);
-      __syncwarp();
-      if (lane == 0) rn_mbar_arrive(&aux_empty[i & 3]);
+#if !RN_F2_EPRE
+      prework(i);
+#endif
+      const double2 fmine_c = fmine, den_c = den, pcn_c = pcn;  // this group's values (prework(i + 2) overwrites them)
+      const double w0_c = w0, w1_c = w1;
+      const bool safe0_c = safe0, safe1_c = safe1;
       rn_mbar_wait(&pw_full[s3], ph3);
       RN_F2_TR(lane == 0, i, 10);
       const double* pw = Pw + (s3 * NCW) * 64 + 2 * lane;
@@ -455,6 +483,9 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
         rn_st_async2(rn_mapa(my_pex + s4 * (RN_FU_MAXC * 64 * 8), rr), acc.x, acc.y,
                      rn_mapa(rn_smem_u32(&pex_full[s4]), rr));
       RN_F2_TR(lane == 0, i, 11);
+#if RN_F2_EPRE
+      if (i + 2 < NGL) prework(i + 2);
+#endif
       rn_mbar_wait_cluster(&pex_full[s4], ph4);
       RN_F2_TR(lane == 0, i, 12);
       // CTA partials in rank order, as a fixed tree over 8 slots (absent ranks count as +0)
@@ -471,15 +502,15 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
       double N0 = (c[0].x + c[2].x) + (c[4].x + c[6].x);
       double N1 = (c[0].y + c[2].y) + (c[4].y + c[6].y);
       if (coupled) {  // star_prod_relevant term (utils.r:63-78), formed by the auxiliary warp
-        N0 += pcn.x;
-        N1 += pcn.y;
+        N0 += pcn_c.x;
+        N1 += pcn_c.y;
       }
       const int64_t grp = g0 + i;
       const int64_t r = grp * 8 + g;
       double o0 = 0.0, o1 = 0.0;
       if (r < vw.n) {
-        if (v0) o0 = (safe0 && fabs(N0) < 1.0e280) ? fabs(N0 * w0) : slow(N0, den.x, fmine.x);
-        if (v1) o1 = (safe1 && fabs(N1) < 1.0e280) ? fabs(N1 * w1) : slow(N1, den.y, fmine.y);
+        if (v0) o0 = (safe0_c && fabs(N0) < 1.0e280) ? fabs(N0 * w0_c) : slow(N0, den_c.x, fmine_c.x);
+        if (v1) o1 = (safe1_c && fabs(N1) < 1.0e280) ? fabs(N1 * w1_c) : slow(N1, den_c.y, fmine_c.y);
       }
       *reinterpret_cast<double2*>(Fp + s3 * 64 + g * 8 + c0) = make_double2(o0, o1);
       __syncwarp();

@@ -57,3 +57,36 @@ resnmtf_jsd_pairs <- function(cols, pairs) {
     as.integer(pairs[, 1]), as.integer(pairs[, 2])
   )
 }
+
+# The independent fits of one apply_resnmtf() call -- the k sweep (R/main.r:270-299), the shuffled refits of
+# obtain_shuffled_f() (R/obtain_bicl.r:31-42), the resamples of stability_check() (R/stability_analysis.r:302-338) -- as
+# ONE .Call: the library uploads `data` once and runs the units on one native worker thread per GPU
+# (resnmtf_batch_run).  Every random input is drawn HERE, in the reference's order (quirk Q14): the k x k noise of
+# init_mats_inner() per view and fit, the sub-sample indices, and one seed per shuffled refit.
+#   units: list of lists with elements k, noise | init_f/init_s/init_g, rows/cols, shuffle_seed, renormalise,
+#          phi/xi/psi, row_indices/column_indices (the hash objects; converted to index maps here), n_iters
+resnmtf_device_batch <- function(data, units, prep = FALSE, n_gpus = 0L) {
+  rn <- lapply(data, rownames)
+  cn <- lapply(data, colnames)
+  units <- lapply(units, function(u) {
+    sub_r <- if (is.null(u$rows)) rn else Map(function(nm, i) nm[i], rn, u$rows)
+    sub_c <- if (is.null(u$cols)) cn else Map(function(nm, i) nm[i], cn, u$cols)
+    u$row_maps <- resnmtf_index_maps(u$row_indices, sub_r)
+    u$col_maps <- resnmtf_index_maps(u$column_indices, sub_c)
+    u$row_indices <- u$column_indices <- NULL
+    u$k <- as.integer(u$k)
+    if (!is.null(u$rows)) u$rows <- lapply(u$rows, as.integer)
+    if (!is.null(u$cols)) u$cols <- lapply(u$cols, as.integer)
+    u$n_iters <- if (is.null(u$n_iters)) NA_integer_ else as.integer(u$n_iters)
+    u
+  })
+  out <- .Call(C_resnmtf_batch, data, isTRUE(prep), units, as.integer(n_gpus))
+  for (i in seq_along(out)) { # dimnames the reference carries (R/update_steps.r:61-64)
+    u <- units[[i]]
+    for (v in seq_along(data)) {
+      rownames(out[[i]]$F[[v]]) <- if (is.null(u$rows)) rn[[v]] else rn[[v]][u$rows[[v]]]
+      rownames(out[[i]]$G[[v]]) <- if (is.null(u$cols)) cn[[v]] else cn[[v]][u$cols[[v]]]
+    }
+  }
+  out
+}

@@ -49,3 +49,15 @@ def test_fails_loudly_without_a_gpu():
         from resnmtf_b200.device import Context
 
         Context()
+
+
+def test_r_shim_compiles_against_the_r_api_declarations():
+    """No R in this image: the .Call shim is at least compiled (syntax, types, argument counts against R's C API as
+    declared in tests/r_stub/, and against include/resnmtf_b200.h) with warnings as errors."""
+    import subprocess
+
+    cmd = ["gcc", "-std=gnu99", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-fsyntax-only",
+           "-I", os.path.join(ROOT, "tests", "r_stub"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "resnmtf_b200", "r", "r_shim.c")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
