@@ -15,7 +15,7 @@
  *     from resnmtf_last_error() (thread-local).  No C++ exception crosses the ABI.
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
  *     RESNMTF_E_CUDA.
- *   - Entry points on one ctx are not re-entrant; different ctx are independent.
+ *   - Entry points on one ctx are not re-entrant; different ctx are independent (a placed fit uses all of its contexts).
  */
 #ifndef RESNMTF_B200_H
 #define RESNMTF_B200_H
@@ -45,7 +45,7 @@ extern "C" {
 #define RESNMTF_MAP_COL 1 /* rows of G (psi coupling)    -- column_indices[[v]] */
 
 /* how the per-iteration error of calculate_error() (R/utils.r:157-166) is evaluated */
-#define RESNMTF_ERR_AUTO 0      /* algebraic (no pass over X); re-done by a direct pass when < 1e-3  */
+#define RESNMTF_ERR_AUTO 0      /* algebraic (no pass over X); re-done by a direct pass when < 1e-4  */
 #define RESNMTF_ERR_ALGEBRAIC 1 /* ||X||^2 - 2<A,S> + <(F'F) S (G'G), S>, always                     */
 #define RESNMTF_ERR_DIRECT 2    /* sum (X - F S G')^2 streamed over X, always (one extra pass)       */
 
@@ -94,6 +94,16 @@ int resnmtf_device_count(void);
 /* n[v] x p[v] is the shape of view v, k[v] its number of clusters (k_vec of R/main.r:35). */
 int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* n, const int64_t* p,
                        const int32_t* k, resnmtf_fit** out);
+/* The same fit with its views PLACED on several GPUs of this process: view v lives on view_ctx[v] (contexts may repeat;
+ * all equal = resnmtf_fit_create).  What the phi / psi / xi terms of a view need from its partners -- the mapped rows of
+ * F^(w) and G^(w), the k x k S^(w) (star_prod_relevant / star_prod, R/utils.r:39-78) -- is read by the update kernels
+ * straight from the partner GPU's memory over NVLink (peer access is enabled between the contexts), and the Gauss-Seidel
+ * order of update_matrices() (R/update_steps.r:282-314) is kept across GPUs by events: a view's kernels start when the
+ * coupled views before it have finished this sweep; views that are not coupled to each other update concurrently.
+ * Results are identical to the single-GPU fit.  Every other entry point takes such a fit unchanged (set_data /
+ * attach_data / set_data_device act on the view's GPU; resnmtf_fit_profile is not available). */
+int resnmtf_fit_create_placed(resnmtf_ctx* const* view_ctx, int n_views, const int64_t* n, const int64_t* p,
+                              const int32_t* k, resnmtf_fit** out);
 int resnmtf_fit_destroy(resnmtf_fit* fit);
 
 /* Copies view v (column-major, leading dimension ld >= n[v]) to the device and computes

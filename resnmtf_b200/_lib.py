@@ -24,7 +24,7 @@ EXPORTS = (
     "resnmtf_ctx_create", "resnmtf_ctx_destroy", "resnmtf_ctx_stream", "resnmtf_ctx_synchronize",
     "resnmtf_ctx_device",
     "resnmtf_last_error", "resnmtf_version", "resnmtf_device_count",
-    "resnmtf_fit_create", "resnmtf_fit_destroy", "resnmtf_fit_set_data", "resnmtf_fit_set_data_device",
+    "resnmtf_fit_create", "resnmtf_fit_create_placed", "resnmtf_fit_destroy", "resnmtf_fit_set_data", "resnmtf_fit_set_data_device",
     "resnmtf_data_create", "resnmtf_data_create_device", "resnmtf_data_destroy", "resnmtf_fit_attach_data",
     "resnmtf_jsd_pairs",
     "resnmtf_data_create_prepped", "resnmtf_data_shape", "resnmtf_data_download", "resnmtf_data_sums",
@@ -117,6 +117,7 @@ def load():
         "resnmtf_version": (C.c_char_p, []),
         "resnmtf_device_count": (C.c_int, []),
         "resnmtf_fit_create": (C.c_int, [vp, C.c_int, pi64, pi64, pi32, C.POINTER(vp)]),
+        "resnmtf_fit_create_placed": (C.c_int, [vp, C.c_int, pi64, pi64, pi32, C.POINTER(vp)]),
         "resnmtf_fit_destroy": (C.c_int, [vp]),
         "resnmtf_fit_set_data": (C.c_int, [vp, C.c_int, vp, i64]),
         "resnmtf_fit_set_data_device": (C.c_int, [vp, C.c_int, vp, i64]),

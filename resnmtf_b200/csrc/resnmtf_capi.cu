@@ -81,7 +81,7 @@ static inline size_t fused_smem(int kind) { return kind == 2 ? rn_fused2_smem() 
 static inline int fused_threads(int kind) { return kind == 2 ? RN_F2_THREADS : RN_FU_THREADS; }
 
 // One-pass fused update of a view: cluster launch (fu_csize CTAs per cluster, fu_clusters clusters).
-static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, cudaStream_t st) {
+static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, cudaStream_t st, bool allow_pdl = true) {
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(vh.d.fu_clusters * vh.d.fu_csize));
@@ -99,7 +99,7 @@ static void launch_fused(const ViewHost& vh, const RnFit& ft, int v, int fuse, c
   // previous kernel of the stream drains; the kernel waits (griddepcontrol.wait) before it reads anything a kernel
   // wrote.  Captured into the iteration graph as a programmatic edge.
   static const bool pdl = rn_env_int("RESNMTF_NO_PDL", 0) == 0;
-  if (pdl) {
+  if (pdl && allow_pdl) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
@@ -409,8 +409,36 @@ extern "C" int resnmtf_ctx_synchronize(resnmtf_ctx* ctx) {
 // ------------------------------------------------------------------------------------------------
 // fit: creation, data, factors, restrictions
 // ------------------------------------------------------------------------------------------------
-extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* n, const int64_t* p,
-                                  const int32_t* k, resnmtf_fit** out) {
+// Peer access between the GPUs of a placed fit: direct loads / stores over NVLink into the other context's memory,
+// including what comes out of its private stream-ordered pool (pool memory needs its own access grant).
+static int enable_peers(const std::vector<resnmtf_ctx*>& ctxs) {
+  for (resnmtf_ctx* a : ctxs)
+    for (resnmtf_ctx* b : ctxs) {
+      if (a == b || a->device == b->device) continue;
+      int can = 0;
+      RN_CUDA(cudaDeviceCanAccessPeer(&can, b->device, a->device));
+      RN_CHECK(can, RESNMTF_E_CUDA, "resnmtf_fit_create_placed: the GPUs of the fit cannot access each other's memory");
+      RN_CUDA(cudaSetDevice(b->device));  // b reads / writes a's memory
+      cudaError_t e = cudaDeviceEnablePeerAccess(a->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+      } else {
+        RN_CUDA(e);
+      }
+      if (a->pooled) {
+        cudaMemAccessDesc desc;
+        std::memset(&desc, 0, sizeof(desc));
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = b->device;
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        RN_CUDA(cudaMemPoolSetAccess(a->pool, &desc, 1));
+      }
+    }
+  return RESNMTF_OK;
+}
+
+static int fit_create_common(resnmtf_ctx* ctx, resnmtf_ctx* const* view_ctx, int n_views, const int64_t* n,
+                             const int64_t* p, const int32_t* k, resnmtf_fit** out) {
   RN_CHECK(ctx && n && p && k && out, RESNMTF_E_INVALID, "resnmtf_fit_create: NULL argument");
   RN_CHECK(n_views >= 1, RESNMTF_E_INVALID, "resnmtf_fit_create: n_views must be >= 1");
   for (int v = 0; v < n_views; ++v) {
@@ -423,7 +451,7 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
   RN_CUDA(cudaSetDevice(ctx->device));
   resnmtf_fit* f = new (std::nothrow) resnmtf_fit();
   RN_CHECK(f != nullptr, RESNMTF_E_NOMEM, "resnmtf_fit_create: out of host memory");
-  f->ctx = ctx;
+  f->ctx = f->cur = ctx;
   ctx->refs.fetch_add(1);
   f->V = n_views;
   f->views.resize(n_views);
@@ -433,7 +461,34 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
     return code;
   };
   const int V = n_views;
+  if (view_ctx) {  // placed fit: the distinct contexts (home first), every one referenced by the fit
+    f->vctx.assign(view_ctx, view_ctx + V);
+    f->vdev.assign(V, 0);
+    std::vector<resnmtf_ctx*> distinct{ctx};
+    for (int v = 0; v < V; ++v) {
+      auto it = std::find(distinct.begin(), distinct.end(), view_ctx[v]);
+      if (it == distinct.end()) {
+        distinct.push_back(view_ctx[v]);
+        view_ctx[v]->refs.fetch_add(1);
+        it = distinct.end() - 1;
+      }
+      f->vdev[v] = (int)(it - distinct.begin());
+    }
+    f->devs.resize(distinct.size());
+    for (size_t i = 0; i < distinct.size(); ++i) f->devs[i].ctx = distinct[i];
+    if ((rc = enable_peers(distinct))) return fail(rc);
+    cudaSetDevice(ctx->device);
+    f->vev.assign(V, nullptr);
+    for (int v = 0; v < V; ++v) {
+      RnViewScope scope(f, v);
+      if (cudaEventCreateWithFlags(&f->vev[v], cudaEventDisableTiming) != cudaSuccess) {
+        rn_fail(RESNMTF_E_CUDA, "resnmtf_fit_create_placed: cudaEventCreate failed");
+        return fail(RESNMTF_E_CUDA);
+      }
+    }
+  }
   for (int v = 0; v < V && rc == RESNMTF_OK; ++v) {
+    RnViewScope scope(f, v);
     ViewHost& vh = f->views[v];
     std::memset(&vh.d, 0, sizeof(RnView));
     vh.d.n = n[v];
@@ -469,6 +524,23 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
     if ((rc = rn_alloc(f, &vh.xticket, 1))) break;
   }
   if (rc) return fail(rc);
+  for (size_t i = 1; i < f->devs.size(); ++i) {  // metadata copies on the other GPUs of a placed fit
+    RnDevMeta& m = f->devs[i];
+    resnmtf_ctx* saved = f->cur;
+    f->cur = m.ctx;
+    cudaSetDevice(m.ctx->device);
+    if (!rc) rc = rn_alloc(f, &m.d_views, (size_t)V);
+    if (!rc) rc = rn_alloc(f, &m.d_phi, (size_t)V * V);
+    if (!rc) rc = rn_alloc(f, &m.d_xi, (size_t)V * V);
+    if (!rc) rc = rn_alloc(f, &m.d_psi, (size_t)V * V);
+    if (!rc) rc = rn_alloc(f, &m.d_rowmap, (size_t)V * V);
+    if (!rc) rc = rn_alloc(f, &m.d_colmap, (size_t)V * V);
+    if (!rc) rc = rn_alloc(f, &m.d_rowmode, (size_t)V * V);
+    if (!rc) rc = rn_alloc(f, &m.d_colmode, (size_t)V * V);
+    f->cur = saved;
+    cudaSetDevice(saved->device);
+    if (rc) return fail(rc);
+  }
   if ((rc = rn_alloc(f, &f->d_views, (size_t)V))) return fail(rc);
   if ((rc = rn_alloc(f, &f->d_ctrl, 1))) return fail(rc);
   if ((rc = rn_alloc(f, &f->d_phi, (size_t)V * V))) return fail(rc);
@@ -502,20 +574,64 @@ extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* 
     }
     for (int v = 0; v < V; ++v) f->views[v].d.n_glob = hn[v];
   }
+  if (!f->devs.empty()) {  // devs[0] mirrors the home context's tables
+    RnDevMeta& m = f->devs[0];
+    m.d_views = f->d_views;
+    m.d_phi = f->d_phi;
+    m.d_xi = f->d_xi;
+    m.d_psi = f->d_psi;
+    m.d_rowmap = f->d_rowmap;
+    m.d_colmap = f->d_colmap;
+    m.d_rowmode = f->d_rowmode;
+    m.d_colmode = f->d_colmode;
+  }
   *out = f;
   return RESNMTF_OK;
 }
 
+extern "C" int resnmtf_fit_create(resnmtf_ctx* ctx, int n_views, const int64_t* n, const int64_t* p,
+                                  const int32_t* k, resnmtf_fit** out) {
+  return fit_create_common(ctx, nullptr, n_views, n, p, k, out);
+}
+
+extern "C" int resnmtf_fit_create_placed(resnmtf_ctx* const* view_ctx, int n_views, const int64_t* n, const int64_t* p,
+                                         const int32_t* k, resnmtf_fit** out) {
+  RN_CHECK(view_ctx && n_views >= 1, RESNMTF_E_INVALID, "resnmtf_fit_create_placed: NULL argument");
+  bool one = true;
+  for (int v = 0; v < n_views; ++v) {
+    RN_CHECK(view_ctx[v] != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_create_placed: NULL context");
+    RN_CHECK(view_ctx[v]->comm == nullptr, RESNMTF_E_INVALID,
+             "resnmtf_fit_create_placed: a row-sharded context cannot hold a placed view");
+    one = one && view_ctx[v] == view_ctx[0];
+  }
+  // all views on one context: an ordinary fit (graphs, chained launches)
+  return fit_create_common(view_ctx[0], one ? nullptr : view_ctx, n_views, n, p, k, out);
+}
+
 extern "C" int resnmtf_fit_destroy(resnmtf_fit* fit) {
   if (!fit) return RESNMTF_OK;
+  for (size_t i = 0; i < fit->devs.size(); ++i) {
+    cudaSetDevice(fit->devs[i].ctx->device);
+    cudaStreamSynchronize(fit->devs[i].ctx->stream);
+  }
   cudaSetDevice(fit->ctx->device);
   cudaStreamSynchronize(fit->ctx->stream);
   if (fit->graph_exec) cudaGraphExecDestroy(fit->graph_exec);
   if (fit->graph) cudaGraphDestroy(fit->graph);
-  for (void* p : fit->allocs) rn_dev_free(fit->ctx, p);
+  for (auto& a : fit->allocs) {
+    if (a.first != fit->ctx) cudaSetDevice(a.first->device);
+    rn_dev_free(a.first, a.second);
+    if (a.first != fit->ctx) cudaSetDevice(fit->ctx->device);
+  }
+  for (cudaEvent_t e : fit->vev)
+    if (e) cudaEventDestroy(e);
   for (ViewHost& vh : fit->views) rn_data_release(vh.shared);
+  cudaSetDevice(fit->ctx->device);
   resnmtf_ctx* ctx = fit->ctx;
+  std::vector<resnmtf_ctx*> others;
+  for (size_t i = 1; i < fit->devs.size(); ++i) others.push_back(fit->devs[i].ctx);
   delete fit;
+  for (resnmtf_ctx* o : others) rn_ctx_release(o);
   rn_ctx_release(ctx);
   return RESNMTF_OK;
 }
@@ -596,6 +712,7 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
   ViewHost& vh = fit->views[v];
   RN_CHECK(ld >= vh.d.n, RESNMTF_E_INVALID, std::string(who) + ": ld < n");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
+  RnViewScope scope(fit, v);  // a placed view lives on its own GPU
   if (vh.shared) {  // the view was attached to a shared handle: give it its own buffer again
     rn_data_release(vh.shared);
     vh.shared = nullptr;
@@ -608,7 +725,7 @@ static int set_data_common(resnmtf_fit* fit, int v, const double* x, int64_t ld,
     if (rc) return rc;
     fit->meta_dirty = true;  // X is a by-value kernel parameter: the iteration graph must be rebuilt
   }
-  int rc = upload_panels(fit->ctx, vh.d, x, ld, on_device, vh.xpart, vh.xticket, who);
+  int rc = upload_panels(fit->cur, vh.d, x, ld, on_device, vh.xpart, vh.xticket, who);
   if (rc) return rc;
   vh.has_data = true;
   if (vh.d.X8) {  // the fused path's copy of X is stale: the next plan rebuilds it
@@ -739,11 +856,12 @@ extern "C" int resnmtf_data_destroy(resnmtf_data* data) {
 extern "C" int resnmtf_fit_attach_data(resnmtf_fit* fit, int v, resnmtf_data* data) {
   RN_CHECK(fit && data, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: NULL argument");
   RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: view index out of range");
-  RN_CHECK(data->ctx == fit->ctx, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: data lives on another context");
+  RN_CHECK(data->ctx == rn_vctx(fit, v), RESNMTF_E_INVALID, "resnmtf_fit_attach_data: data lives on another context");
   ViewHost& vh = fit->views[v];
   RN_CHECK(data->n == vh.d.n && data->p == vh.d.p, RESNMTF_E_INVALID, "resnmtf_fit_attach_data: shape mismatch");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
-  RN_CUDA(cudaStreamSynchronize(fit->ctx->stream));
+  RnViewScope scope(fit, v);
+  RN_CUDA(cudaStreamSynchronize(fit->cur->stream));
   if (vh.shared) rn_data_release(vh.shared);
   else if (vh.d.X) {
     int rc = rn_free(fit, vh.d.X);
@@ -773,7 +891,8 @@ extern "C" int resnmtf_fit_set_factors(resnmtf_fit* fit, int v, const double* f,
   RN_CHECK(v >= 0 && v < fit->V, RESNMTF_E_INVALID, "resnmtf_fit_set_factors: view index out of range");
   ViewHost& vh = fit->views[v];
   RN_CUDA(cudaSetDevice(fit->ctx->device));
-  cudaStream_t st = fit->ctx->stream;
+  RnViewScope scope(fit, v);
+  cudaStream_t st = fit->cur->stream;
   const int K = vh.d.k, KP = vh.d.kp;
   const int64_t n = vh.d.n, p = vh.d.p;
   std::vector<double> fp((size_t)vh.d.ldx * KP, 0.0);  // F in the device's swizzled 64-row panel layout
@@ -848,6 +967,7 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
   RN_CHECK(len >= 0 && (len == 0 || (idx_v && idx_w)), RESNMTF_E_INVALID,
            "resnmtf_fit_set_shared_map: NULL index array");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
+  RnViewScope scope(fit, v);  // the map is read by view v's kernels: it lives on v's GPU
   const bool row = kind == RESNMTF_MAP_ROW;
   ViewHost& vh = fit->views[v];
   const ViewHost& wh = fit->views[w];
@@ -874,8 +994,8 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
     if (rc) return rc;
   }
   RN_CUDA(cudaMemcpyAsync(own[w], map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
-                          fit->ctx->stream));
-  RN_CUDA(cudaStreamSynchronize(fit->ctx->stream));
+                          fit->cur->stream));
+  RN_CUDA(cudaStreamSynchronize(fit->cur->stream));
   modes[slot] = RN_MODE_MAP;
   ptrs[slot] = own[w];
   fit->meta_dirty = true;
@@ -912,6 +1032,7 @@ static int build_plan(resnmtf_fit* fit) {
   const int g_target_dfma = sms * rn_env_int("RESNMTF_G_CTAS_PER_SM_DFMA", 3);
   int rc;
   for (int v = 0; v < fit->V; ++v) {
+    RnViewScope scope(fit, v);  // placed fit: occupancy queries, kernel attributes and workspaces on the view's GPU
     ViewHost& vh = fit->views[v];
     RnView& d = vh.d;
     // the one-pass fused kernel serves the views that qualify (fused_csize); the others of the fit run the
@@ -977,7 +1098,7 @@ static int build_plan(resnmtf_fit* fit) {
       const int64_t pp8_new = kind == 2 ? d.pp : (int64_t)csz * RN_FU_CCOLS;
       if (d.X8 && d.pp8 != pp8_new) d.X8 = nullptr;  // the copy at hand has the other kernel's width
       d.pp8 = pp8_new;
-      d.col_groups = (int)((d.pp + RN_COL_GROUP - 1) / RN_COL_GROUP);
+      d.col_groups = (int)((d.pp + RN_FU_TG - 1) / RN_FU_TG);
       d.cs = d.rs = 1;
       d.nff = 0;
       d.f_ctas = d.g_ctas = 0;
@@ -999,7 +1120,7 @@ static int build_plan(resnmtf_fit* fit) {
             convert = false;
             d.X8 = vh.shared->X8;
           } else if (!vh.shared->X8) {
-            RN_CUDA(rn_dev_alloc(fit->ctx, (void**)&vh.shared->X8, x8_count * sizeof(double)));
+            RN_CUDA(rn_dev_alloc(fit->cur, (void**)&vh.shared->X8, x8_count * sizeof(double)));
             vh.shared->pp8 = d.pp8;
             d.X8 = vh.shared->X8;
           } else {  // the handle's copy has another width and other fits may be running on it: this fit keeps its own
@@ -1012,7 +1133,7 @@ static int build_plan(resnmtf_fit* fit) {
         }
         if (convert) {
           const int blocks = (int)std::min<int64_t>(((int64_t)x8_count / 2 + 255) / 256, 1 << 20);
-          rn_panels_to_x8<<<blocks, 256, 0, fit->ctx->stream>>>(d);
+          rn_panels_to_x8<<<blocks, 256, 0, fit->cur->stream>>>(d);
           RN_CUDA(cudaGetLastError());
         }
       }
@@ -1089,7 +1210,7 @@ static int build_plan(resnmtf_fit* fit) {
     if ((rc = rn_alloc(fit, &d.Rpart, (size_t)d.row_tiles * d.resid_cs))) return rc;
     if ((rc = rn_alloc(fit, &d.tile_ticket, (size_t)d.row_tiles))) return rc;
     if ((rc = rn_alloc(fit, &d.group_ticket, (size_t)d.col_groups))) return rc;
-    RN_CUDA(cudaMemsetAsync(d.misc_ticket, 0, 4 * sizeof(int32_t), fit->ctx->stream));
+    RN_CUDA(cudaMemsetAsync(d.misc_ticket, 0, 4 * sizeof(int32_t), fit->cur->stream));
   }
   {  // persisting-L2 budget: 90 % of the carve-out, split over the views in proportion to their size
     double total = 0.0;
@@ -1152,6 +1273,35 @@ static int sync_meta(resnmtf_fit* fit) {
   }
   d.psi_total = ps;
   d.xi_total = xs;
+  // placed fit: every other GPU gets its own copy of the tables (the pointers inside reach peer memory); the control
+  // block and the error history stay on the home GPU
+  for (size_t i = 1; i < fit->devs.size(); ++i) {
+    RnDevMeta& m = fit->devs[i];
+    RN_CUDA(cudaSetDevice(m.ctx->device));
+    cudaStream_t ms = m.ctx->stream;
+    RN_CUDA(cudaMemcpyAsync(m.d_views, hv.data(), V * sizeof(RnView), cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_phi, fit->h_phi.data(), VV * sizeof(double), cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_xi, fit->h_xi.data(), VV * sizeof(double), cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_psi, fit->h_psi.data(), VV * sizeof(double), cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_rowmap, fit->h_rowmap.data(), VV * sizeof(int32_t*), cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_colmap, fit->h_colmap.data(), VV * sizeof(int32_t*), cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_rowmode, fit->h_rowmode.data(), VV, cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaMemcpyAsync(m.d_colmode, fit->h_colmode.data(), VV, cudaMemcpyHostToDevice, ms));
+    RN_CUDA(cudaStreamSynchronize(ms));
+    m.d = d;
+    m.d.views = m.d_views;
+    m.d.phi = m.d_phi;
+    m.d.xi = m.d_xi;
+    m.d.psi = m.d_psi;
+    m.d.rowmap = m.d_rowmap;
+    m.d.colmap = m.d_colmap;
+    m.d.rowmode = m.d_rowmode;
+    m.d.colmode = m.d_colmode;
+  }
+  if (!fit->devs.empty()) {
+    fit->devs[0].d = d;
+    RN_CUDA(cudaSetDevice(fit->ctx->device));
+  }
   fit->meta_dirty = false;
   // kernel parameters are baked into the graph: rebuild it
   if (fit->graph_exec) {
@@ -1163,6 +1313,54 @@ static int sync_meta(resnmtf_fit* fit) {
     fit->graph = nullptr;
   }
   return RESNMTF_OK;
+}
+
+// One update-iteration of a PLACED fit (views on several GPUs of this process; SURVEY 8e "several coupled views").
+// update_matrices() (R/update_steps.r:282-314) is a Gauss-Seidel sweep: view v sees the NEW factors of the views before
+// it and the OLD ones of the views after it.  Across GPUs that order is a chain of events: the kernels of view v are
+// enqueued on the stream of v's GPU behind (a) the event of every view w < v it is coupled to by phi, psi or xi -- w's
+// kernels of THIS sweep have finished, so the rows v's kernels read over NVLink are the new ones -- and (b) the event of
+// the last view of the PREVIOUS sweep, whose kernel did the sweep's bookkeeping (error history, stop flag): no view may
+// start a sweep before the stop rule of the one before is decided, and by then every partner w > v has finished reading
+// v's old factors.  Views that are not coupled to each other run their sweeps concurrently on their GPUs.  The partner
+// rows themselves are read by the update kernels straight from peer memory (the gather maps live on the reader's GPU).
+static int64_t enqueue_iteration_placed(resnmtf_fit* fit, bool direct) {
+  int64_t launches = 0;
+  const int V = fit->V;
+  const int last = V - 1;
+  auto coupled = [&](int v, int w) {
+    const size_t a = (size_t)w + (size_t)v * V, b = (size_t)v + (size_t)w * V;
+    return fit->h_phi[a] != 0.0 || fit->h_phi[b] != 0.0 || fit->h_psi[a] != 0.0 || fit->h_psi[b] != 0.0 ||
+           fit->h_xi[a] != 0.0 || fit->h_xi[b] != 0.0;
+  };
+  for (int v = 0; v < V; ++v) {
+    RnViewScope scope(fit, v);
+    const ViewHost& vh = fit->views[v];
+    const RnFit& ft = fit->devs[fit->vdev[v]].d;
+    cudaStream_t st = fit->cur->stream;
+    cudaStreamWaitEvent(st, fit->vev[last], 0);  // previous sweep's bookkeeping (a no-op before the first record)
+    for (int w = 0; w < v; ++w)
+      if (coupled(v, w) || (!direct && v == last)) cudaStreamWaitEvent(st, fit->vev[w], 0);
+    const int fuse = (!direct && v == last) ? 1 : 0;  // the last view's kernel also reads every view's error
+    if (vh.d.fu_csize) {
+      launch_fused(vh, ft, v, fuse, st, false);
+      launches += 1;
+    } else {
+      launch_f_step(vh, ft, v, vh.impl, st);
+      launches += 1 + launch_g_step(vh, ft, v, vh.impl, fuse, st, nullptr, &fit->comm_rc);
+    }
+    if (direct) launches += launch_residual(vh, ft, 0, st, nullptr, &fit->comm_rc);
+    if (!(direct && v == last)) cudaEventRecord(fit->vev[v], st);
+  }
+  if (direct) {  // bookkeeping as its own launch on the last view's GPU, behind every view's residual
+    RnViewScope scope(fit, last);
+    cudaStream_t st = fit->cur->stream;
+    for (int w = 0; w < last; ++w) cudaStreamWaitEvent(st, fit->vev[w], 0);
+    rn_finish<<<1, 1, 0, st>>>(fit->devs[fit->vdev[last]].d, 0);
+    cudaEventRecord(fit->vev[last], st);
+    launches += 1;
+  }
+  return launches;
 }
 
 // Enqueues one update-iteration (all views, Gauss-Seidel order) on `st`.  When ev is non-null an event
@@ -1181,6 +1379,7 @@ static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<
     ev_class->push_back(cls);
   };
   const bool direct = fit->d.err_mode == RESNMTF_ERR_DIRECT;
+  if (rn_placed(fit)) return enqueue_iteration_placed(fit, direct);
   for (int v = 0; v < fit->V; ++v) {
     const ViewHost& vh = fit->views[v];
     const int fuse = (!direct && v == fit->V - 1) ? 1 : 0;
@@ -1234,7 +1433,8 @@ static int prepare(resnmtf_fit* fit) {
   // cannot do; one kernel per view and iteration leaves nothing for a graph to save.
   bool chained = rn_env_int("RESNMTF_NO_PDL", 0) == 0 && fit->d.err_mode != RESNMTF_ERR_DIRECT;
   for (int v = 0; v < fit->V; ++v) chained = chained && fit->views[v].d.fu_csize > 0;
-  if (!fit->graph_exec && !chained && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
+  // a placed fit enqueues on one stream per GPU with events in between: plain launches, no graph
+  if (!fit->graph_exec && !chained && !rn_placed(fit) && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
     cudaStream_t st = fit->ctx->stream;
     RN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     fit->launches_per_iter = enqueue_iteration(fit, st, nullptr, nullptr);
@@ -1247,14 +1447,26 @@ static int prepare(resnmtf_fit* fit) {
   return RESNMTF_OK;
 }
 
+// every stream of a placed fit has drained (the home stream alone orders nothing on the other GPUs)
+static int sync_placed(resnmtf_fit* fit) {
+  for (size_t i = 1; i < fit->devs.size(); ++i) {
+    RN_CUDA(cudaSetDevice(fit->devs[i].ctx->device));
+    RN_CUDA(cudaStreamSynchronize(fit->devs[i].ctx->stream));
+  }
+  if (fit->devs.size() > 1) RN_CUDA(cudaSetDevice(fit->ctx->device));
+  return RESNMTF_OK;
+}
+
 static int push_ctrl(resnmtf_fit* fit) {
   RN_CUDA(cudaMemcpyAsync(fit->d_ctrl, &fit->h_ctrl, sizeof(RnCtrl), cudaMemcpyHostToDevice, fit->ctx->stream));
+  if (rn_placed(fit)) RN_CUDA(cudaStreamSynchronize(fit->ctx->stream));  // kernels on the other GPUs read it too
   return RESNMTF_OK;
 }
 
 // Reads the control block and drains the error history accumulated since the last call.
 static int pull_ctrl(resnmtf_fit* fit) {
   cudaStream_t st = fit->ctx->stream;
+  if (int rc = sync_placed(fit)) return rc;
   RN_CUDA(cudaMemcpyAsync(&fit->h_ctrl, fit->d_ctrl, sizeof(RnCtrl), cudaMemcpyDeviceToHost, st));
   RN_CUDA(cudaStreamSynchronize(st));
   const int64_t cnt = std::min<int64_t>(fit->h_ctrl.hist_count, fit->hist_cap);
@@ -1304,7 +1516,7 @@ static double alg_bytes_per_iter(const resnmtf_fit* fit) {
 }
 
 // AUTO error mode hand-over: the device paused (done == 3) at the end of a sweep whose algebraic error
-// fell below 1e-3.  Re-evaluate that sweep's error with the direct residual pass, do its bookkeeping,
+// fell below RN_AUTO_DIRECT_BELOW (1e-4).  Re-evaluate that sweep's error with the direct residual pass, do its bookkeeping,
 // and continue in DIRECT mode for the rest of the fit.
 static int handle_pause(resnmtf_fit* fit) {
   cudaStream_t st = fit->ctx->stream;
@@ -1313,7 +1525,16 @@ static int handle_pause(resnmtf_fit* fit) {
   int rc;
   if ((rc = push_ctrl(fit))) return rc;
   int nl = 1;
-  for (int v = 0; v < fit->V; ++v) nl += launch_residual(fit->views[v], fit->d, 1, st, fit->ctx, &fit->comm_rc);
+  if (rn_placed(fit)) {  // every view's residual on its own GPU, then the bookkeeping on the home GPU
+    for (int v = 0; v < fit->V; ++v) {
+      RnViewScope scope(fit, v);
+      nl += launch_residual(fit->views[v], fit->devs[fit->vdev[v]].d, 1, fit->cur->stream, nullptr, &fit->comm_rc);
+      RN_CUDA(cudaGetLastError());
+    }
+    if ((rc = sync_placed(fit))) return rc;
+  } else {
+    for (int v = 0; v < fit->V; ++v) nl += launch_residual(fit->views[v], fit->d, 1, st, fit->ctx, &fit->comm_rc);
+  }
   rn_finish<<<1, 1, 0, st>>>(fit->d, 0);
   RN_CUDA(cudaGetLastError());
   fit->counters.kernel_launches += nl;
@@ -1493,6 +1714,7 @@ extern "C" int resnmtf_fit_step(resnmtf_fit* fit) { return resnmtf_fit_run(fit, 
 
 extern "C" int resnmtf_fit_profile(resnmtf_fit* fit, int64_t n_iters, double ms[5], int64_t launches[5]) {
   RN_CHECK(fit && ms && launches, RESNMTF_E_INVALID, "resnmtf_fit_profile: NULL argument");
+  RN_CHECK(!rn_placed(fit), RESNMTF_E_UNSUPPORTED, "resnmtf_fit_profile: not available for a placed fit");
   int rc;
   if ((rc = prepare(fit))) return rc;
   cudaStream_t st = fit->ctx->stream;
@@ -1537,7 +1759,8 @@ extern "C" int resnmtf_fit_get_factors(resnmtf_fit* fit, int v, double* f, doubl
   const ViewHost& vh = fit->views[v];
   RN_CHECK(vh.has_factors, RESNMTF_E_STATE, "resnmtf_fit_get_factors: factors were never set");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
-  cudaStream_t st = fit->ctx->stream;
+  RnViewScope scope(fit, v);
+  cudaStream_t st = fit->cur->stream;
   const int K = vh.d.k, KP = vh.d.kp;
   const int64_t n = vh.d.n, p = vh.d.p;
   std::vector<double> gt, fp;
@@ -1565,8 +1788,9 @@ extern "C" int resnmtf_fit_get_factors(resnmtf_fit* fit, int v, double* f, doubl
 extern "C" int resnmtf_fit_normalise(resnmtf_fit* fit) {
   RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_normalise: fit is NULL");
   RN_CUDA(cudaSetDevice(fit->ctx->device));
-  cudaStream_t st = fit->ctx->stream;
   for (int v = 0; v < fit->V; ++v) {
+    RnViewScope scope(fit, v);
+    cudaStream_t st = fit->cur->stream;
     const ViewHost& vh = fit->views[v];
     RN_CHECK(vh.has_factors, RESNMTF_E_STATE, "resnmtf_fit_normalise: factors were never set");
     rn_factor_sums<<<2 * vh.d.k + vh.d.k * vh.d.k, 1024, 0, st>>>(vh.d);
@@ -1576,9 +1800,9 @@ extern "C" int resnmtf_fit_normalise(resnmtf_fit* fit) {
     rn_normalise<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(vh.d);
     rn_factor_sums<<<2 * vh.d.k + vh.d.k * vh.d.k, 1024, 0, st>>>(vh.d);  // keep G'G / colsums consistent with the scaled factors
     if ((rc2 = rn_allreduce(fit->ctx, vh.d.csF, (size_t)vh.d.k))) return rc2;
+    RN_CUDA(cudaGetLastError());
+    RN_CUDA(cudaStreamSynchronize(st));
   }
-  RN_CUDA(cudaGetLastError());
-  RN_CUDA(cudaStreamSynchronize(st));
   return RESNMTF_OK;
 }
 

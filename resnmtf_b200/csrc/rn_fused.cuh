@@ -40,6 +40,9 @@
 #pragma once
 #include "rn_kernels.cuh"
 
+#ifndef RN_FU_TG
+#define RN_FU_TG 64  // data columns per column group of the tail (G update, G'G | A partials); 4000 columns: 63 groups
+#endif
 #define RN_FU_NCW 9                                       // consumer warps (3 per sub-partition 0..2)
 #define RN_FU_THREADS 384                                 // 12 warps: 9 consumers, producer (3), epilogue (7), auxiliary (11)
 #define RN_FU_NB 7                                        // 16-column blocks per consumer warp and row group
@@ -675,15 +678,15 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   if (ctid == 0) atomicAdd(&vw.misc_ticket[3], 1);
 
   double* Ts = reinterpret_cast<double*>(ring);  // the ring is idle now: epilogue scratch lives there
-  double* Gs = Ts + RN_COL_GROUP * KP;
-  double* FtFs = Gs + RN_COL_GROUP * K;
+  double* Gs = Ts + RN_FU_TG * KP;
+  double* FtFs = Gs + RN_FU_TG * K;
   double* Vs = FtFs + NFF;
   double* fin = Vs + KK;
   double* Us = fin + NOUT;
   double* Sn = Us + KK;
   double* red = Sn + KK;
   const int64_t pp = vw.pp;
-  const int64_t NG = (pp + RN_COL_GROUP - 1) / RN_COL_GROUP;
+  const int64_t NG = (pp + RN_FU_TG - 1) / RN_FU_TG;
   if ((int64_t)blockIdx.x >= NG) return;  // no column group for this CTA (it must not wait: the finisher re-arms)
   if (ctid == 0) {
     while (rn_ld_acquire(&vw.misc_ticket[3]) < (int)gridDim.x) __nanosleep(32);
@@ -695,10 +698,10 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
   bool ff_ready = false;
   const int64_t tstride = vw.pp8 * KP;
   for (int64_t grp = blockIdx.x; grp < NG; grp += gridDim.x) {
-    const int64_t j0 = grp * RN_COL_GROUP;
-    const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
+    const int64_t j0 = grp * RN_FU_TG;
+    const int njb = (int)min((int64_t)(RN_FU_TG / 8), (pp - j0) >> 3);
     rn_fu_consumer_sync();  // previous group's epilogue is done with Ts / Gs
-    for (int i = ctid; i < RN_COL_GROUP * KP; i += NCT)
+    for (int i = ctid; i < RN_FU_TG * KP; i += NCT)
       Ts[i] = (i < 8 * njb * KP) ? rn_sum_wide(vw.Tpart + j0 * KP + i, tstride, (int)n_clusters) : 0.0;
     if (!ff_ready) {
       if (ctid < NFF) FtFs[ctid] = rn_sum_wide(vw.FFpart + ctid, NFF, (int)n_clusters);
@@ -713,7 +716,7 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
     }
     rn_fu_consumer_sync();
     if (ctid == 0) rn_fu_stamp(vw, 5);
-    if (ctid < RN_COL_GROUP) {
+    if (ctid < RN_FU_TG) {
       const int64_t j = j0 + ctid;
       double gn[K];
       if (j < vw.p) {
@@ -733,13 +736,13 @@ __global__ void __launch_bounds__(RN_FU_THREADS, 1) rn_fused_step(const RnView v
       double s = 0.0;
       if (o < KK) {
         const int a = o % K, b = o / K;
-        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
+        for (int i = 0; i < RN_FU_TG; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
       } else if (o < 2 * KK) {
         const int a = (o - KK) % K, b = (o - KK) / K;
-        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
+        for (int i = 0; i < RN_FU_TG; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
       } else {
         const int c = o - 2 * KK;
-        for (int i = 0; i < RN_COL_GROUP; ++i) s += Gs[i * K + c];
+        for (int i = 0; i < RN_FU_TG; ++i) s += Gs[i * K + c];
       }
       vw.GGpart[grp * NOUT + o] = s;
     }

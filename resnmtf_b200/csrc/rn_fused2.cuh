@@ -42,11 +42,14 @@
 #ifndef RN_F2_PROBE
 #define RN_F2_PROBE 0                                    // 1: early non-blocking probes of the next phase's barrier
 #endif
+#ifndef RN_F2_STAGGER
+#define RN_F2_STAGGER 0                                  // 1: one consumer warp per sub-partition runs G phase first, then F
+#endif
 #ifndef RN_F2_SKEW
 #define RN_F2_SKEW 0                                     // 1: fewer blocks on the sub-partitions of the epilogue warps
 #endif
 #ifndef RN_F2_EPRE
-#define RN_F2_EPRE 1                                     // 1: epilogue warps form a group's denominator reciprocal one group early
+#define RN_F2_EPRE 0                                     // 1: epilogue warps form a group's denominator reciprocal one group early
 #endif
 #ifndef RN_F2_PF
 #define RN_F2_PF 4                                       // L2 prefetch distance in row groups (ahead of the ring copy)
@@ -669,6 +672,23 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
         f_phase(i);
         publish(i);
       }
+#if RN_F2_STAGGER
+      // The warps of a sub-partition do not all run the same phase at the same time: the middle one of its three consumer
+      // warps (ci 4..7) does the whole G phase of group i first and the F phase of group i+2 after it, the other two the
+      // F phase first.  All warps wait for the same two events per group (X there, F_new there); staggered, the
+      // sub-partition's FP64 pipe has another warp's MMAs to run while one of them sits in such a wait.
+      if ((ci >> 2) == 1) {
+        for (int i = 0; i < NGL; ++i) {
+          g_phase_a(i);
+          g_phase_b(i);
+          if (i + 2 < NGL) {
+            f_phase(i + 2);
+            publish(i + 2);
+          }
+        }
+        return;
+      }
+#endif
       for (int i = 0; i < NGL; ++i) {
 #if RN_F2_FFIRST
         if (i + 2 < NGL) {
@@ -740,15 +760,15 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
   if (ctid == 0) atomicAdd(&vw.misc_ticket[3], 1);
 
   double* Ts = reinterpret_cast<double*>(ring);  // the ring is idle now: epilogue scratch lives there
-  double* Gs = Ts + RN_COL_GROUP * KP;
-  double* FtFs = Gs + RN_COL_GROUP * K;
+  double* Gs = Ts + RN_FU_TG * KP;
+  double* FtFs = Gs + RN_FU_TG * K;
   double* Vs = FtFs + NFF;
   double* fin = Vs + KK;
   double* Us = fin + NOUT;
   double* Sn = Us + KK;
   double* red = Sn + KK;
   const int64_t pp = vw.pp;
-  const int64_t NG = (pp + RN_COL_GROUP - 1) / RN_COL_GROUP;
+  const int64_t NG = (pp + RN_FU_TG - 1) / RN_FU_TG;
   if ((int64_t)blockIdx.x >= NG) return;  // no column group for this CTA (it must not wait: the finisher re-arms)
   if (ctid == 0) {
     while (rn_ld_acquire(&vw.misc_ticket[3]) < (int)gridDim.x) __nanosleep(32);
@@ -760,10 +780,10 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
   bool ff_ready = false;
   const int64_t tstride = vw.pp8 * KP;
   for (int64_t grp = blockIdx.x; grp < NG; grp += gridDim.x) {
-    const int64_t j0 = grp * RN_COL_GROUP;
-    const int njb = (int)min((int64_t)8, (pp - j0) >> 3);
+    const int64_t j0 = grp * RN_FU_TG;
+    const int njb = (int)min((int64_t)(RN_FU_TG / 8), (pp - j0) >> 3);
     rn_f2_consumer_sync();  // previous group's epilogue is done with Ts / Gs
-    for (int i = ctid; i < RN_COL_GROUP * KP; i += NCT)
+    for (int i = ctid; i < RN_FU_TG * KP; i += NCT)
       Ts[i] = (i < 8 * njb * KP) ? rn_sum_wide(vw.Tpart + j0 * KP + i, tstride, (int)n_clusters) : 0.0;
     if (!ff_ready) {
       if (ctid < NFF) FtFs[ctid] = rn_sum_wide(vw.FFpart + ctid, NFF, (int)n_clusters);
@@ -778,7 +798,7 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
     }
     rn_f2_consumer_sync();
     if (ctid == 0) rn_fu_stamp(vw, 5);
-    if (ctid < RN_COL_GROUP) {
+    if (ctid < RN_FU_TG) {
       const int64_t j = j0 + ctid;
       double gn[K];
       if (j < vw.p) {
@@ -798,13 +818,13 @@ __global__ void __launch_bounds__(RN_F2_THREADS, 1) rn_fused2_step(const RnView 
       double s = 0.0;
       if (o < KK) {
         const int a = o % K, b = o / K;
-        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
+        for (int i = 0; i < RN_FU_TG; ++i) s = fma(Gs[i * K + a], Gs[i * K + b], s);
       } else if (o < 2 * KK) {
         const int a = (o - KK) % K, b = (o - KK) / K;
-        for (int i = 0; i < RN_COL_GROUP; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
+        for (int i = 0; i < RN_FU_TG; ++i) s = fma(Ts[i * KP + a], Gs[i * K + b], s);
       } else {
         const int c = o - 2 * KK;
-        for (int i = 0; i < RN_COL_GROUP; ++i) s += Gs[i * K + c];
+        for (int i = 0; i < RN_FU_TG; ++i) s += Gs[i * K + c];
       }
       vw.GGpart[grp * NOUT + o] = s;
     }

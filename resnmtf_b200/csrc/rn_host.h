@@ -165,11 +165,32 @@ struct ViewHost {
   int32_t* xticket = nullptr;
 };
 
-struct resnmtf_fit {
+// Per-GPU copy of a fit's metadata (PLACED fits only: the views of one fit live on several GPUs of one process,
+// resnmtf_fit_create_placed).  Every device reads its own copy of the view table, the restriction matrices and the map
+// tables; the pointers inside refer to peer memory where a partner view lives on another GPU.
+struct RnDevMeta {
   resnmtf_ctx* ctx = nullptr;
+  RnFit d;
+  RnView* d_views = nullptr;
+  double *d_phi = nullptr, *d_xi = nullptr, *d_psi = nullptr;
+  const int32_t** d_rowmap = nullptr;
+  const int32_t** d_colmap = nullptr;
+  int8_t *d_rowmode = nullptr, *d_colmode = nullptr;
+};
+
+struct resnmtf_fit {
+  resnmtf_ctx* ctx = nullptr;   // home context: control block, error history, metadata of a single-GPU fit
+  resnmtf_ctx* cur = nullptr;   // context device allocations / frees go to right now (RnViewScope; normally == ctx)
   int V = 0;
   std::vector<ViewHost> views;
-  std::vector<void*> allocs;
+  std::vector<std::pair<resnmtf_ctx*, void*>> allocs;
+  // placed fit (coupled views on different GPUs): context of every view, the distinct contexts with their
+  // metadata copies (devs[0] is the home context), the view -> devs index, and one event per view recorded after the
+  // view's last kernel of a sweep (what the Gauss-Seidel order of update_matrices() chains on across GPUs)
+  std::vector<resnmtf_ctx*> vctx;
+  std::vector<RnDevMeta> devs;
+  std::vector<int> vdev;
+  std::vector<cudaEvent_t> vev;
   RnFit d;               // passed by value to the kernels
   RnView* d_views = nullptr;
   RnCtrl* d_ctrl = nullptr;
@@ -197,22 +218,53 @@ struct resnmtf_fit {
   RnCtrl h_ctrl{};
 };
 
+inline bool rn_placed(const resnmtf_fit* f) { return !f->vctx.empty(); }
+inline resnmtf_ctx* rn_vctx(const resnmtf_fit* f, int v) { return f->vctx.empty() ? f->ctx : f->vctx[v]; }
+
+// Makes the context of view v (v < 0: the home context) the fit's current one -- CUDA device, allocation target, stream
+// of fit->cur -- for the lifetime of the scope.  A no-op in effect for single-GPU fits.
+struct RnViewScope {
+  resnmtf_fit* f;
+  resnmtf_ctx* saved;
+  RnViewScope(resnmtf_fit* fit, int v) : f(fit), saved(fit->cur) {
+    f->cur = v < 0 ? f->ctx : rn_vctx(f, v);
+    if (f->cur != saved) cudaSetDevice(f->cur->device);
+  }
+  ~RnViewScope() {
+    if (f->cur != saved) cudaSetDevice(saved->device);
+    f->cur = saved;
+  }
+};
+
+// device memory on the fit's CURRENT context (fit->cur), released with the fit
 template <typename T>
 inline int rn_alloc(resnmtf_fit* f, T** out, size_t count, bool zero = true) {
   void* p = nullptr;
   size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  RN_CUDA(rn_dev_alloc(f->ctx, &p, bytes));
-  f->allocs.push_back(p);
-  if (zero) RN_CUDA(cudaMemsetAsync(p, 0, bytes, f->ctx->stream));
+  RN_CUDA(rn_dev_alloc(f->cur, &p, bytes));
+  f->allocs.emplace_back(f->cur, p);
+  if (zero) RN_CUDA(cudaMemsetAsync(p, 0, bytes, f->cur->stream));
   *out = static_cast<T*>(p);
   return RESNMTF_OK;
 }
 
 inline int rn_free(resnmtf_fit* f, void* p) {
   if (!p) return RESNMTF_OK;
-  auto it = std::find(f->allocs.begin(), f->allocs.end(), p);
-  if (it != f->allocs.end()) f->allocs.erase(it);
-  RN_CUDA(rn_dev_free(f->ctx, p));
+  resnmtf_ctx* owner = f->cur;
+  for (auto it = f->allocs.begin(); it != f->allocs.end(); ++it)
+    if (it->second == p) {
+      owner = it->first;
+      f->allocs.erase(it);
+      break;
+    }
+  if (owner != f->cur) {
+    cudaSetDevice(owner->device);
+    cudaError_t e = rn_dev_free(owner, p);
+    cudaSetDevice(f->cur->device);
+    RN_CUDA(e);
+    return RESNMTF_OK;
+  }
+  RN_CUDA(rn_dev_free(owner, p));
   return RESNMTF_OK;
 }
 

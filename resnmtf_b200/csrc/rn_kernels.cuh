@@ -288,7 +288,10 @@ __device__ __forceinline__ void rn_view_finish(const RnView& vw, const RnFit& ft
     vw.scal[1] = e;
     vw.scal[2] = e;
     vw.flags[0] = (ft.err_mode == 2) ? 1 : 0;  // DIRECT: the residual pass that follows overwrites scal[1]
-    const bool want = ft.err_mode == 0 && e < 1.0e-3;  // AUTO: cancellation would cost digits
+    // AUTO: the algebraic form loses digits to cancellation -- measured relative deviation from the direct residual
+    // ~1e-15 / e with a factor of 1..10 (<= 1e-10 for e in [1e-4, 1e-3), up to 8e-10 in [1e-5, 1e-4)) -- so the direct
+    // residual pass takes over below RN_AUTO_DIRECT_BELOW, a factor of 10 inside the 1e-9 bar
+    const bool want = ft.err_mode == 0 && e < RN_AUTO_DIRECT_BELOW;
     if (want) ft.ctrl->want_direct = 1;
     if (fuse_finish) {  // the other views' errors were written by earlier launches, this view's by this thread
       if (ft.err_mode == 0 && (want || cc.want_direct)) {

@@ -11,6 +11,9 @@
 //                  uniform / vector load in the X.G pass and one gather in the psi coupling.
 //   S, F'F, G'G, A  k x k column-major compact, lambda/mu/colsums length k.
 #pragma once
+// error mode AUTO: per-view error below which the algebraic form of calculate_error() (R/utils.r:157-166) hands over to the
+// direct residual pass (rn_view_finish, rn_kernels.cuh)
+#define RN_AUTO_DIRECT_BELOW 1.0e-4
 #include <stdint.h>
 
 #define RN_MAXK 16
@@ -33,7 +36,7 @@ struct RnCtrl {
   double tol;
   double last_diff;
   int64_t direct_passes;
-  int32_t want_direct;  // sticky: some view's algebraic error fell below 1e-3 (AUTO mode)
+  int32_t want_direct;  // sticky: some view's algebraic error fell below RN_AUTO_DIRECT_BELOW (AUTO mode)
   int32_t pad_;
 };
 

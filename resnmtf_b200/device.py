@@ -237,10 +237,15 @@ class DeviceData:
 
 
 class DeviceFit:
-    """Device-resident state of one fit.  Shapes: view v is n[v] x p[v] with k[v] clusters."""
+    """Device-resident state of one fit.  Shapes: view v is n[v] x p[v] with k[v] clusters.  ``ctx`` is a Context, or a
+    list with one Context per view: the views are then placed on those GPUs (resnmtf_fit_create_placed) and the coupled
+    factor rows travel over NVLink inside the update kernels."""
 
     def __init__(self, ctx, n, p, k):
         self._lib = L.require_device()
+        self.view_ctx = list(ctx) if isinstance(ctx, (list, tuple)) else None
+        if self.view_ctx is not None:
+            ctx = self.view_ctx[0]
         self.ctx = ctx
         self.n = [int(x) for x in n]
         self.p = [int(x) for x in p]
@@ -253,7 +258,13 @@ class DeviceFit:
         ap = (C.c_int64 * V)(*self.p)
         ak = (C.c_int32 * V)(*self.k)
         h = C.c_void_p()
-        L.check(self._lib.resnmtf_fit_create(ctx._h, V, an, ap, ak, C.byref(h)))
+        if self.view_ctx is not None:
+            if len(self.view_ctx) != V:
+                raise ValueError("one context per view")
+            actx = (C.c_void_p * V)(*[c._h.value for c in self.view_ctx])
+            L.check(self._lib.resnmtf_fit_create_placed(actx, V, an, ap, ak, C.byref(h)))
+        else:
+            L.check(self._lib.resnmtf_fit_create(ctx._h, V, an, ap, ak, C.byref(h)))
         self._h = h
 
     # ---- inputs ------------------------------------------------------------------------------

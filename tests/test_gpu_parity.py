@@ -245,3 +245,58 @@ def test_shared_data_handle_matches_private_copy(ctx):
             assert np.array_equal(a, b)
         assert np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
     data.close()
+
+
+def clean_block_problem(sigma, n=1500, p=600, k=3, seed=11):
+    """Three disjoint blocks of height 10 (the reference's test data, test-resnmtf.R:38-52) with little noise, factors
+    started near the blocks: the error falls through 1e-3 within a few sweeps."""
+    rng = np.random.default_rng(seed)
+    x = sigma * np.abs(rng.standard_normal((n, p)))
+    for b in range(3):
+        x[b * n // 3:(b + 1) * n // 3, b * p // 3:(b + 1) * p // 3] += 10.0
+    x = synth.prep(x)
+    f = 0.1 * np.abs(rng.standard_normal((n, k)))
+    g = 0.1 * np.abs(rng.standard_normal((p, k)))
+    for b in range(3):
+        f[b * n // 3:(b + 1) * n // 3, b] += 1.0
+        g[b * p // 3:(b + 1) * p // 3, b] += 1.0
+    f /= f.sum(0)
+    g /= g.sum(0)
+    s = np.eye(k) + 0.05 * np.abs(rng.standard_normal((k, k)))
+    return Problem([x], [k], [f], [s], [g])
+
+
+def test_auto_error_mode_stays_on_the_one_pass_path_above_1e_4(ctx):
+    """AUTO error mode on clean data: between 1e-3 and 1e-4 the algebraic error still holds the 1e-9 bar (deviation
+    ~1e-15 / err), so no direct residual pass runs and the fit keeps one launch and one read of X per sweep; the whole
+    error history and the stop sweep are the oracle's."""
+    prob = clean_block_problem(sigma=0.1)
+    ref = prob.oracle()
+    assert 1.0e-4 < ref["All_Error"][-1] < 1.0e-3
+    fit = prob.device_fit(ctx, err_mode=L.ERR_AUTO)
+    try:
+        done = fit.run(None, 1.0e-6)
+        assert done == len(ref["All_Error"])
+        assert rel_err(fit.errors(), ref["All_Error"]) <= RTOL
+        c = fit.counters()
+        assert c["direct_error_passes"] == 0 and c["impl"] == L.IMPL_FUSED
+        assert c["kernel_launches"] <= 32  # one launch per enqueued sweep (one batch of 32), none for the error
+    finally:
+        fit.close()
+
+
+def test_auto_error_mode_hands_over_below_1e_4(ctx):
+    """Cleaner data: the error drops below 1e-4, where cancellation would cost the algebraic form its ninth digit; the
+    direct residual pass takes over from that sweep on and the history still matches to 1e-9."""
+    prob = clean_block_problem(sigma=0.01)
+    ref = prob.oracle()
+    assert ref["All_Error"][-1] < 1.0e-5
+    fit = prob.device_fit(ctx, err_mode=L.ERR_AUTO)
+    try:
+        done = fit.run(None, 1.0e-6)
+        assert done == len(ref["All_Error"])
+        assert rel_err(fit.errors(), ref["All_Error"]) <= RTOL
+        below = int((np.asarray(ref["All_Error"]) < 1.0e-4).sum())
+        assert fit.counters()["direct_error_passes"] >= 1 and below >= 1
+    finally:
+        fit.close()

@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
 # A/B of one-pass kernel builds on one box.
 # usage: tools/gpu_f2.sh <outdir> [variant ...]   variant: k1 (in-tree library, first generation forced) | k2 (in-tree,
-#        second generation forced) | auto (in-tree, the plan's choice) | <name> (= ab/lib_<name>.so, second generation forced)
+#        second generation forced) | auto (in-tree, the plan's choice) | <name> (= ab/lib_<name>.so, second generation
+#        forced) | <name>@1 (the same library, first generation forced)
 set -u
 o=${1:-gpurun_out/f2}; shift
 mkdir -p "$o"
@@ -13,6 +14,7 @@ for v in "$@"; do
     k1) export RESNMTF_FUSED_KIND=1;;
     k2) export RESNMTF_FUSED_KIND=2;;
     auto) ;;
+    *@1) export RESNMTF_FUSED_KIND=1 RESNMTF_B200_LIB=$PWD/ab/lib_${v%@1}.so;;
     *) export RESNMTF_FUSED_KIND=2 RESNMTF_B200_LIB=$PWD/ab/lib_$v.so;;
   esac
   timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-sharded --no-ksweep > "$o/ab_$v.json" 2> "$o/ab_$v.err"
