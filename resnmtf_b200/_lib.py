@@ -104,6 +104,18 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with resnmtf_b200/csrc/build.sh "
             "(or __graft_entry__.build()).  resnmtf_b200 has no CPU fallback.")
+    if not os.environ.get("RESNMTF_NCCL_LIB"):
+        # The row-sharded path resolves NCCL with dlopen on first use.  When this interpreter carries a pip-bundled NCCL
+        # (the one torch links against), that copy must be the one in the process: an older system libnccl.so.2 loaded
+        # first would be handed to a later `import torch` by SONAME and break it.
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec is not None and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["RESNMTF_NCCL_LIB"] = cand
+                break
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     pd, pi32, pi64 = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)

@@ -36,10 +36,23 @@ inline RnNccl& rn_nccl() {
   static bool tried = false;
   if (!tried) {
     tried = true;
+    // Order: (1) an NCCL this process has ALREADY loaded (a host framework's bundled copy: loading a second, older
+    // libnccl.so.2 beside it -- or before it -- would make the framework bind to the wrong one by SONAME);
+    // (2) the path in RESNMTF_NCCL_LIB (the Python binding points it at the pip-bundled library before first use);
+    // (3) the system library.  RTLD_LOCAL: this library's NCCL symbols are looked up with dlsym, nobody else's are
+    // affected.
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
-      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
       if (api.handle) break;
+    }
+    if (!api.handle) {
+      const char* forced = std::getenv("RESNMTF_NCCL_LIB");
+      if (forced && *forced) api.handle = dlopen(forced, RTLD_NOW | RTLD_LOCAL);
+    }
+    for (const char* nm : names) {
+      if (api.handle) break;
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
     }
     if (api.handle) {
       api.GetUniqueId = (int (*)(rn_ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");

@@ -407,9 +407,77 @@ SEXP C_resnmtf_batch(SEXP data, SEXP prep, SEXP units, SEXP n_gpus) {
   return out;
 }
 
+/* ---- SVD initialisation and bisilhouette on the device ------------------------------------
+ * C_resnmtf_svd_topk(x, k): what init_mats_inner() takes from svd(x) (R/update_steps.r:92-95) -- list(u = |U[, 1:k]|,
+ * d = d[1:k], v = |V[, 1:k]|) -- from resnmtf_data_svd_topk (Gram matrix of the smaller side + filtered subspace
+ * iteration on the GPU instead of a full LAPACK svd).
+ * C_resnmtf_bisil(x, row_clusters, col_clusters, method): bisilhouette::bisilhouette(x, row_clusters, col_clusters,
+ * method)$bisil as obtain_biclusters() calls it (R/obtain_bicl.r:190-199); method 0 euclidean, 1 manhattan, 2 cosine.
+ * Returns list(bisil = , vals = per-bicluster values). */
+static void data_finalizer(SEXP guard) {
+  resnmtf_data* d = (resnmtf_data*)R_ExternalPtrAddr(guard);
+  if (d) {
+    resnmtf_data_destroy(d);
+    R_ClearExternalPtr(guard);
+  }
+}
+
+static SEXP upload_view(SEXP x, resnmtf_data** out) { /* returns the PROTECTed guard of the handle */
+  if (!Rf_isReal(x) || !Rf_isMatrix(x)) Rf_error("x must be a numeric matrix");
+  if (!g_ctx && resnmtf_ctx_create(-1, &g_ctx) != RESNMTF_OK) Rf_error("%s", resnmtf_last_error());
+  resnmtf_data* d = NULL;
+  if (resnmtf_data_create(g_ctx, Rf_nrows(x), Rf_ncols(x), REAL(x), Rf_nrows(x), &d) != RESNMTF_OK)
+    Rf_error("%s", resnmtf_last_error());
+  SEXP guard = PROTECT(R_MakeExternalPtr(d, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(guard, data_finalizer, TRUE);
+  *out = d;
+  return guard;
+}
+
+SEXP C_resnmtf_svd_topk(SEXP x, SEXP k) {
+  const int kk = Rf_asInteger(k);
+  resnmtf_data* d = NULL;
+  SEXP guard = upload_view(x, &d);
+  const char* names[] = {"u", "d", "v", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SEXP u = Rf_allocMatrix(REALSXP, Rf_nrows(x), kk);
+  SET_VECTOR_ELT(out, 0, u);
+  SEXP dd = Rf_allocVector(REALSXP, kk);
+  SET_VECTOR_ELT(out, 1, dd);
+  SEXP v = Rf_allocMatrix(REALSXP, Rf_ncols(x), kk);
+  SET_VECTOR_ELT(out, 2, v);
+  const int rc = resnmtf_data_svd_topk(d, kk, REAL(u), REAL(dd), REAL(v));
+  data_finalizer(guard);
+  UNPROTECT(2);
+  if (rc != RESNMTF_OK) Rf_error("%s", resnmtf_last_error());
+  return out;
+}
+
+SEXP C_resnmtf_bisil(SEXP x, SEXP row_cl, SEXP col_cl, SEXP method) {
+  if (!Rf_isReal(row_cl) || !Rf_isReal(col_cl) || Rf_nrows(row_cl) != Rf_nrows(x) || Rf_nrows(col_cl) != Rf_ncols(x) ||
+      Rf_ncols(row_cl) != Rf_ncols(col_cl))
+    Rf_error("row_clusters must be n x k and col_clusters p x k numeric matrices");
+  const int kk = Rf_ncols(row_cl);
+  resnmtf_data* d = NULL;
+  SEXP guard = upload_view(x, &d);
+  const char* names[] = {"bisil", "vals", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+  SEXP vals = Rf_allocVector(REALSXP, kk);
+  SET_VECTOR_ELT(out, 1, vals);
+  double bisil = 0.0;
+  const int rc = resnmtf_data_bisil(d, REAL(row_cl), REAL(col_cl), kk, Rf_asInteger(method), REAL(vals), &bisil);
+  SET_VECTOR_ELT(out, 0, Rf_ScalarReal(bisil));
+  data_finalizer(guard);
+  UNPROTECT(2);
+  if (rc != RESNMTF_OK) Rf_error("%s", resnmtf_last_error());
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {{"C_resnmtf_fit", (DL_FUNC)&C_resnmtf_fit, 12},
                                                {"C_resnmtf_jsd_pairs", (DL_FUNC)&C_resnmtf_jsd_pairs, 5},
                                                {"C_resnmtf_batch", (DL_FUNC)&C_resnmtf_batch, 4},
+                                               {"C_resnmtf_svd_topk", (DL_FUNC)&C_resnmtf_svd_topk, 2},
+                                               {"C_resnmtf_bisil", (DL_FUNC)&C_resnmtf_bisil, 4},
                                                {NULL, NULL, 0}};
 
 void R_init_resnmtf(DllInfo* dll) {

@@ -90,3 +90,19 @@ resnmtf_device_batch <- function(data, units, prep = FALSE, n_gpus = 0L) {
   }
   out
 }
+
+# init_mats_inner() (R/update_steps.r:78-125) with the three pieces of svd(x) it uses computed on the GPU: replace
+#   ss <- svd(x[[i]])   by   ss <- resnmtf_svd_topk(x[[i]], k_vec[i])   (ss$u, ss$d, ss$v already truncated to k and made
+# non-negative by abs(), which is all the function does with them).
+resnmtf_svd_topk <- function(x, k) {
+  storage.mode(x) <- "double"
+  .Call(C_resnmtf_svd_topk, x, as.integer(k))
+}
+
+# bisilhouette::bisilhouette(x, row_clusters, col_clusters, method = distance)$bisil as obtain_biclusters() calls it
+# (R/obtain_bicl.r:190-199), distance blocks on the GPU.
+resnmtf_bisil <- function(x, row_clusters, col_clusters, method = "euclidean") {
+  storage.mode(x) <- storage.mode(row_clusters) <- storage.mode(col_clusters) <- "double"
+  m <- match(method, c("euclidean", "manhattan", "cosine")) - 1L
+  .Call(C_resnmtf_bisil, x, row_clusters, col_clusters, m)$bisil
+}
