@@ -24,6 +24,7 @@ driver's default run (--steps 20) lasts about a second and the clock sampler see
   sharded    BASELINE configs[4] structure: one view ROW-SHARDED over the N ranks of the run through the library's
              own NCCL communicator (resnmtf_ctx_join), one 250000 x 20000 shard (40 GB) per GPU generated on the
              device; at N = 1 the same code path on a communicator of one rank
+  toy        BASELINE configs[0] (README toy, 64 KB of X): update-iterations/s of the persistent single-CTA loop
   k_sweep_wall   wall time of ONE default apply_resnmtf call (k sweep 3..8 + spurious-bicluster removal + stability:
              66 fits) on the bench view through the public API, on the N GPUs of the run (strong scaling: the work is
              fixed) -- first call and steady state -- measured by rank 0 after the timed region, when the other ranks
@@ -66,6 +67,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the row-sharded leg (configs[4] shard per GPU)")
+    ap.add_argument("--no-toy", action="store_true", help="skip the configs[0] leg (README toy, persistent single-CTA loop)")
     ap.add_argument("--no-ksweep", action="store_true",
                     help="skip the wall time of the default apply_resnmtf call (BASELINE metric, third part)")
     return ap.parse_args()
@@ -92,6 +94,48 @@ def make_workload(rank=0):
     x = synth.prep(x)
     inits = {k: synth.random_factors(N_ROWS, N_COLS, k, rng) for k in K_SWEEP}
     return x, inits
+
+
+def toy_leg(iters=20000):
+    """BASELINE configs[0] (the README toy: 2 views 100 x 50 and 100 x 30 with shared rows, phi[1,2] = 200, k = 3): its
+    64 KB of X are launch-latency-bound, so the whole loop runs as ONE persistent CTA (RESNMTF_IMPL_SMALL); reported as
+    update-iterations/s over `iters` fixed sweeps (R/main.r:83-108), one launch per 4096 sweeps (the size of the
+    error-history buffer the host drains)."""
+    from resnmtf_b200 import _lib as L
+    from resnmtf_b200 import synth
+    from resnmtf_b200.device import Context, DeviceFit
+
+    try:
+        rng = np.random.default_rng(synth.config_seed(1, 0))
+        x1, rows, _ = synth.planted_view(100, 50, 3, rng, row_prob=0.5, col_prob=0.4, sigma=1.0)
+        x2, _, _ = synth.planted_view(100, 30, 3, rng, row_prob=0.5, col_prob=0.4, sigma=0.01, rows=rows)
+        data = [synth.prep(x1), synth.prep(x2)]
+        phi = np.zeros((2, 2))
+        phi[0, 1] = phi[1, 0] = 200.0
+        ctx = Context()
+        fit = DeviceFit(ctx, [100, 100], [50, 30], [3, 3])
+        fit.set_options(err_mode=L.ERR_ALGEBRAIC)
+        for v in range(2):
+            fit.set_data(v, data[v])
+            fit.set_factors(v, *synth.random_factors(100, data[v].shape[1], 3, rng))
+        fit.set_restrictions(phi, None, None)
+        idx = np.arange(100, dtype=np.int32)
+        fit.set_shared_map(L.MAP_ROW, 0, 1, idx, idx)
+        fit.set_shared_map(L.MAP_ROW, 1, 0, idx, idx)
+        fit.run(200)
+        t0 = time.perf_counter()
+        fit.run(iters)
+        wall = time.perf_counter() - t0
+        c = fit.counters()
+        out = {"workload": "configs[0]: README toy, 2 views 100x50 + 100x30, shared rows, phi = 200, k = 3, fixed sweeps",
+               "update_iterations_per_s": iters / (c["device_ms"] * 1e-3), "us_per_update_iteration": c["device_ms"] * 1e3 / iters,
+               "wall_update_iterations_per_s": iters / wall, "iters": iters, "launches": int(c["kernel_launches"]),
+               "impl": int(c["impl"]), "bound": "latency (64 KB of X): one persistent CTA, no roofline"}
+        fit.close()
+        ctx.close()
+        return out
+    except Exception as exc:  # noqa: BLE001 - the headline line must still be printed
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def ksweep_wall(x, n_gpus):
@@ -521,6 +565,7 @@ def run_gpu(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    toy = None if args.no_toy else toy_leg()
     ksweep = None if args.no_ksweep else ksweep_wall(x, world)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -528,7 +573,7 @@ def run_gpu(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-        "cpu_baseline": cpu, "sharded": sharded, "k_sweep_wall": ksweep, "impl": "b200",
+        "cpu_baseline": cpu, "sharded": sharded, "toy": toy, "k_sweep_wall": ksweep, "impl": "b200",
     }
     print(json.dumps(line), flush=True)
 

@@ -57,7 +57,12 @@ extern "C" {
 #define RESNMTF_IMPL_FUSED 4 /* one pass over X per update-iteration: 8-row groups resident in the shared memory of a
                                 cluster of 1..8 CTAs do the F step and the G step (k <= 8, p <= 8064, one GPU per view,
                                 at most 7 phi partners); views that do not qualify run RESNMTF_IMPL_TMA.  This is what
-                                RESNMTF_IMPL_AUTO picks */
+                                RESNMTF_IMPL_AUTO picks for views of matrix size */
+#define RESNMTF_IMPL_SMALL 5 /* the whole loop of a tiny fit (BASELINE configs[0]: every view <= 1024 x 1024 padded and <= 1 MB,
+                                k <= 8, one GPU) as ONE persistent launch of one CTA: all views, all sweeps of a batch, the stop
+                                rule on the device.  RESNMTF_IMPL_AUTO picks it for fits of at most 16384 padded entries in
+                                total (where it beats one launch per view and sweep); a fit that does not qualify runs the
+                                streaming kernels */
 
 typedef struct resnmtf_ctx resnmtf_ctx;
 typedef struct resnmtf_fit resnmtf_fit;

@@ -17,7 +17,7 @@ E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_NAN, E_UNSUPPORTED, E_COMM = -1, -2, -3, 
 MAX_K = 16
 MAP_ROW, MAP_COL = 0, 1
 ERR_AUTO, ERR_ALGEBRAIC, ERR_DIRECT = 0, 1, 2
-IMPL_AUTO, IMPL_DFMA, IMPL_DMMA, IMPL_TMA, IMPL_FUSED = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_DFMA, IMPL_DMMA, IMPL_TMA, IMPL_FUSED, IMPL_SMALL = 0, 1, 2, 3, 4, 5
 
 # every symbol include/resnmtf_b200.h declares (tests check the library exports all of them)
 EXPORTS = (

@@ -23,6 +23,7 @@
 // ------------------------------------------------------------------------------------------------
 #define RN_K_CASES_LE8(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #define RN_K_CASES_GT8(X) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#include "rn_small.cuh"
 
 typedef void (*FStepSkFn)(const RnView, const RnFit, const int);
 typedef void (*GStepSkFn)(const RnView, const RnFit, const int, const int);
@@ -1005,7 +1006,7 @@ extern "C" int resnmtf_fit_set_shared_map(resnmtf_fit* fit, int kind, int v, int
 
 extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl) {
   RN_CHECK(fit != nullptr, RESNMTF_E_INVALID, "resnmtf_fit_set_options: fit is NULL");
-  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= 4, RESNMTF_E_INVALID,
+  RN_CHECK(err_mode >= 0 && err_mode <= 2 && impl >= 0 && impl <= RESNMTF_IMPL_SMALL, RESNMTF_E_INVALID,
            "resnmtf_fit_set_options: unknown option value");
   if (fit->err_mode != err_mode) {
     fit->meta_dirty = true;
@@ -1024,7 +1025,28 @@ extern "C" int resnmtf_fit_set_options(resnmtf_fit* fit, int err_mode, int impl)
 static int build_plan(resnmtf_fit* fit) {
   const int sms = fit->ctx->sm_count;
   int impl = fit->impl_req;
-  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_FUSED);
+  if (impl == RESNMTF_IMPL_AUTO) impl = rn_env_int("RESNMTF_IMPL", RESNMTF_IMPL_AUTO);
+  // Fits whose every view is tiny run the whole loop as one persistent CTA (rn_small.cuh): picked by AUTO and by
+  // RESNMTF_IMPL_SMALL when every view qualifies (k <= 8, at most 1024 padded rows and columns, at most 1 MB of X; one
+  // GPU, not row-sharded).  The streaming plan below is still built: resnmtf_fit_profile and the AUTO hand-over use it.
+  bool small = (impl == RESNMTF_IMPL_AUTO || impl == RESNMTF_IMPL_SMALL) && !rn_placed(fit) && fit->ctx->comm == nullptr &&
+               rn_env_int("RESNMTF_SMALL", 1) != 0;
+  int64_t small_elems = 0;
+  for (int v = 0; v < fit->V && small; ++v) {
+    const RnView& d = fit->views[v].d;
+    small = d.k <= 8 && d.ldx <= RN_SM_MAXDIM && d.pp <= RN_SM_MAXDIM && d.ldx * d.pp <= RN_SM_MAXELEMS;
+    small_elems += d.ldx * d.pp;
+  }
+  // AUTO takes it only where it wins: measured 25.6 us per sweep against 34.8 us for two launches per view on the
+  // README toy (12288 padded entries), but 59.7 against 35.5 us on 2 x 180 x 180 (73728): one SM against a cluster
+  if (impl == RESNMTF_IMPL_AUTO && small_elems > RN_SM_AUTO_ELEMS) small = false;
+  fit->small = small;
+  fit->small_dim = 64;
+  for (int v = 0; v < fit->V; ++v)
+    fit->small_dim = (int)std::max<int64_t>(fit->small_dim, std::max(fit->views[v].d.ldx, fit->views[v].d.pp));
+  if (small)
+    RN_CUDA(cudaFuncSetAttribute(rn_small_sweeps, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)rn_small_smem(RN_SM_MAXDIM)));
   if (impl < RESNMTF_IMPL_DFMA || impl > RESNMTF_IMPL_FUSED) impl = RESNMTF_IMPL_FUSED;
   const int impl_fit = impl;
   bool any_fused = false;
@@ -1223,7 +1245,7 @@ static int build_plan(resnmtf_fit* fit) {
       vh.l2_window = (size_t)(w / 32768.0) * 32768;  // whole 32 KB units
     }
   }
-  fit->impl = (impl_fit == RESNMTF_IMPL_FUSED && !any_fused) ? RESNMTF_IMPL_TMA : impl_fit;
+  fit->impl = fit->small ? RESNMTF_IMPL_SMALL : (impl_fit == RESNMTF_IMPL_FUSED && !any_fused) ? RESNMTF_IMPL_TMA : impl_fit;
   fit->plan_dirty = false;
   fit->meta_dirty = true;
   if (fit->graph_exec) {
@@ -1385,7 +1407,7 @@ static int64_t enqueue_iteration(resnmtf_fit* fit, cudaStream_t st, std::vector<
     const int fuse = (!direct && v == fit->V - 1) ? 1 : 0;
     if (vh.d.fu_csize) {  // one pass over X: F step and G step in one launch
       mark(2);
-      launch_fused(vh, fit->d, v, fuse, st);
+      launch_fused(vh, fit->d, v, fuse, st, fit->pdl_ok);
       launches += 1;
     } else {
       mark(0);
@@ -1431,10 +1453,20 @@ static int prepare(resnmtf_fit* fit) {
   // A fit whose every view runs the one-pass kernel launches straight into the stream: consecutive launches then
   // chain through programmatic dependent launch (launch_fused), which a chain of single-iteration graph launches
   // cannot do; one kernel per view and iteration leaves nothing for a graph to save.
-  bool chained = rn_env_int("RESNMTF_NO_PDL", 0) == 0 && fit->d.err_mode != RESNMTF_ERR_DIRECT;
+  // Programmatic dependent launch places the next kernel's clusters on SMs one by one as the CTAs of the running
+  // kernel exit.  Clusters of 1, 2, 4, 6 or 8 CTAs are whole TPCs (SM pairs) and always find their full count again;
+  // clusters of an ODD size do not: measured on the C3 structure (50000 x 5000, 5-CTA clusters) only about half of
+  // the 26 clusters were resident when the grid started, the rest ran as a second wave after the first had finished
+  // (2200 us per update-iteration against 1644 us without the attribute).  Such fits launch without it.
+  fit->pdl_ok = true;
+  for (int v = 0; v < fit->V; ++v) {
+    const int cs = fit->views[v].d.fu_csize;
+    if (cs > 1 && (cs & 1)) fit->pdl_ok = false;
+  }
+  bool chained = rn_env_int("RESNMTF_NO_PDL", 0) == 0 && fit->pdl_ok && fit->d.err_mode != RESNMTF_ERR_DIRECT;
   for (int v = 0; v < fit->V; ++v) chained = chained && fit->views[v].d.fu_csize > 0;
   // a placed fit enqueues on one stream per GPU with events in between: plain launches, no graph
-  if (!fit->graph_exec && !chained && !rn_placed(fit) && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
+  if (!fit->graph_exec && !chained && !rn_placed(fit) && !fit->small && rn_env_int("RESNMTF_NO_GRAPH", 0) == 0) {
     cudaStream_t st = fit->ctx->stream;
     RN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     fit->launches_per_iter = enqueue_iteration(fit, st, nullptr, nullptr);
@@ -1484,6 +1516,13 @@ static int pull_ctrl(resnmtf_fit* fit) {
 
 static int run_batch(resnmtf_fit* fit, int64_t iters) {
   cudaStream_t st = fit->ctx->stream;
+  if (fit->small) {  // the whole batch of sweeps is ONE launch of one persistent CTA
+    rn_small_sweeps<<<1, RN_SM_THREADS, rn_small_smem(fit->small_dim), st>>>(fit->d, iters, fit->small_dim);
+    RN_CUDA(cudaGetLastError());
+    fit->launches_per_iter = 0;
+    fit->counters.kernel_launches += 1;
+    return RESNMTF_OK;
+  }
   for (int64_t i = 0; i < iters; ++i) {
     if (fit->graph_exec) {
       RN_CUDA(cudaGraphLaunch(fit->graph_exec, st));

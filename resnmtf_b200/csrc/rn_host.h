@@ -223,6 +223,9 @@ struct resnmtf_fit {
   bool meta_dirty = true;   // device copies of views / maps / restrictions need a refresh
   bool plan_dirty = true;   // grids / workspaces / graph need a rebuild
   bool auto_direct = false; // AUTO error mode has handed over to the direct residual pass
+  bool pdl_ok = true;       // the fused launches of this fit may carry the programmatic-dependent-launch attribute
+  int small_dim = 64;       // largest padded row / column count of the views (shared-memory copies of F and G)
+  bool small = false;       // every view fits one SM's caches: the whole loop runs as one persistent CTA (rn_small.cuh)
   int comm_rc = 0;          // first NCCL failure seen while enqueueing (row-sharded path)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;

@@ -33,7 +33,7 @@
 template <int K>
 __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& ft, const int v, const int64_t r,
                                                 const double* P, const double* Ssm, const double* Wsm,
-                                                const double* lamh) {
+                                                const double* lamh, double* fnew = nullptr) {
   const int kp = vw.kp;
   const int V = ft.n_views;
   double f[K], N[K], FS[K], D[K];
@@ -67,7 +67,9 @@ __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& f
     for (int c = 0; c < K; ++c) {
       double ratio = N[c] / (D[c] + lamh[c]);
       if (isnan(ratio)) ratio = 1.0;
-      vw.F[rn_fidx(r, c, kp)] = fabs(f[c] * ratio);
+      const double o = fabs(f[c] * ratio);
+      vw.F[rn_fidx(r, c, kp)] = o;
+      if (fnew) fnew[c] = o;
     }
   } else {
     double pc[K];
@@ -95,7 +97,9 @@ __device__ __forceinline__ void rn_update_f_row(const RnView& vw, const RnFit& f
     for (int c = 0; c < K; ++c) {
       const double num = N[c] + pc[c] / nv;
       const double den = (D[c] + phisum * f[c]) + lamh[c];
-      vw.F[rn_fidx(r, c, kp)] = fabs(f[c] * (num / den));
+      const double o = fabs(f[c] * (num / den));
+      vw.F[rn_fidx(r, c, kp)] = o;
+      if (fnew) fnew[c] = o;
     }
   }
 }

@@ -11,7 +11,7 @@ from resnmtf_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA, L.IMPL_FUSED])
+@pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA, L.IMPL_FUSED, L.IMPL_SMALL])
 @pytest.mark.parametrize("name", CASES)
 def test_fixed_sweeps_match_golden(ctx, name, impl, monkeypatch):
     if impl == L.IMPL_FUSED:  # the golden views are narrow: lift the fused kernel's padding rule
@@ -34,19 +34,29 @@ def test_fixed_sweeps_match_golden(ctx, name, impl, monkeypatch):
         fit.close()
 
 
-@pytest.mark.parametrize("family", ["default kernels", "two-pass kernels", "first one-pass kernel"])
+@pytest.mark.parametrize("family", ["default kernels", "two-pass kernels", "first one-pass kernel",
+                                    "second one-pass kernel"])
 @pytest.mark.parametrize("name", CASES)
 def test_converged_run_matches_golden(ctx, name, family, monkeypatch):
-    """Default for these narrow views: rn_fused2_step; then the two-pass TMA kernels and rn_fused_step forced."""
+    """Default for these tiny fits: the persistent single-CTA loop (rn_small_sweeps) up to 16384 padded entries, else
+    rn_fused2_step; then the two-pass TMA kernels, rn_fused_step and rn_fused2_step forced."""
+    want = L.IMPL_FUSED if name == "three_views" else L.IMPL_SMALL
     if family == "two-pass kernels":
         monkeypatch.setenv("RESNMTF_IMPL", str(L.IMPL_TMA))
+        want = L.IMPL_TMA
     elif family == "first one-pass kernel":
+        monkeypatch.setenv("RESNMTF_SMALL", "0")
         monkeypatch.setenv("RESNMTF_FUSED_MAX_PAD", "100000000")
         monkeypatch.setenv("RESNMTF_FUSED_KIND", "1")
+        want = L.IMPL_FUSED
+    elif family == "second one-pass kernel":
+        monkeypatch.setenv("RESNMTF_SMALL", "0")
+        want = L.IMPL_FUSED
     prob, z, V = load(name)
     fit = prob.device_fit(ctx)
     try:
         done = fit.run(None, 1.0e-6)
+        assert fit.counters()["impl"] == want
         assert done == len(z["all_error"])
         assert rel_err(fit.errors(), z["all_error"]) <= RTOL
         fit.normalise()
