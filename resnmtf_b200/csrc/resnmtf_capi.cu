@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
 #include "rn_host.h"
 #include "rn_kernels.cuh"
 #include "rn_fused.cuh"
@@ -384,6 +386,13 @@ void rn_ctx_release(resnmtf_ctx* ctx) {
     if (ctx->tiled[b]) cudaEventDestroy(ctx->tiled[b]);
   }
   if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+  for (int t = 0; t < RN_UP_T; ++t) {
+    for (int b = 0; b < 2; ++b) {
+      if (ctx->up_pin[t][b]) cudaFreeHost(ctx->up_pin[t][b]);
+      if (ctx->up_ev[t][b]) cudaEventDestroy(ctx->up_ev[t][b]);
+    }
+    if (ctx->up_st[t]) cudaStreamDestroy(ctx->up_st[t]);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -641,6 +650,59 @@ extern "C" int resnmtf_fit_destroy(resnmtf_fit* fit) {
 // leaves ||X||_F^2 (all-reduced when the context is row-sharded) in g.scal[0].  `g` needs n, p, pp, ldx,
 // row_tiles, X, scal.  Host sources go through two <= 128 MB device staging buffers so that the H2D copy of
 // chunk c+1 overlaps the re-tiling of chunk c.
+// Pinned pieces, events and streams of the threaded upload of pageable host memory (created on first use).
+static cudaError_t rn_upload_setup(resnmtf_ctx* ctx) {
+  if (ctx->up_ready) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  for (int t = 0; t < RN_UP_T && e == cudaSuccess; ++t) {
+    if (!ctx->up_st[t]) e = cudaStreamCreateWithFlags(&ctx->up_st[t], cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+      if (!ctx->up_pin[t][b]) e = cudaHostAlloc((void**)&ctx->up_pin[t][b], RN_UP_BYTES, cudaHostAllocDefault);
+      if (e == cudaSuccess && !ctx->up_ev[t][b]) e = cudaEventCreateWithFlags(&ctx->up_ev[t][b], cudaEventDisableTiming);
+    }
+  }
+  ctx->up_ready = e == cudaSuccess;
+  return e;
+}
+
+// nc columns of n doubles from PAGEABLE host memory (leading dimension ld) into the compact device buffer dst: column
+// groups of <= RN_UP_BYTES are dealt round-robin to RN_UP_T host threads; each copies its group into one of its two
+// pinned pieces and sends it on its own stream while it fills the other.  Returns when everything has landed.
+static cudaError_t rn_upload_pageable(resnmtf_ctx* ctx, double* dst, const double* x, int64_t ld, int64_t n, int64_t nc) {
+  const int64_t gcols = std::max<int64_t>(1, (int64_t)(RN_UP_BYTES / ((size_t)n * sizeof(double))));
+  const int64_t groups = (nc + gcols - 1) / gcols;
+  cudaError_t errs[RN_UP_T];
+  std::vector<std::thread> threads;
+  const int nt = (int)std::min<int64_t>(RN_UP_T, groups);
+  for (int t = 0; t < nt; ++t) {
+    errs[t] = cudaSuccess;
+    threads.emplace_back([=, &errs]() {
+      cudaError_t e = cudaSetDevice(ctx->device);
+      int used = 0;
+      for (int64_t gi = t; gi < groups && e == cudaSuccess; gi += nt, ++used) {
+        const int b = used & 1;
+        if (used >= 2) e = cudaEventSynchronize(ctx->up_ev[t][b]);  // the piece's previous copy has left it
+        if (e != cudaSuccess) break;
+        const int64_t c0 = gi * gcols, cn = std::min(gcols, nc - c0);
+        double* pin = ctx->up_pin[t][b];
+        if (ld == n) {
+          std::memcpy(pin, x + c0 * ld, (size_t)cn * n * sizeof(double));
+        } else {
+          for (int64_t c = 0; c < cn; ++c) std::memcpy(pin + c * n, x + (c0 + c) * ld, (size_t)n * sizeof(double));
+        }
+        e = cudaMemcpyAsync(dst + c0 * n, pin, (size_t)cn * n * sizeof(double), cudaMemcpyHostToDevice, ctx->up_st[t]);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->up_ev[t][b], ctx->up_st[t]);
+      }
+      cudaError_t e2 = cudaStreamSynchronize(ctx->up_st[t]);
+      errs[t] = e != cudaSuccess ? e : e2;
+    });
+  }
+  for (auto& th : threads) th.join();
+  for (int t = 0; t < nt; ++t)
+    if (errs[t] != cudaSuccess) return errs[t];
+  return cudaSuccess;
+}
+
 static int upload_panels(resnmtf_ctx* ctx, const RnView& g, const double* x, int64_t ld, bool on_device,
                          double* xpart, int32_t* xticket, const char* who) {
   cudaStream_t st = ctx->stream;
@@ -671,6 +733,17 @@ static int upload_panels(resnmtf_ctx* ctx, const RnView& g, const double* x, int
       for (int b = 0; b < nbuf && e == cudaSuccess; ++b) e = cudaMalloc(&ctx->stage[b], need);
       if (e == cudaSuccess) ctx->stage_bytes = need;
     }
+    // pageable source (what R hands over) and columns that fit a pinned piece: the threaded path
+    bool pageable = false;
+    if (e == cudaSuccess && rn_env_int("RESNMTF_UPLOAD_THREADS", 1) != 0 && (size_t)n * sizeof(double) <= RN_UP_BYTES) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, x) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+      else cudaGetLastError();
+      if (pageable && rn_upload_setup(ctx) != cudaSuccess) {
+        cudaGetLastError();
+        pageable = false;
+      }
+    }
     double** stage = ctx->stage;
     cudaStream_t copy_st = ctx->copy_st;
     cudaEvent_t* copied = ctx->copied;
@@ -679,12 +752,19 @@ static int upload_panels(resnmtf_ctx* ctx, const RnView& g, const double* x, int
     for (int64_t c0 = 0; c0 < p && e == cudaSuccess; c0 += chunk, ++ci) {
       const int b = (int)(ci % nbuf);
       const int64_t nc = std::min(chunk, p - c0);
-      if (ci >= nbuf) e = cudaStreamWaitEvent(copy_st, tiled[b], 0);  // the buffer's previous chunk is re-tiled
-      if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(stage[b], (size_t)n * sizeof(double), x + c0 * ld, (size_t)ld * sizeof(double),
-                              (size_t)n * sizeof(double), (size_t)nc, cudaMemcpyHostToDevice, copy_st);
-      if (e == cudaSuccess) e = cudaEventRecord(copied[b], copy_st);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
+      if (pageable) {
+        // the buffer's previous chunk is re-tiled; then RN_UP_T threads bring this chunk over (they return when their
+        // last copy has landed, so the re-tiling kernel below needs no event)
+        if (ci >= nbuf) e = cudaEventSynchronize(tiled[b]);
+        if (e == cudaSuccess) e = rn_upload_pageable(ctx, stage[b], x + c0 * ld, ld, n, nc);
+      } else {
+        if (ci >= nbuf) e = cudaStreamWaitEvent(copy_st, tiled[b], 0);  // the buffer's previous chunk is re-tiled
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync(stage[b], (size_t)n * sizeof(double), x + c0 * ld, (size_t)ld * sizeof(double),
+                                (size_t)n * sizeof(double), (size_t)nc, cudaMemcpyHostToDevice, copy_st);
+        if (e == cudaSuccess) e = cudaEventRecord(copied[b], copy_st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
+      }
       if (e == cudaSuccess) {
         const int blocks = (int)std::min<int64_t>(((int64_t)g.row_tiles * nc * 32 + 255) / 256, 1 << 20);
         rn_to_panels<<<blocks, 256, 0, st>>>(g, stage[b], n, c0, nc);

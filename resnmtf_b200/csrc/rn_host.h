@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -100,6 +101,8 @@ inline int rn_fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
+#define RN_UP_T 6
+#define RN_UP_BYTES ((size_t)4 << 20)
 struct resnmtf_ctx {
   int device = 0;
   int sm_count = 148;
@@ -124,6 +127,13 @@ struct resnmtf_ctx {
   size_t stage_bytes = 0;
   cudaStream_t copy_st = nullptr;
   cudaEvent_t copied[2] = {nullptr, nullptr}, tiled[2] = {nullptr, nullptr};
+  // PAGEABLE host sources (what R hands over): RN_UP_T host threads copy column groups into their own pinned buffers
+  // (two of RN_UP_BYTES each) and send them on their own streams -- the driver's single-threaded staging of a pageable
+  // cudaMemcpy runs at ~10 GB/s, six threads saturate the link
+  double* up_pin[RN_UP_T][2] = {};
+  cudaEvent_t up_ev[RN_UP_T][2] = {};
+  cudaStream_t up_st[RN_UP_T] = {};
+  bool up_ready = false;
 };
 
 inline cudaError_t rn_dev_alloc(resnmtf_ctx* ctx, void** p, size_t bytes) {
@@ -151,6 +161,8 @@ struct resnmtf_data {
   // k-sweep slices the same triplets for every k.  Host copies, column-major.
   std::vector<double> svd_u, svd_d, svd_v;
   int svd_kc = 0;
+  std::mutex svd_mu;  // the cache is filled by the first fit that asks and copied by resnmtf_data_copy, possibly from
+                      // different worker threads of a pool
 };
 
 void rn_ctx_release(resnmtf_ctx* ctx);  // resnmtf_capi.cu

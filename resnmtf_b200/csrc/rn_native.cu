@@ -238,9 +238,11 @@ extern "C" int resnmtf_data_copy(resnmtf_data* src, resnmtf_ctx* dst_ctx, resnmt
   resnmtf_data* d = nullptr;
   int rc = rn_data_alloc(dst_ctx, src->n, src->p, &d);
   if (rc) return rc;
-  cudaError_t e = cudaSetDevice(src->ctx->device);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(src->ctx->stream);
-  if (e == cudaSuccess) e = cudaSetDevice(dst_ctx->device);
+  // The source is a sealed handle: whatever wrote its X was synchronised when the handle was handed out (rn_data_seal),
+  // and X is never written afterwards.  The source context's stream must NOT be touched from here: in a pool another
+  // worker thread owns it and may have it in CUDA-graph capture (found on 8 GPUs: "operation not permitted when stream
+  // is capturing").
+  cudaError_t e = cudaSetDevice(dst_ctx->device);
   if (e == cudaSuccess)
     e = cudaMemcpyPeerAsync(d->X, dst_ctx->device, src->X, src->ctx->device, (size_t)src->ldx * src->pp * sizeof(double),
                             dst_ctx->stream);
@@ -250,6 +252,7 @@ extern "C" int resnmtf_data_copy(resnmtf_data* src, resnmtf_ctx* dst_ctx, resnmt
     return rn_fail(RESNMTF_E_CUDA, std::string("resnmtf_data_copy: ") + cudaGetErrorString(e));
   }
   d->xnorm2 = src->xnorm2;
+  std::lock_guard<std::mutex> lk(src->svd_mu);
   d->svd_u = src->svd_u;
   d->svd_d = src->svd_d;
   d->svd_v = src->svd_v;
@@ -673,6 +676,7 @@ int compute_svd(resnmtf_data* data) {
 
 // |U[, 1:k]|, d[1:k], |V[, 1:k]| of the view: what init_mats_inner() (R/update_steps.r:92-95) takes from svd(x)
 int rn_data_svd(resnmtf_data* data) {
+  std::lock_guard<std::mutex> lk(data->svd_mu);
   if (data->svd_kc > 0) return RESNMTF_OK;
   RN_CUDA(cudaSetDevice(data->ctx->device));
   return compute_svd(data);

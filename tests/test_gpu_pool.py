@@ -146,3 +146,26 @@ def test_a_failing_unit_reports_its_own_status(ctx):
         pool.put_host(0, [x])
         with pytest.raises(L.ResnmtfError, match="unit 1"):
             pool.run([dict(key=0, k=[3], n_iters=2), dict(key=0, k=[40], n_iters=2)])  # k > 16
+
+
+def test_two_workers_with_graph_capturing_units_and_a_view_copy(ctx):
+    """Two worker threads (a pool of two contexts, here on ONE GPU): units with k > 8 run the CUDA-core kernels, whose
+    sweep is captured into a CUDA graph by the worker, while the other worker copies the view from the first context
+    (resnmtf_data_copy) and runs its own units.  Regression: the copy used to synchronise the source context's stream,
+    which fails while the other thread has it in capture (found on 8 GPUs).  Results equal the one-worker pool's."""
+    rng = np.random.default_rng(9)
+    x = synth.prep(synth.planted_view(700, 300, 3, rng, 0.3, 0.3)[0])
+    ks = [9, 3, 10, 4, 11, 5, 9, 6]
+    units = lambda: [dict(key=3, k=[k], noise=[np.abs(np.sqrt(0.05) * np.random.default_rng(k).standard_normal((k, k)))],  # noqa: E731
+                          n_iters=None, max_iters=400) for k in ks]
+    with NativePool(devices=[ctx.device, ctx.device]) as pool:
+        assert len(pool) == 2
+        pool.put_host(3, [x])
+        two = pool.run(units())
+    with NativePool(devices=[ctx.device]) as pool:
+        pool.put_host(3, [x])
+        one = pool.run(units())
+    assert {u["gpu"] for u in two} == {0, 1}
+    for a, b in zip(two, one):
+        assert a["iters"] == b["iters"] and np.array_equal(a["total_err"], b["total_err"])
+        assert np.array_equal(a["output_f"][0], b["output_f"][0]) and np.array_equal(a["output_g"][0], b["output_g"][0])
