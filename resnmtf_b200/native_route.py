@@ -10,6 +10,9 @@ Every unit draws from its own child generator (per k, per shuffled repeat, per r
 so the result of a call does not depend on the number of GPUs or on which GPU ran which unit."""
 from __future__ import annotations
 
+import os
+import sys
+import time
 import warnings
 from concurrent.futures import ThreadPoolExecutor
 
@@ -19,6 +22,23 @@ from . import _lib as L
 from . import prep
 from .native import NativePool
 from .prep import NamedMatrix
+
+TRACE = os.environ.get("RESNMTF_TRACE", "0") not in ("", "0")
+
+
+def _trace(label, t0, units=None):
+    """RESNMTF_TRACE=1: wall time of a phase of the call and, for a batch of units, the busy seconds of every GPU."""
+    if not TRACE:
+        return
+    msg = f"  [resnmtf trace] {label:44s} {time.perf_counter() - t0:7.3f} s"
+    if units:
+        per = {}
+        for u in units:
+            per.setdefault(u["gpu"], []).append(u["seconds"])
+        msg += f"  {len(units)} units, longest {max(u['seconds'] for u in units):.3f} s, busy " + " ".join(
+            f"g{g}={sum(v):.2f}({len(v)})" for g, v in sorted(per.items()))
+    print(msg, file=sys.stderr, flush=True)
+
 
 KEY_DATA = 0
 SIGMA = 0.05  # variance of the noise term of init_mats_inner (R/update_steps.r:96-99)
@@ -66,14 +86,63 @@ def _maps(data, row_indices, col_indices):
     return out
 
 
+import threading  # noqa: E402
+
+_POOLS = {}  # device tuple -> NativePool kept for the life of the process (release_pools() lets go of them)
+_POOLS_LOCK = threading.Lock()
+
+
+def _shared_pool(n_gpus, devices):
+    """One native pool per set of GPUs for the whole process: creating a pool (contexts, streams, private memory pools)
+    and above all destroying it -- every block of the memory pools goes back to the driver, 0.6 s per call on one GPU,
+    measured -- were serial time inside every apply_resnmtf call; kept, the pool also keeps its device memory and the
+    loaded kernels warm for the next call.  RESNMTF_KEEP_POOLS=0 goes back to one pool per call."""
+    key = ("n", int(n_gpus)) if devices is None else ("d",) + tuple(int(d) for d in devices)
+    with _POOLS_LOCK:
+        pool = _POOLS.get(key)
+        if pool is None or not pool._h.value:
+            pool = NativePool(n_gpus=n_gpus, devices=devices)
+            pool.call_lock = threading.Lock()  # one apply_resnmtf call at a time on a shared pool
+            _POOLS[key] = pool
+    return pool
+
+
+def release_pools():
+    """Destroys the cached pools (their contexts, streams and device memory)."""
+    for pool in list(_POOLS.values()):
+        pool.close()
+    _POOLS.clear()
+
+
+import atexit  # noqa: E402
+
+atexit.register(release_pools)
+
+
 class NativeRunner:
     """The pool of one call and the unit bookkeeping of its fits."""
 
     def __init__(self, n_gpus=0, devices=None):
-        self.pool = NativePool(n_gpus=n_gpus, devices=devices)
+        self.keep = os.environ.get("RESNMTF_KEEP_POOLS", "1") not in ("", "0")
+        self.pool = _shared_pool(n_gpus, devices) if self.keep else NativePool(n_gpus=n_gpus, devices=devices)
+        self._held = False
+        if self.keep:
+            self.pool.call_lock.acquire()
+            self._held = True
 
     def close(self):
-        self.pool.close()
+        t0 = time.perf_counter()
+        if self.keep:
+            try:
+                if KEY_DATA in self.pool.shapes:
+                    self.pool.drop(KEY_DATA)  # the views of this call; the pool itself stays
+            finally:
+                if self._held:
+                    self._held = False
+                    self.pool.call_lock.release()
+        else:
+            self.pool.close()
+        _trace("pool released" if not self.keep else "data set dropped (pool kept)", t0)
 
     def __enter__(self):
         return self
@@ -84,7 +153,9 @@ class NativeRunner:
     def put(self, views, prep_values):
         """Uploads the views (NamedMatrix list) under KEY_DATA; with ``prep_values`` through make_non_neg_inner and
         matrix_normalisation on the device (same warning as the host version, R/utils.r:20-27)."""
+        t0 = time.perf_counter()
         neg = self.pool.put_host(KEY_DATA, [m.x for m in views], prep=prep_values)
+        _trace("upload + prep on the first GPU", t0)
         if neg:
             warnings.warn("Matrix is not non-negative. Has been made non-negative.")
 
@@ -127,7 +198,10 @@ class NativeRunner:
                     units.append(dict(base, k=[k_vec[0]] * V, shuffle_seed=seed, renormalise=True,
                                       noise=_noise(srng, [k_vec[0]] * V), n_iters=None, max_iters=max_iters))
             shuffle_at.append(mine)
+        t0 = time.perf_counter()
         done = self.pool.run(units)
+        _trace(f"batch of units ({len(specs)} fits{' + shuffled refits' if need_shuffles else ''})", t0, done)
+        t0 = time.perf_counter()
 
         def post(si):
             sp = specs[si]
@@ -145,9 +219,12 @@ class NativeRunner:
                              resident=resident, want_bisil=sp.get("want_bisil", True))
 
         if len(specs) == 1:
-            return [post(0)]
-        with ThreadPoolExecutor(max_workers=max(1, min(len(specs), 2 * len(self.pool)))) as ex:
-            return list(ex.map(post, range(len(specs))))
+            out = [post(0)]
+        else:
+            with ThreadPoolExecutor(max_workers=max(1, min(len(specs), 2 * len(self.pool)))) as ex:
+                out = list(ex.map(post, range(len(specs))))
+        _trace("post-processing (JSD thresholds, binarise, bisilhouette)", t0)
+        return out
 
     # ---- stability analysis (R/stability_analysis.r:302-338) -----------------------------------------------------------
     def stability_check(self, data, results, k, phi, xi, psi, n_iters, spurious, num_repeats, no_clusts, distance,
@@ -171,8 +248,10 @@ class NativeRunner:
             finally:
                 sub.close()
 
+        t0 = time.perf_counter()
         samples = [draw_subsample(sums, shapes, dim_1, n_views, sample_rate, child_rngs[i])
                    for i in range(int(n_stability))]
+        _trace("stability: sub-sample draws + sums on the device", t0)
         if any(smp is None for smp in samples):
             return results
         specs = []
