@@ -246,6 +246,12 @@ int resnmtf_jsd_pairs(resnmtf_ctx* ctx, const double* vecs, int64_t n, int32_t m
  * restated from its published definition, parity unpinned. */
 int resnmtf_data_bisil(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method, double* vals,
                        double* bisil);
+/* The same for the biclusters j with want[j] != 0 only (vals[j]; 0 for the others): the per-bicluster values do not
+ * depend on each other, so the biclusters of one fit can be scored on different GPUs that each hold a copy of the view
+ * and combined by the caller -- *n_live (may be NULL) receives the number of non-empty biclusters of the whole
+ * clustering, the denominator of the mean. */
+int resnmtf_data_bisil_part(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method,
+                            const int32_t* want, double* vals, int32_t* n_live);
 
 /* ---- fan-out: independent fits over the GPUs of a pool ----------------------------------- */
 

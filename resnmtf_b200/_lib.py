@@ -29,7 +29,7 @@ EXPORTS = (
     "resnmtf_jsd_pairs",
     "resnmtf_data_create_prepped", "resnmtf_data_shape", "resnmtf_data_download", "resnmtf_data_sums",
     "resnmtf_data_shuffle", "resnmtf_data_subsample", "resnmtf_data_copy", "resnmtf_data_svd_topk",
-    "resnmtf_data_bisil",
+    "resnmtf_data_bisil", "resnmtf_data_bisil_part",
     "resnmtf_pool_create", "resnmtf_pool_destroy", "resnmtf_pool_size", "resnmtf_pool_ctx", "resnmtf_pool_put",
     "resnmtf_pool_put_host", "resnmtf_pool_get", "resnmtf_pool_drop", "resnmtf_batch_run", "resnmtf_unit_size",
     "resnmtf_fit_set_factors", "resnmtf_fit_set_restrictions", "resnmtf_fit_set_shared_map",
@@ -147,6 +147,7 @@ def load():
         "resnmtf_data_copy": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "resnmtf_data_svd_topk": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "resnmtf_data_bisil": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, pd]),
+        "resnmtf_data_bisil_part": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, pi32]),
         "resnmtf_pool_create": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "resnmtf_pool_destroy": (C.c_int, [vp]),
         "resnmtf_pool_size": (C.c_int, [vp]),

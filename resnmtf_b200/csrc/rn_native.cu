@@ -702,8 +702,28 @@ extern "C" int resnmtf_data_svd_topk(resnmtf_data* data, int k, double* u, doubl
 // non-empty bicluster (R_j, C_j) the silhouette of the rows of R_j computed on the columns C_j only, against the other
 // row clusters R_l \ R_j (or, when there is none, against the rows outside R_j); vals[j] = mean row silhouette (0 for
 // empty biclusters), *bisil = mean over the non-empty ones.  row_cl n x k, col_cl p x k: column-major, non-zero = member.
+static int bisil_impl(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method,
+                      const int32_t* want, double* vals, double* bisil, int32_t* n_live);
+
 extern "C" int resnmtf_data_bisil(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method,
                                   double* vals, double* bisil) {
+  RN_CHECK(bisil != nullptr, RESNMTF_E_INVALID, "resnmtf_data_bisil: NULL argument");
+  return bisil_impl(data, row_cl, col_cl, k, method, nullptr, vals, bisil, nullptr);
+}
+
+// The same for a SUBSET of the biclusters (want[j] != 0): the per-bicluster values are independent of each other, so the
+// biclusters of one fit can be scored on different GPUs (each holding a copy of the view) and combined by the caller --
+// vals[j] of the wanted ones, 0 elsewhere; *n_live = number of non-empty biclusters of the whole clustering, the
+// denominator of the mean.
+extern "C" int resnmtf_data_bisil_part(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method,
+                                       const int32_t* want, double* vals, int32_t* n_live) {
+  RN_CHECK(want && vals, RESNMTF_E_INVALID, "resnmtf_data_bisil_part: NULL argument");
+  double ignored = 0.0;
+  return bisil_impl(data, row_cl, col_cl, k, method, want, vals, &ignored, n_live);
+}
+
+static int bisil_impl(resnmtf_data* data, const double* row_cl, const double* col_cl, int k, int method,
+                      const int32_t* want, double* vals, double* bisil, int32_t* n_live) {
   RN_CHECK(data && row_cl && col_cl && bisil, RESNMTF_E_INVALID, "resnmtf_data_bisil: NULL argument");
   RN_CHECK(k >= 1 && k <= 64, RESNMTF_E_INVALID, "resnmtf_data_bisil: k out of range");
   RN_CHECK(method >= 0 && method <= 2, RESNMTF_E_INVALID,
@@ -724,7 +744,9 @@ extern "C" int resnmtf_data_bisil(resnmtf_data* data, const double* row_cl, cons
   if (vals)
     for (int j = 0; j < k; ++j) vals[j] = 0.0;
   double total = 0.0;
+  if (n_live) *n_live = (int32_t)live.size();
   for (int j : live) {
+    if (want && !want[j]) continue;
     // segments: R_j, then R_l \ R_j for every other live l (non-empty ones), else the complement of R_j
     std::vector<std::vector<int32_t>> seg;
     seg.push_back(R[j]);

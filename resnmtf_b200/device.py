@@ -111,8 +111,15 @@ def jsd_pairs(ctx, vecs, bw, vmax, pair_a, pair_b):
     if pa.shape != pb.shape or bw.size != vecs.shape[1] or vmax.size != vecs.shape[1]:
         raise ValueError("jsd_pairs: inconsistent arguments")
     out = np.empty(pa.size, dtype=np.float64)
-    L.check(lib.resnmtf_jsd_pairs(ctx._h, _ptr(vecs), vecs.shape[0], vecs.shape[1], vecs.shape[0], _ptr(bw),
-                                  _ptr(vmax), _ptr(pa), _ptr(pb), pa.size, _ptr(out)))
+    lock = getattr(ctx, "lock", None)  # a context shared by several host threads (native_route) carries one
+    if lock is not None:
+        lock.acquire()
+    try:
+        L.check(lib.resnmtf_jsd_pairs(ctx._h, _ptr(vecs), vecs.shape[0], vecs.shape[1], vecs.shape[0], _ptr(bw),
+                                      _ptr(vmax), _ptr(pa), _ptr(pb), pa.size, _ptr(out)))
+    finally:
+        if lock is not None:
+            lock.release()
     return out
 
 
@@ -223,6 +230,17 @@ class DeviceData:
                                              C.byref(out)))
         live = [j for j in range(k) if rc[:, j].any() and cc[:, j].any()]
         return {"bisil": float(out.value), "vals": [float(vals[j]) for j in live]}
+
+    def bisil_part(self, rc, cc, want, method="euclidean"):
+        """Per-bicluster bisilhouette values of the biclusters flagged in ``want`` only (resnmtf_data_bisil_part); ``rc``
+        / ``cc`` are the 0/1 float64 column-major cluster matrices.  Returns (vals[k], number of non-empty biclusters)."""
+        k = rc.shape[1]
+        vals = np.zeros(k, dtype=np.float64)
+        flags = np.ascontiguousarray(want, dtype=np.int32)
+        n_live = C.c_int32(0)
+        L.check(self._lib.resnmtf_data_bisil_part(self._h, _ptr(rc), _ptr(cc), k, L.DISTANCES[method], _ptr(flags),
+                                                  _ptr(vals), C.byref(n_live)))
+        return vals, int(n_live.value)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -133,3 +133,49 @@ def test_resident_matrix_has_shape_and_names_but_no_host_values():
     assert m.shape == (5, 3) and m.x is None and m.rownames[4] == "e"
     cp = as_named(m)
     assert isinstance(cp, ResidentMatrix) and cp.shape == (5, 3) and cp.colnames == ["x", "y", "z"]
+
+
+def test_split_bisilhouette_combines_pieces_in_bicluster_order():
+    """native_route._SplitBisil deals the biclusters of one fit over the GPUs of the pool and sums the per-bicluster
+    values in bicluster order: with a host stand-in for the per-GPU entry point the result equals the whole score."""
+    import threading
+
+    import numpy as np
+
+    from resnmtf_b200 import bicluster as B
+    from resnmtf_b200.native_route import _SplitBisil
+
+    rng = np.random.default_rng(3)
+    n, p, k = 120, 40, 5
+    x = np.abs(rng.standard_normal((n, p)))
+    rc = (rng.random((n, k)) < 0.3).astype(float)
+    cc = (rng.random((p, k)) < 0.4).astype(float)
+    rc[:, 1] = 0.0
+    calls = []
+
+    class Handle:
+        def __init__(self, g):
+            self.g = g
+
+        def bisil_part(self, rcm, ccm, want, method):
+            live = [j for j in range(k) if rcm[:, j].any() and ccm[:, j].any()]
+            full = B.bisilhouette(x, rcm, ccm, method=method)["vals"]
+            vals = np.zeros(k)
+            for j, v in zip(live, full):
+                if want[j]:
+                    vals[j] = v
+            calls.append((self.g, [j for j in range(k) if want[j]]))
+            return vals, len(live)
+
+    class Runner:
+        pool = [0, 1, 2]
+        gpu_locks = [threading.Lock() for _ in range(3)]
+
+        def handle(self, view, g):
+            return Handle(g)
+
+    whole = B.bisilhouette(x, rc, cc)
+    got = _SplitBisil(Runner(), 0, first_gpu=1).bisil(rc, cc)
+    assert got["vals"] == whole["vals"] and abs(got["bisil"] - whole["bisil"]) <= 1e-15
+    assert sorted(j for _, js in calls for j in js) == [0, 2, 3, 4]  # every live bicluster exactly once
+    assert len({g for g, _ in calls}) == 3                            # over all three "GPUs"

@@ -196,3 +196,32 @@ def test_bisilhouette_single_cluster_scores_against_the_rows_outside(ctx):
     assert d.bisil(rc, cc)["bisil"] == 0.0 == B.bisilhouette(x, rc, cc)["bisil"]
     assert d.bisil(np.zeros((300, 3)), cc)["bisil"] == 0.0
     d.close()
+
+
+def test_bisilhouette_of_a_subset_of_the_biclusters_combines_to_the_whole(ctx):
+    """resnmtf_data_bisil_part: the per-bicluster values are independent, so the biclusters of one fit can be scored in
+    pieces (on different GPUs holding copies of the view) and summed in bicluster order -- bit-identical to the one
+    call; this is what the native route does with the sweep fits of a multi-GPU call (native_route._SplitBisil)."""
+    rng = np.random.default_rng(29)
+    n, p, k = 500, 130, 6
+    x = synth.prep(synth.planted_view(n, p, 3, rng, row_prob=0.3, col_prob=0.3)[0])
+    rc = np.asfortranarray((rng.random((n, k)) < 0.25).astype(float))
+    cc = np.asfortranarray((rng.random((p, k)) < 0.3).astype(float))
+    rc[:, 2] = 0.0  # an empty bicluster does not count towards the mean
+    d = DeviceData(ctx, x)
+    whole = d.bisil(rc, cc)
+    live = [j for j in range(k) if rc[:, j].any() and cc[:, j].any()]
+    vals = np.zeros(k)
+    for piece in ([0, 5], [1], [3, 4], [2]):
+        want = np.zeros(k, dtype=np.int32)
+        want[piece] = 1
+        part, n_live = d.bisil_part(rc, cc, want)
+        assert n_live == len(live)
+        assert all(part[j] == 0.0 for j in range(k) if j not in piece)
+        vals += part
+    total = 0.0
+    for j in live:
+        total += float(vals[j])
+    assert [float(vals[j]) for j in live] == whole["vals"]
+    assert total / len(live) == whole["bisil"]
+    d.close()
