@@ -361,9 +361,16 @@ def obtain_biclusters(data, output_f, output_g, output_s, num_repeats, remove_sp
     """R/obtain_bicl.r:151-204.  ``shuffled_f`` / ``resident``: shuffled refits already computed by the caller / the
     views as device tensors (both None: the reference's serial route).  ``want_bisil=False`` skips the bisilhouette
     of callers that never read it (the resample fits of the stability analysis use the clusters only)."""
+    import os as _os
+    import sys as _sys
+    import time as _time
+
+    _trace = _os.environ.get("RESNMTF_TRACE", "0") not in ("", "0")
+    _t0 = _time.perf_counter()
     n_views = len(output_f)
     biclusts = (check_biclusters(data, output_f, num_repeats, rng, ctx, shuffled_f, resident)
                 if remove_spurious else None)
+    _t1 = _time.perf_counter()
     row_clustering, col_clustering = binarise(output_f, output_g)
     bisil = []
     for i in range(n_views):
@@ -391,5 +398,8 @@ def obtain_biclusters(data, output_f, output_g, output_s, num_repeats, remove_sp
             score = bisilhouette(xi, row_clustering[i], col_clustering[i], method=distance)
         bisil.append(score["bisil"])
     bisil = np.asarray(bisil)
+    if _trace:
+        print(f"  [resnmtf trace]   post of a k = {output_f[0].shape[1]} fit: spurious test {_t1 - _t0:.3f} s, binarise + "
+              f"bisilhouette {_time.perf_counter() - _t1:.3f} s", file=_sys.stderr, flush=True)
     overall = 0.0 if bisil.sum() == 0 else float(bisil[bisil != 0].mean())
     return {"row_clustering": row_clustering, "col_clustering": col_clustering, "bisil": overall}

@@ -19,5 +19,7 @@ for src in "$here"/*.cu; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$out" "${objs[@]}" -lpthread
+# linked beside the target and moved into place: a reader (a running test, a snapshot of the tree) never sees a partial file
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o "$out.tmp.$$" "${objs[@]}" -lpthread
+mv -f "$out.tmp.$$" "$out"
 echo "built $out"

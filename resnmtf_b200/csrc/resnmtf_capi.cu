@@ -47,7 +47,11 @@ static GStepSkFn g_step_sk_fn(int K) {
   return nullptr;
 }
 
+FStepSkFn rn_f_step_tma_gt8(int K);  // k = 9..16: rn_tma_gt8.cu
+GStepSkFn rn_g_step_tma_gt8(int K);
+
 static FStepSkFn f_step_tma_fn(int K) {
+  if (K > 8) return rn_f_step_tma_gt8(K);
   switch (K) {
 #define X(KC) case KC: return rn_f_step_tma<KC>;
     RN_K_CASES_LE8(X)
@@ -56,6 +60,7 @@ static FStepSkFn f_step_tma_fn(int K) {
   return nullptr;
 }
 static GStepSkFn g_step_tma_fn(int K) {
+  if (K > 8) return rn_g_step_tma_gt8(K);
   switch (K) {
 #define X(KC) case KC: return rn_g_step_tma<KC>;
     RN_K_CASES_LE8(X)
@@ -171,8 +176,13 @@ static void launch_windowed(void (*fn)(Args...), int grid, int block, size_t sme
   cudaLaunchKernelEx(&cfg, fn, args...);
 }
 
+// FP64 tensor-core kernels: the register-path pair (RESNMTF_IMPL_DMMA) serves k <= 8, the TMA pair k <= 16 (two 8-wide
+// tiles in the factor dimension for k = 9..16; RESNMTF_TMA_GT8=0 sends those k back to the CUDA-core kernels)
 static inline bool use_mma(const ViewHost& vh, int impl) {
-  return (impl == RESNMTF_IMPL_DMMA || impl == RESNMTF_IMPL_TMA || impl == RESNMTF_IMPL_FUSED) && vh.d.k <= 8;
+  if (impl == RESNMTF_IMPL_DMMA) return vh.d.k <= 8;
+  if (impl != RESNMTF_IMPL_TMA && impl != RESNMTF_IMPL_FUSED) return false;
+  static const bool gt8 = rn_env_int("RESNMTF_TMA_GT8", 1) != 0;
+  return vh.d.k <= 8 || gt8;
 }
 
 static void launch_f_step(const ViewHost& vh, const RnFit& ft, int v, int impl, cudaStream_t st) {

@@ -683,22 +683,26 @@ __global__ void __launch_bounds__(128, 3) rn_g_step_sk(const RnView vw, const Rn
 __device__ __forceinline__ void rn_consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 #define RN_TMA_THREADS 288  // 8 consumer warps + 1 producer warp
-#define RN_F_STAGES 11
-#define RN_F_STAGE_BYTES (32 * 512 + 32 * 64)  // one 64x32 unit of X (16 KB, verbatim) + its 32 rows of G
-#define RN_G_STAGES 5
-#define RN_G_STAGE_BYTES (64 * 512 + 8 * 512)  // one 64x64 unit of X (32 KB, verbatim) + the step's 64 rows of F
+// k <= 8: factor rows of 8 doubles (kp = 8), one 8-wide MMA tile in the factor dimension; k = 9..16: kp = 16, two tiles.
+// The rings shrink by one stage for kp = 16 (a stage carries the factor rows of its unit, twice as many bytes).
+#define RN_F_STAGES_KP(kp) ((kp) == 8 ? 11 : 10)
+#define RN_F_STAGE_BYTES_KP(kp) (32 * 512 + 32 * (kp) * 8)  // one 64x32 unit of X (16 KB, verbatim) + its 32 rows of G
+#define RN_G_STAGES_KP(kp) ((kp) == 8 ? 5 : 4)
+#define RN_G_STAGE_BYTES_KP(kp) (64 * 512 + (kp) * 512)     // one 64x64 unit of X (32 KB, verbatim) + the step's 64 rows of F
 // dynamic shared memory of the two TMA kernels (stages | 2*NST mbarriers | epilogue scratch)
 static inline size_t rn_f_tma_smem(int k) {
-  return (size_t)RN_F_STAGES * RN_F_STAGE_BYTES + 2 * RN_F_STAGES * 8 + (RN_ROW_TILE * 8 + 2 * k * k + k) * 8 + 16;
+  const int kp = k <= 8 ? 8 : 16, nst = RN_F_STAGES_KP(kp);
+  return (size_t)nst * RN_F_STAGE_BYTES_KP(kp) + 2 * nst * 8 + (RN_ROW_TILE * kp + 2 * k * k + k) * 8 + 16;
 }
 static inline size_t rn_g_tma_smem(int k) {
+  const int kp = k <= 8 ? 8 : 16, nst = RN_G_STAGES_KP(kp);
   const int nff = k * k + k;
-  return (size_t)RN_G_STAGES * RN_G_STAGE_BYTES + 2 * RN_G_STAGES * 8 +
-         (RN_COL_GROUP * 8 + RN_COL_GROUP * k + 8 * nff + nff + 2 * k * k + k) * 8 + 16;
+  return (size_t)nst * RN_G_STAGE_BYTES_KP(kp) + 2 * nst * 8 +
+         (RN_COL_GROUP * kp + RN_COL_GROUP * k + 8 * nff + nff + 2 * k * k + k) * 8 + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
-// F step, tensor-core path fed by a TMA ring (k <= 8), persistent stream-K, 1 CTA per SM.
+// F step, tensor-core path fed by a TMA ring (k <= 16), persistent stream-K, 1 CTA per SM.
 //   Same work decomposition and epilogue as rn_f_step_sk; what differs is how X reaches the MMAs: per 64x32
 //   unit one thread issues ONE 16 KB bulk copy (the unit is contiguous in the panel layout) plus a 2 KB copy
 //   of the unit's 32 rows of G into an 11-stage shared-memory ring; the 8 consumer warps wait on the stage's
@@ -708,7 +712,10 @@ static inline size_t rn_g_tma_smem(int k) {
 // ------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView vw, const RnFit ft, const int v) {
-  constexpr int KP = 8, NST = RN_F_STAGES, XB = 32 * 512, STAGE = RN_F_STAGE_BYTES;
+  // k = 9..16: NT = 2 tiles of 8 factor columns -- the B operand (the unit's rows of G) has two fragments per lane and
+  // every X fragment feeds two MMAs; accumulators, Ps and the partials carry kp = 16 columns
+  constexpr int KP = K <= 8 ? 8 : 16, NT = KP / 8, NST = RN_F_STAGES_KP(KP), XB = 32 * 512, GB = 32 * KP * 8;
+  constexpr int STAGE = RN_F_STAGE_BYTES_KP(KP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   if (ft.ctrl->done) return;
@@ -717,7 +724,7 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
   unsigned char* stages = rn_smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(rn_smem + NST * STAGE);
   uint64_t* empty = full + NST;
-  double* Ps = reinterpret_cast<double*>(empty + NST);
+  double* Ps = reinterpret_cast<double*>(empty + NST);  // [NT][64 x 8 fragment-major]
   double* Ssm = Ps + RN_ROW_TILE * KP;
   double* Wsm = Ssm + K * K;
   double* lamh = Wsm + K * K;
@@ -750,9 +757,9 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
       rn_mbar_wait(&empty[st], ph ^ 1u);
       unsigned char* sb = stages + st * STAGE;
       if (lane == 0) {
-        rn_mbar_expect_tx(&full[st], XB + 32 * 64);
+        rn_mbar_expect_tx(&full[st], XB + GB);
         rn_bulk_g2s(sb, vw.X + (tile * pp + 32 * cb) * RN_ROW_TILE, XB, &full[st]);
-        rn_bulk_g2s(sb + XB, vw.G + (32 * cb) * KP, 32 * 64, &full[st]);
+        rn_bulk_g2s(sb + XB, vw.G + (32 * cb) * KP, GB, &full[st]);
       }
       __syncwarp();
     }
@@ -774,11 +781,13 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
     const bool first_seg = (u == u0);
     u += cb1 - cb0;
 
-    double acc[4][2][2];
+    double acc[NT][4][2][2];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) acc[m][h][0] = acc[m][h][1] = 0.0;
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) acc[nt][m][h][0] = acc[nt][m][h][1] = 0.0;
     int xo[4];  // swizzled piece offsets (doubles) of rows 16m + 2g + {0,1} in column 4w + t of the unit
 #pragma unroll
     for (int m = 0; m < 4; ++m) xo[m] = (4 * warp + t) * RN_ROW_TILE + 2 * ((8 * m + g) ^ rn_sigma(t));
@@ -788,15 +797,19 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
       rn_mbar_wait(&full[st], ph);
       const unsigned char* sb = stages + st * STAGE;
       const double* xs = reinterpret_cast<const double*>(sb);
-      const double b = *(reinterpret_cast<const double*>(sb + XB) + (4 * warp + t) * KP + g);
+      double b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = *(reinterpret_cast<const double*>(sb + XB) + (4 * warp + t) * KP + 8 * nt + g);
       double2 x[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) x[m] = *reinterpret_cast<const double2*>(xs + xo[m]);
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        rn_dmma(acc[m][0][0], acc[m][0][1], x[m].x, b);
-        rn_dmma(acc[m][1][0], acc[m][1][1], x[m].y, b);
-      }
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          rn_dmma(acc[nt][m][0][0], acc[nt][m][0][1], x[m].x, b[nt]);
+          rn_dmma(acc[nt][m][1][0], acc[nt][m][1][1], x[m].y, b[nt]);
+        }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&empty[st]);
     }
@@ -807,13 +820,15 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
     for (int w = 0; w < 8; ++w) {  // fixed warp order
       if (warp == w) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            // fragment-major layout: (register, lane) -> conflict-free; rn_ps_index maps (row, col) back
-            Ps[((m * 2 + h) * 2 + 0) * 32 + lane] += acc[m][h][0];
-            Ps[((m * 2 + h) * 2 + 1) * 32 + lane] += acc[m][h][1];
-          }
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              // fragment-major layout: (register, lane) -> conflict-free; rn_ps_index maps (row, col) back
+              Ps[nt * 512 + ((m * 2 + h) * 2 + 0) * 32 + lane] += acc[nt][m][h][0];
+              Ps[nt * 512 + ((m * 2 + h) * 2 + 1) * 32 + lane] += acc[nt][m][h][1];
+            }
       }
       rn_consumer_sync();
     }
@@ -845,7 +860,7 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
       if (r < vw.n) {
         double P[K];
 #pragma unroll
-        for (int c = 0; c < K; ++c) P[c] = Ps[rn_ps_index(tid, c)];
+        for (int c = 0; c < K; ++c) P[c] = Ps[(c >> 3) * 512 + rn_ps_index(tid, c & 7)];
         rn_update_f_row<K>(vw, ft, v, r, P, Ssm, Wsm, lamh);
       }
     }
@@ -853,7 +868,7 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
 }
 
 // ------------------------------------------------------------------------------------------------
-// G step, tensor-core path fed by a TMA ring (k <= 8), persistent stream-K, fused epilogue, 1 CTA per SM.
+// G step, tensor-core path fed by a TMA ring (k <= 16), persistent stream-K, fused epilogue, 1 CTA per SM.
 //   Unit = 64 data columns x 64 rows of X = one contiguous 32 KB run: ONE bulk copy per unit into a 6-stage
 //   ring (~190 KB in flight per SM).  Consumer warp w owns data columns 8w..8w+7 of the group for every row
 //   step, so there is no cross-warp reduction of T; the F fragment of a step comes straight from global/L1
@@ -863,8 +878,10 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_f_step_tma(const RnView 
 template <int K>
 __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView vw, const RnFit ft, const int v,
                                                                    const int fuse_finish) {
-  constexpr int KP = 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
-  constexpr int NST = RN_G_STAGES, STAGE = RN_G_STAGE_BYTES;
+  // k = 9..16: NT = 2 tiles of 8 factor columns -- two F fragments per X fragment, two accumulator tiles per warp,
+  // F'F as 2 x 2 tiles; the stage's F block is kp x 512 B
+  constexpr int KP = K <= 8 ? 8 : 16, NT = KP / 8, KK = K * K, NFF = KK + K, NOUT = 2 * KK + K;
+  constexpr int NST = RN_G_STAGES_KP(KP), FB = KP * 512, STAGE = RN_G_STAGE_BYTES_KP(KP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   if (ft.ctrl->done) return;
@@ -873,7 +890,7 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView 
   unsigned char* stages = rn_smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(rn_smem + NST * STAGE);
   uint64_t* empty = full + NST;
-  double* Ts = reinterpret_cast<double*>(empty + NST);  // [64][8]
+  double* Ts = reinterpret_cast<double*>(empty + NST);  // [64][KP]
   double* Gs = Ts + RN_COL_GROUP * KP;                   // [64][K]
   double* FFw = Gs + RN_COL_GROUP * K;                   // [8][NFF] per-warp partials; later fin / scratch
   double* FtFs = FFw + 8 * NFF;                          // [NFF]
@@ -917,9 +934,9 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView 
       rn_mbar_wait(&empty[st], ph ^ 1u);
       unsigned char* sb = stages + st * STAGE;
       if (lane == 0) {
-        rn_mbar_expect_tx(&full[st], (uint32_t)ncol * 512u + 4096u);
+        rn_mbar_expect_tx(&full[st], (uint32_t)ncol * 512u + (uint32_t)FB);
         rn_bulk_g2s(sb, vw.X + (s * pp + j0) * RN_ROW_TILE, (uint32_t)ncol * 512u, &full[st]);
-        rn_bulk_g2s(sb + 32768, vw.F + s * (KP * RN_ROW_TILE), 4096u, &full[st]);
+        rn_bulk_g2s(sb + 32768, vw.F + s * (KP * RN_ROW_TILE), (uint32_t)FB, &full[st]);
       }
       __syncwarp();
     }
@@ -940,12 +957,19 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView 
     const bool doFF = (grp == 0);
     const bool have_cols = warp < njb;
 
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;  // two MMA chains (even / odd i)
-    double aff0 = 0.0, aff1 = 0.0, acs0 = 0.0, acs1 = 0.0;
+    double a0[NT], a1[NT], b0[NT], b1[NT];  // two MMA chains (even / odd i) per tile of 8 factor columns
+    double aff[NT][NT][2], acs[NT][2];       // F'F tile (ta, tb): rows 8 ta + g, columns 8 tb + 2t + {0,1}; colSums(F)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      a0[nt] = a1[nt] = b0[nt] = b1[nt] = 0.0;
+      acs[nt][0] = acs[nt][1] = 0.0;
+#pragma unroll
+      for (int n2 = 0; n2 < NT; ++n2) aff[nt][n2][0] = aff[nt][n2][1] = 0.0;
+    }
     int xo[8];  // swizzled piece offsets (doubles) of rows 8i + 2t + {0,1} in column 8w + g of the unit
 #pragma unroll
     for (int i = 0; i < 8; ++i) xo[i] = (8 * warp + g) * RN_ROW_TILE + 2 * ((4 * i + t) ^ rn_sigma(g));
-    int fo[8];  // F fragment (column c = g, same rows) inside the stage's F block
+    int fo[8];  // F fragment (column c = g of tile 0, same rows; tile nt: + 512 nt) inside the stage's F block
 #pragma unroll
     for (int i = 0; i < 8; ++i) fo[i] = 4096 + g * RN_ROW_TILE + 2 * ((4 * i + t) ^ rn_sigma(g));
     for (int64_t s = s0; s < s1; ++s, ++it) {
@@ -953,53 +977,79 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView 
       const uint32_t ph = (uint32_t)((it / NST) & 1);
       rn_mbar_wait(&full[st], ph);
       const double* xs = reinterpret_cast<const double*>(stages + st * STAGE);
-      double2 fw = make_double2(0.0, 0.0);
-      if (doFF) fw = *reinterpret_cast<const double2*>(xs + 4096 + g * RN_ROW_TILE + 2 * ((4 * warp + t) ^ rn_sigma(g)));
+      double2 fw[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        fw[nt] = make_double2(0.0, 0.0);
+        // sigma depends on the column modulo 4 only: column 8 nt + g has the swizzle of column g
+        if (doFF) fw[nt] = *reinterpret_cast<const double2*>(xs + 4096 + (8 * nt + g) * RN_ROW_TILE + 2 * ((4 * warp + t) ^ rn_sigma(g)));
+      }
       if (have_cols) {
-        double2 x2[8], f2[8];
+        double2 x2[8], f2[NT][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           x2[i] = *reinterpret_cast<const double2*>(xs + xo[i]);
-          f2[i] = *reinterpret_cast<const double2*>(xs + fo[i]);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) f2[nt][i] = *reinterpret_cast<const double2*>(xs + fo[i] + 512 * nt);
         }
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          rn_dmma(a0, a1, x2[i].x, f2[i].x);
-          rn_dmma(b0, b1, x2[i + 1].x, f2[i + 1].x);
-          rn_dmma(a0, a1, x2[i].y, f2[i].y);
-          rn_dmma(b0, b1, x2[i + 1].y, f2[i + 1].y);
-        }
+        for (int i = 0; i < 8; i += 2)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            rn_dmma(a0[nt], a1[nt], x2[i].x, f2[nt][i].x);
+            rn_dmma(b0[nt], b1[nt], x2[i + 1].x, f2[nt][i + 1].x);
+            rn_dmma(a0[nt], a1[nt], x2[i].y, f2[nt][i].y);
+            rn_dmma(b0[nt], b1[nt], x2[i + 1].y, f2[nt][i + 1].y);
+          }
       }
       __syncwarp();
       if (lane == 0) rn_mbar_arrive(&empty[st]);
       if (doFF) {  // warp w covers rows 8w + 2t + {0,1} of the step
-        rn_dmma(aff0, aff1, fw.x, fw.x);
-        rn_dmma(aff0, aff1, fw.y, fw.y);
-        rn_dmma(acs0, acs1, 1.0, fw.x);
-        rn_dmma(acs0, acs1, 1.0, fw.y);
+#pragma unroll
+        for (int ta = 0; ta < NT; ++ta) {
+#pragma unroll
+          for (int tb = 0; tb < NT; ++tb) {
+            rn_dmma(aff[ta][tb][0], aff[ta][tb][1], fw[ta].x, fw[tb].x);
+            rn_dmma(aff[ta][tb][0], aff[ta][tb][1], fw[ta].y, fw[tb].y);
+          }
+          rn_dmma(acs[ta][0], acs[ta][1], 1.0, fw[ta].x);
+          rn_dmma(acs[ta][0], acs[ta][1], 1.0, fw[ta].y);
+        }
       }
     }
 
     rn_consumer_sync();  // previous segment's epilogue is done with Ts / Gs / FFw
-    Ts[(8 * warp + g) * KP + 2 * t] = a0 + b0;
-    Ts[(8 * warp + g) * KP + 2 * t + 1] = a1 + b1;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      Ts[(8 * warp + g) * KP + 8 * nt + 2 * t] = a0[nt] + b0[nt];
+      Ts[(8 * warp + g) * KP + 8 * nt + 2 * t + 1] = a1[nt] + b1[nt];
+    }
     if (doFF) {
       double* mine = FFw + warp * NFF;
-      if (g < K) {
-        if (2 * t < K) mine[g + (2 * t) * K] = aff0;
-        if (2 * t + 1 < K) mine[g + (2 * t + 1) * K] = aff1;
-      }
-      if (g == 0) {
-        if (2 * t < K) mine[KK + 2 * t] = acs0;
-        if (2 * t + 1 < K) mine[KK + 2 * t + 1] = acs1;
+#pragma unroll
+      for (int ta = 0; ta < NT; ++ta) {
+        const int ra = 8 * ta + g;
+#pragma unroll
+        for (int tb = 0; tb < NT; ++tb) {
+          const int cb = 8 * tb + 2 * t;
+          if (ra < K) {
+            if (cb < K) mine[ra + cb * K] = aff[ta][tb][0];
+            if (cb + 1 < K) mine[ra + (cb + 1) * K] = aff[ta][tb][1];
+          }
+        }
+        if (g == 0) {
+          const int cb = 8 * ta + 2 * t;
+          if (cb < K) mine[KK + cb] = acs[ta][0];
+          if (cb + 1 < K) mine[KK + cb + 1] = acs[ta][1];
+        }
       }
     }
     rn_consumer_sync();
     if (doFF) {  // publish this CTA's F'F | colSums(F) partial (warps summed in order)
-      if (tid < NFF) {
+      for (int o = tid; o < NFF; o += 256) {
         double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += FFw[w * NFF + tid];
-        vw.FFpart[cta * NFF + tid] = s;
+        for (int w = 0; w < 8; ++w) s += FFw[w * NFF + o];
+        vw.FFpart[cta * NFF + o] = s;
       }
       __threadfence();
       rn_consumer_sync();
@@ -1038,10 +1088,10 @@ __global__ void __launch_bounds__(RN_TMA_THREADS, 1) rn_g_step_tma(const RnView 
         while (rn_ld_acquire(&vw.misc_ticket[2]) < nffc) __nanosleep(64);
       }
       rn_consumer_sync();
-      if (tid < NFF) {
+      for (int o = tid; o < NFF; o += 256) {
         double s = 0.0;
-        for (int i = 0; i < nffc; ++i) s += __ldcg(vw.FFpart + (int64_t)i * NFF + tid);
-        FtFs[tid] = s;
+        for (int i = 0; i < nffc; ++i) s += __ldcg(vw.FFpart + (int64_t)i * NFF + o);
+        FtFs[o] = s;
       }
       rn_consumer_sync();
       for (int o = tid; o < KK; o += 256) {  // V = crossprod(F) %*% S

@@ -150,16 +150,19 @@ class _SplitBisil:
             g = min(range(n_gpus), key=lambda g: (load[g], (g - self.first_gpu) % n_gpus))
             mine[g].append(j)
             load[g] += cost[j]
-        vals = np.zeros(k, dtype=np.float64)
-        for off in range(n_gpus):
-            g = (self.first_gpu + off) % n_gpus
-            if not mine[g]:
-                continue
+        def piece(g):
             want = np.zeros(k, dtype=np.int32)
             want[mine[g]] = 1
             with self.runner.gpu_locks[g]:  # entry points on one context are not re-entrant
-                part, _ = self.runner.handle(self.view, g).bisil_part(rc, cc, want, method)
-            vals += part
+                return self.runner.handle(self.view, g).bisil_part(rc, cc, want, method)[0]
+
+        busy = [g for g in range(n_gpus) if mine[g]]
+        vals = np.zeros(k, dtype=np.float64)
+        # the pieces of this fit run at the same time on their GPUs (ctypes releases the interpreter lock); the pieces
+        # of the other fits' host threads queue on the same per-GPU locks
+        with ThreadPoolExecutor(max_workers=len(busy)) as ex:
+            for part in ex.map(piece, busy):
+                vals += part  # disjoint supports: exact
         total = 0.0
         for j in live:  # in bicluster order, as resnmtf_data_bisil accumulates them
             total += float(vals[j])

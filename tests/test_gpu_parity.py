@@ -28,10 +28,50 @@ def test_single_view_every_k(ctx, k, impl):
     compare_trace(prob, ctx, n_iters=6, err_mode=L.ERR_DIRECT, impl=impl)
 
 
-@pytest.mark.parametrize("k", [9, 12, 16])
-def test_single_view_k_above_8(ctx, k):
+@pytest.mark.parametrize("impl", [L.IMPL_AUTO, L.IMPL_DFMA, L.IMPL_TMA])
+@pytest.mark.parametrize("k", [9, 10, 11, 12, 13, 14, 15, 16])
+def test_single_view_k_above_8(ctx, k, impl):
+    """k = 9..16 (the k-extension loop, R/main.r:306-320): the CUDA-core kernels and the two-tile tensor-core TMA pair
+    (what AUTO picks) against the oracle."""
     prob = single_view_problem(200, 150, k, seed=200 + k, n_planted=6)
-    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT)
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=impl)
+    if impl == L.IMPL_AUTO:
+        fit = prob.device_fit(ctx)
+        try:
+            fit.run(1, 0.0)
+            assert fit.counters()["impl"] == L.IMPL_TMA
+        finally:
+            fit.close()
+
+
+@pytest.mark.parametrize("split", [(0, 0), (7, 5), (23, 41), (1, 1)])
+@pytest.mark.parametrize("k", [9, 16])
+def test_k_above_8_tma_straddling_units(ctx, k, split, monkeypatch):
+    """Two-tile TMA kernels with row tiles / column groups that straddle CTAs (odd persistent grids, one CTA), on a shape
+    with ragged rows and columns."""
+    if split[0]:
+        monkeypatch.setenv("RESNMTF_F_CTAS", str(split[0]))
+        monkeypatch.setenv("RESNMTF_G_CTAS", str(split[1]))
+    prob = single_view_problem(1300, 710, k, seed=400 + k, n_planted=8)
+    compare_trace(prob, ctx, n_iters=4, err_mode=L.ERR_DIRECT, impl=L.IMPL_TMA)
+
+
+def test_k_above_8_tma_equals_cuda_core_path_and_is_repeatable(ctx):
+    """k = 12 on a mid-size view: the TMA pair against the independently written CUDA-core kernels (1e-9), bit-identical
+    run to run, and the algebraic error of the fused finish against the direct residual."""
+    prob = single_view_problem(3000, 1100, 12, seed=77, n_planted=10)
+    outs = []
+    for impl in (L.IMPL_TMA, L.IMPL_TMA, L.IMPL_DFMA):
+        fit = prob.device_fit(ctx, err_mode=L.ERR_ALGEBRAIC, impl=impl)
+        fit.run(12, 0.0)
+        outs.append((fit.get_factors(0), fit.errors()))
+        fit.close()
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][0], outs[2][0]):
+        assert rel_err(a, b) <= RTOL
+    assert rel_err(outs[0][1], outs[2][1]) <= RTOL
 
 
 @pytest.mark.parametrize("impl", [L.IMPL_DFMA, L.IMPL_DMMA, L.IMPL_TMA])
