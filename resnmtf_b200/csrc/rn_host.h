@@ -162,7 +162,8 @@ struct resnmtf_data {
   std::vector<double> svd_u, svd_d, svd_v;
   int svd_kc = 0;
   std::mutex svd_mu;  // the cache is filled by the first fit that asks and copied by resnmtf_data_copy, possibly from
-                      // different worker threads of a pool
+                      // different worker threads of a pool: held only while the vectors are published or copied
+  std::mutex svd_compute_mu;  // held for the whole computation (one at a time per handle); copies do not wait for it
 };
 
 void rn_ctx_release(resnmtf_ctx* ctx);  // resnmtf_capi.cu
@@ -322,3 +323,4 @@ int rn_data_alloc(resnmtf_ctx* ctx, int64_t n, int64_t p, resnmtf_data** out);
 int rn_data_seal(resnmtf_data* d);
 // rn_native.cu: fills the handle's cache of top singular triplets (no-op when it is there)
 int rn_data_svd(resnmtf_data* data);
+void rn_data_svd_adopt(resnmtf_data* dst, resnmtf_data* src);  // dst takes src's cached triplets (same view on another GPU)

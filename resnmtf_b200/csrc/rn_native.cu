@@ -660,6 +660,7 @@ int compute_svd(resnmtf_data* data) {
   RN_CUDA(cudaMemcpyAsync(oth.data(), other.d(), oth.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   RN_CUDA(cudaStreamSynchronize(ctx->stream));
   for (double& x : side) x = std::fabs(x);
+  std::lock_guard<std::mutex> pub(data->svd_mu);
   data->svd_d = dvals;
   if (cols_side) {
     data->svd_v = side;  // p x kc
@@ -676,10 +677,35 @@ int compute_svd(resnmtf_data* data) {
 
 // |U[, 1:k]|, d[1:k], |V[, 1:k]| of the view: what init_mats_inner() (R/update_steps.r:92-95) takes from svd(x)
 int rn_data_svd(resnmtf_data* data) {
-  std::lock_guard<std::mutex> lk(data->svd_mu);
-  if (data->svd_kc > 0) return RESNMTF_OK;
+  auto cached = [&]() {
+    std::lock_guard<std::mutex> lk(data->svd_mu);
+    return data->svd_kc > 0;
+  };
+  if (cached()) return RESNMTF_OK;
+  std::lock_guard<std::mutex> one(data->svd_compute_mu);  // svd_mu itself stays free: resnmtf_data_copy must not wait ~50 ms
+  if (cached()) return RESNMTF_OK;
   RN_CUDA(cudaSetDevice(data->ctx->device));
   return compute_svd(data);
+}
+
+void rn_data_svd_adopt(resnmtf_data* dst, resnmtf_data* src) {
+  if (!dst || !src || dst == src) return;
+  std::vector<double> u, d, v;
+  int kc;
+  {
+    std::lock_guard<std::mutex> lk(src->svd_mu);
+    u = src->svd_u;
+    d = src->svd_d;
+    v = src->svd_v;
+    kc = src->svd_kc;
+  }
+  if (kc <= 0) return;
+  std::lock_guard<std::mutex> lk(dst->svd_mu);
+  if (dst->svd_kc > 0) return;
+  dst->svd_u.swap(u);
+  dst->svd_d.swap(d);
+  dst->svd_v.swap(v);
+  dst->svd_kc = kc;
 }
 
 extern "C" int resnmtf_data_svd_topk(resnmtf_data* data, int k, double* u, double* d, double* v) {

@@ -8,8 +8,11 @@
 // through the entry points of this library.  No collective on the data path: the views are uploaded once and copied
 // GPU to GPU on first use.  What a unit returns does not depend on where or when it ran.
 #include <chrono>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 
 #include "rn_host.h"
@@ -20,6 +23,9 @@ struct resnmtf_pool {
     int n_views = 0;
     std::vector<std::vector<resnmtf_data*>> on_gpu;  // [gpu][view]; empty until that GPU first needs the set
     int home = 0;                                    // GPU that holds the original handles
+    // on_gpu[g] is filled under gpu_mu[g] only (by GPU g's worker or a resnmtf_pool_get for that GPU): the GPUs of a pool
+    // fetch their copies of a set at the same time instead of one after the other under the pool's mutex
+    std::unique_ptr<std::mutex[]> gpu_mu;
   };
   std::map<int, DataSet> sets;
   std::mutex mu;  // guards `sets` (handles are created under it; a set is only dropped between batches)
@@ -112,6 +118,7 @@ extern "C" int resnmtf_pool_put(resnmtf_pool* pool, int key, int n_views, resnmt
   s.n_views = n_views;
   s.home = home;
   s.on_gpu.assign(pool->ctx.size(), {});
+  s.gpu_mu.reset(new std::mutex[pool->ctx.size()]);
   for (int v = 0; v < n_views; ++v) {
     views[v]->refs.fetch_add(1);  // the pool holds its own reference
     s.on_gpu[home].push_back(views[v]);
@@ -140,10 +147,15 @@ extern "C" int resnmtf_pool_put_host(resnmtf_pool* pool, int key, int n_views, c
 
 // the views of set `key` on GPU g (copied from the home GPU, with their cached SVD triplets, on first use)
 static int set_on_gpu(resnmtf_pool* pool, int key, int g, std::vector<resnmtf_data*>* out) {
-  std::lock_guard<std::mutex> lk(pool->mu);
-  auto it = pool->sets.find(key);
-  RN_CHECK(it != pool->sets.end(), RESNMTF_E_INVALID, "resnmtf_batch_run: unknown data set key");
-  resnmtf_pool::DataSet& s = it->second;
+  resnmtf_pool::DataSet* sp = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(pool->mu);  // the map only; a set is dropped between batches, never under one
+    auto it = pool->sets.find(key);
+    RN_CHECK(it != pool->sets.end(), RESNMTF_E_INVALID, "resnmtf_batch_run: unknown data set key");
+    sp = &it->second;
+  }
+  resnmtf_pool::DataSet& s = *sp;
+  std::lock_guard<std::mutex> lk(s.gpu_mu[g]);
   if (s.on_gpu[g].empty()) {
     std::vector<resnmtf_data*> mine;
     for (resnmtf_data* src : s.on_gpu[s.home]) {
@@ -207,11 +219,35 @@ static int svd_init(resnmtf_data* d, int k, const double* noise, std::vector<dou
   return RESNMTF_OK;
 }
 
-static int run_unit(resnmtf_pool* pool, int g, resnmtf_unit* u) {
+// The SVD triplets of resident data that several units of a batch initialise from are computed ONCE, on the set's home
+// GPU, by that GPU's worker before it takes its first unit -- while the other GPUs already run the units that derive
+// their own data (shuffled refits, sub-samples).  A unit that needs the triplets waits for them here and adopts them when
+// its GPU's copy of the view was made before they existed.
+struct HomeSvd {
+  std::mutex mu;
+  std::condition_variable cv;
+  bool done = true;  // false while the home worker still owes the computation
+  int rc = RESNMTF_OK;
+  std::string message;
+  int key = -1;
+  std::vector<resnmtf_data*> handles;  // the home GPU's handles of set `key`
+  int wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done; });
+    if (rc) return rn_fail(rc, message);
+    return RESNMTF_OK;
+  }
+};
+
+static int run_unit(resnmtf_pool* pool, int g, resnmtf_unit* u, HomeSvd* hs) {
   resnmtf_ctx* ctx = pool->ctx[g];
   std::vector<resnmtf_data*> base;
   int rc = set_on_gpu(pool, u->data_key, g, &base);
   if (rc) return rc;
+  if (hs && u->derive == 0 && !(u->init_f && u->init_s && u->init_g) && u->data_key == hs->key) {
+    if ((rc = hs->wait())) return rc;
+    for (size_t v = 0; v < base.size() && v < hs->handles.size(); ++v) rn_data_svd_adopt(base[v], hs->handles[v]);
+  }
   const int V = (int)base.size();
   RN_CHECK(u->k != nullptr, RESNMTF_E_INVALID, "resnmtf_batch_run: unit without k");
   std::vector<resnmtf_data*> views((size_t)V, nullptr), owned;
@@ -320,23 +356,51 @@ static double unit_cost(resnmtf_pool* pool, const resnmtf_unit& u) {
 extern "C" int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_units) {
   RN_CHECK(pool && (units || n_units == 0) && n_units >= 0, RESNMTF_E_INVALID, "resnmtf_batch_run: bad argument");
   if (n_units == 0) return RESNMTF_OK;
-  // SVD triplets of resident data that several units initialise from are computed ONCE, on the home GPU, before the
-  // views fan out (the copies carry them)
-  for (int i = 0; i < n_units; ++i) {
-    resnmtf_unit& u = units[i];
-    if (u.derive != 0 || (u.init_f && u.init_s && u.init_g)) continue;
-    std::vector<resnmtf_data*> home;
-    int home_gpu;
-    {
+  // SVD triplets of resident data that several units initialise from are computed ONCE, on the home GPU (the copies
+  // of the views carry them, or adopt them later).  With several workers and one such data set, the home GPU's worker
+  // computes them as its first job while the other GPUs start on the units that derive their own data (HomeSvd);
+  // otherwise they are computed here, before the views fan out.
+  const int n_workers = std::min<int>((int)pool->ctx.size(), n_units);
+  HomeSvd hs;
+  int hs_gpu = -1;
+  {
+    bool several_keys = false;
+    for (int i = 0; i < n_units; ++i) {
+      resnmtf_unit& u = units[i];
+      if (u.derive != 0 || (u.init_f && u.init_s && u.init_g)) continue;
+      if (hs.key >= 0 && hs.key != u.data_key) several_keys = true;
+      if (hs.key >= 0) continue;
       std::lock_guard<std::mutex> lk(pool->mu);
       auto it = pool->sets.find(u.data_key);
       RN_CHECK(it != pool->sets.end(), RESNMTF_E_INVALID, "resnmtf_batch_run: unknown data set key");
-      home_gpu = it->second.home;
-      home = it->second.on_gpu[home_gpu];
+      hs.key = u.data_key;
+      hs_gpu = it->second.home;
+      hs.handles = it->second.on_gpu[hs_gpu];
     }
-    for (resnmtf_data* d : home) {
-      int rc = rn_data_svd(d);
-      if (rc) return rc;
+    const bool overlap = hs.key >= 0 && !several_keys && n_workers > 1 && hs_gpu < n_workers &&
+                         rn_env_int("RESNMTF_POOL_SVD_OVERLAP", 1) != 0;
+    if (hs.key >= 0 && !overlap) {
+      for (int i = 0; i < n_units; ++i) {
+        resnmtf_unit& u = units[i];
+        if (u.derive != 0 || (u.init_f && u.init_s && u.init_g)) continue;
+        std::vector<resnmtf_data*> home;
+        {
+          std::lock_guard<std::mutex> lk(pool->mu);
+          auto it = pool->sets.find(u.data_key);
+          RN_CHECK(it != pool->sets.end(), RESNMTF_E_INVALID, "resnmtf_batch_run: unknown data set key");
+          home = it->second.on_gpu[it->second.home];
+        }
+        for (resnmtf_data* d : home) {
+          int rc = rn_data_svd(d);
+          if (rc) return rc;
+        }
+      }
+      hs.key = -1;  // nothing owed: units find the triplets in their copies
+      hs_gpu = -1;
+    } else if (overlap) {
+      hs.done = false;
+    } else {
+      hs_gpu = -1;
     }
   }
   std::vector<int> order((size_t)n_units);
@@ -352,12 +416,24 @@ extern "C" int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_
   std::atomic<int> next{0};
   std::atomic<int> worst{RESNMTF_OK};
   auto worker = [&](int g) {
+    if (g == hs_gpu) {  // first job of the home GPU's worker: the shared SVD triplets
+      int rc = RESNMTF_OK;
+      for (resnmtf_data* d : hs.handles)
+        if ((rc = rn_data_svd(d))) break;
+      {
+        std::lock_guard<std::mutex> lk(hs.mu);
+        hs.rc = rc;
+        if (rc) hs.message = resnmtf_last_error();
+        hs.done = true;
+      }
+      hs.cv.notify_all();
+    }
     for (;;) {
       const int slot = next.fetch_add(1);
       if (slot >= n_units) return;
       resnmtf_unit* u = &units[order[slot]];
       const auto t0 = std::chrono::steady_clock::now();
-      const int rc = run_unit(pool, g, u);
+      const int rc = run_unit(pool, g, u, hs_gpu >= 0 ? &hs : nullptr);
       u->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       u->status = rc;
       u->gpu = g;
@@ -368,7 +444,6 @@ extern "C" int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_
       }
     }
   };
-  const int n_workers = std::min<int>((int)pool->ctx.size(), n_units);
   if (n_workers <= 1) {
     worker(0);
   } else {

@@ -169,3 +169,30 @@ def test_two_workers_with_graph_capturing_units_and_a_view_copy(ctx):
     for a, b in zip(two, one):
         assert a["iters"] == b["iters"] and np.array_equal(a["total_err"], b["total_err"])
         assert np.array_equal(a["output_f"][0], b["output_f"][0]) and np.array_equal(a["output_g"][0], b["output_g"][0])
+
+
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_home_svd_is_computed_by_the_home_worker_while_the_others_start(ctx, overlap, monkeypatch):
+    """Two workers (two contexts on ONE GPU), a k-sweep's worth of units: the SVD triplets of the resident view are the
+    first job of the home GPU's worker while the other worker already runs shuffled refits (its copy of the view is made
+    before the triplets exist and adopts them later); RESNMTF_POOL_SVD_OVERLAP=0 computes them before the fan-out.
+    Same numbers as the one-worker pool either way."""
+    monkeypatch.setenv("RESNMTF_POOL_SVD_OVERLAP", overlap)
+    x = synth.prep(synth.planted_view(900, 350, 3, np.random.default_rng(18), 0.3, 0.3)[0])
+    rng = np.random.default_rng(19)
+    units = []
+    for k in (5, 4, 3):
+        noise = [np.abs(np.sqrt(0.05) * rng.standard_normal((k, k)))]
+        for r in range(2):
+            units.append(dict(key=0, k=[k], noise=noise, shuffle_seed=77 * k + r, n_iters=None, max_iters=200))
+        units.append(dict(key=0, k=[k], noise=noise, n_iters=None, max_iters=200))
+    with NativePool(devices=[ctx.device, ctx.device]) as pool:
+        pool.put_host(0, [x])
+        two = pool.run(units)
+    with NativePool(devices=[ctx.device]) as pool:
+        pool.put_host(0, [x])
+        one = pool.run(units)
+    assert {u["gpu"] for u in two} == {0, 1}
+    for a, b in zip(two, one):
+        assert a["iters"] == b["iters"] and np.array_equal(a["total_err"], b["total_err"])
+        assert np.array_equal(a["output_f"][0], b["output_f"][0]) and np.array_equal(a["output_s"][0], b["output_s"][0])
