@@ -9,6 +9,7 @@
 // GPU to GPU on first use.  What a unit returns does not depend on where or when it ran.
 #include <chrono>
 #include <condition_variable>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -58,10 +59,23 @@ extern "C" int resnmtf_pool_create(const int* devices, int n_devices, resnmtf_po
   for (size_t a = 0; a < devs.size(); ++a)
     for (size_t b = 0; b < devs.size(); ++b) {
       if (a == b) continue;
+      if (devs[a] == devs[b]) continue;
       int can = 0;
       if (cudaDeviceCanAccessPeer(&can, devs[a], devs[b]) == cudaSuccess && can) {
         cudaSetDevice(devs[a]);
         cudaDeviceEnablePeerAccess(devs[b], 0);
+        // The views live in the contexts' private stream-ordered pools, and pool memory needs its own access grant: without
+        // it cudaMemcpyPeerAsync stages the copy through the host (measured on 8 GPUs: seven 640 MB copies from the home GPU
+        // at the start of a batch stretched the first unit of every GPU by 60-130 ms and the home GPU's SVD from 20 to
+        // 126 ms).  GPU a may read and write what GPU b's pool hands out.
+        if (p->ctx[b]->pooled) {
+          cudaMemAccessDesc desc;
+          std::memset(&desc, 0, sizeof(desc));
+          desc.location.type = cudaMemLocationTypeDevice;
+          desc.location.id = devs[a];
+          desc.flags = cudaMemAccessFlagsProtReadWrite;
+          cudaMemPoolSetAccess(p->ctx[b]->pool, &desc, 1);
+        }
       }
       cudaGetLastError();
     }
@@ -415,6 +429,12 @@ extern "C" int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
   std::atomic<int> next{0};
   std::atomic<int> worst{RESNMTF_OK};
+  // RESNMTF_POOL_TRACE=1: one line per unit on stderr (GPU, start and end in ms since the batch began, what it was)
+  const bool trace = rn_env_int("RESNMTF_POOL_TRACE", 0) != 0;
+  const auto batch_t0 = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(t - batch_t0).count();
+  };
   auto worker = [&](int g) {
     if (g == hs_gpu) {  // first job of the home GPU's worker: the shared SVD triplets
       int rc = RESNMTF_OK;
@@ -427,6 +447,9 @@ extern "C" int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_
         hs.done = true;
       }
       hs.cv.notify_all();
+      if (trace)
+        std::fprintf(stderr, "  [resnmtf pool] gpu %d  %8.1f .. %8.1f ms  SVD triplets of the resident view\n", g, 0.0,
+                     ms_since(std::chrono::steady_clock::now()));
     }
     for (;;) {
       const int slot = next.fetch_add(1);
@@ -437,6 +460,11 @@ extern "C" int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_
       u->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       u->status = rc;
       u->gpu = g;
+      if (trace)
+        std::fprintf(stderr, "  [resnmtf pool] gpu %d  %8.1f .. %8.1f ms  unit %3d  k=%d%s%s  %lld sweeps\n", g, ms_since(t0),
+                     ms_since(std::chrono::steady_clock::now()), order[slot], u->k ? u->k[0] : 0,
+                     (u->derive & RESNMTF_DERIVE_SUBSAMPLE) ? " sub-sample" : "",
+                     (u->derive & RESNMTF_DERIVE_SHUFFLE) ? " shuffled" : "", (long long)u->iters);
       if (rc) {
         std::snprintf(u->message, sizeof(u->message), "%s", resnmtf_last_error());
         int expected = RESNMTF_OK;

@@ -170,6 +170,8 @@ def test_split_bisilhouette_combines_pieces_in_bicluster_order():
     class Runner:
         pool = [0, 1, 2]
         gpu_locks = [threading.Lock() for _ in range(3)]
+        bisil_lock = threading.Lock()
+        bisil_load = [0.0, 0.0, 0.0]  # shared by the fits of one batch (a second fit would start from the first one's loads)
 
         def handle(self, view, g):
             return Handle(g)
@@ -179,3 +181,7 @@ def test_split_bisilhouette_combines_pieces_in_bicluster_order():
     assert got["vals"] == whole["vals"] and abs(got["bisil"] - whole["bisil"]) <= 1e-15
     assert sorted(j for _, js in calls for j in js) == [0, 2, 3, 4]  # every live bicluster exactly once
     assert len({g for g, _ in calls}) == 3                            # over all three "GPUs"
+    first = list(Runner.bisil_load)
+    assert min(first) > 0.0
+    _SplitBisil(Runner(), 0, first_gpu=1).bisil(rc, cc)                # a second fit adds to the same table
+    assert all(b > a for a, b in zip(first, Runner.bisil_load))
