@@ -53,7 +53,8 @@ extern "C" {
 #define RESNMTF_IMPL_AUTO 0
 #define RESNMTF_IMPL_DFMA 1 /* CUDA-core FP64 FMA                                    */
 #define RESNMTF_IMPL_DMMA 2 /* FP64 tensor-core mma.sync m8n8k4 (k <= 8), X loaded straight into fragments */
-#define RESNMTF_IMPL_TMA 3  /* same MMAs, X staged through a shared-memory ring by TMA bulk copies       */
+#define RESNMTF_IMPL_TMA 3  /* same MMAs, X staged through a shared-memory ring by TMA bulk copies; k <= 16 (two 8-wide
+                               tiles in the factor dimension for k = 9..16, the k-extension loop of R/main.r:306-320)   */
 #define RESNMTF_IMPL_FUSED 4 /* one pass over X per update-iteration: 8-row groups resident in the shared memory of a
                                 cluster of 1..8 CTAs do the F step and the G step (k <= 8, p <= 8064, one GPU per view,
                                 at most 7 phi partners); views that do not qualify run RESNMTF_IMPL_TMA.  This is what
@@ -332,8 +333,10 @@ typedef struct resnmtf_unit {
   char message[200];            /* resnmtf_last_error() of the worker thread when status != 0                           */
 } resnmtf_unit;
 
-/* Runs the units, longest first, on one native worker thread per GPU of the pool (no interpreter, no host language
- * involved), and returns when all are done: RESNMTF_OK, or the code of the first failed unit (every unit carries its
+/* Runs the units on one native worker thread per GPU of the pool (no interpreter, no host language involved) -- the
+ * fits of the resident data before the units that derive their own, each group longest first; SVD triplets that several
+ * units share are computed once, by the home GPU's worker, while the other GPUs start on derived units -- and returns
+ * when all are done: RESNMTF_OK, or the code of the first failed unit (every unit carries its
  * own status).  What a unit returns does not depend on the GPU that ran it or on the number of GPUs. */
 int resnmtf_batch_run(resnmtf_pool* pool, resnmtf_unit* units, int n_units);
 /* sizeof(resnmtf_unit) as this library was built: lets a binding verify its own declaration of the struct. */

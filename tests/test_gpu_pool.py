@@ -149,7 +149,7 @@ def test_a_failing_unit_reports_its_own_status(ctx):
 
 
 def test_two_workers_with_graph_capturing_units_and_a_view_copy(ctx):
-    """Two worker threads (a pool of two contexts, here on ONE GPU): units with k > 8 run the CUDA-core kernels, whose
+    """Two worker threads (a pool of two contexts, here on ONE GPU): units with k > 8 run the two-pass kernels, whose
     sweep is captured into a CUDA graph by the worker, while the other worker copies the view from the first context
     (resnmtf_data_copy) and runs its own units.  Regression: the copy used to synchronise the source context's stream,
     which fails while the other thread has it in capture (found on 8 GPUs).  Results equal the one-worker pool's."""
