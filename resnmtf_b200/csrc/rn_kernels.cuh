@@ -1545,6 +1545,9 @@ __global__ void __launch_bounds__(256) rn_residual(const RnView vw, const RnFit 
   }
 }
 
+// The kernels below are not templates: they belong to ONE translation unit (resnmtf_capi.cu); a unit that only
+// instantiates the templates above (rn_tma_gt8.cu) defines RN_KERNEL_TEMPLATES_ONLY.
+#ifndef RN_KERNEL_TEMPLATES_ONLY
 // Row-sharded path: sums the `count` F'F | colSums(F) partials in order into the tail of the T buffer
 // (T | F'F | colSums(F) is then one contiguous all-reduce) and re-arms the F'F publication counter.
 __global__ void rn_pack_ff(const RnView vw, const RnFit ft, const int count) {
@@ -1690,3 +1693,4 @@ __global__ void __launch_bounds__(256) rn_normalise(const RnView vw) {
     vw.S[threadIdx.x] *= vw.csF[b] * vw.csG[b];
   }
 }
+#endif  // RN_KERNEL_TEMPLATES_ONLY

@@ -1,17 +1,9 @@
 // Instantiations of the two-pass TMA kernels for k = 9..16 (two 8-wide MMA tiles in the factor dimension,
 // rn_kernels.cuh), in their own translation unit so that they compile beside resnmtf_capi.cu instead of inside it.
 // The reference's k-extension loop (R/main.r:306-320) reaches k = 9 whenever the selected k is k_max = 8.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdint.h>
-
-#include "rn_types.h"
-
-// rn_kernels.cuh also defines the library's non-template kernels, which resnmtf_capi.cu owns: here the whole header gets
-// internal linkage (the system headers and the descriptor types above are already in, their guards make them no-ops)
-namespace {
+// rn_kernels.cuh also defines the library's non-template kernels, which resnmtf_capi.cu owns: templates only here
+#define RN_KERNEL_TEMPLATES_ONLY
 #include "rn_kernels.cuh"
-}  // namespace
 
 typedef void (*FStepSkFn)(const RnView, const RnFit, const int);
 typedef void (*GStepSkFn)(const RnView, const RnFit, const int, const int);
