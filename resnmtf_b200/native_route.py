@@ -296,8 +296,13 @@ class NativeRunner:
         if len(specs) == 1:
             out = [post(0)]
         else:
+            # the fits with the most biclusters carry the most distance work: they start first (with fewer host threads than
+            # fits -- one or two GPUs -- the k = 8 fit of a sweep was otherwise the last to start)
+            first = sorted(range(len(specs)), key=lambda si: -int(np.asarray(done[core_at[si]]["output_f"][0]).shape[1]))
+            out = [None] * len(specs)
             with ThreadPoolExecutor(max_workers=max(1, min(len(specs), 2 * len(self.pool)))) as ex:
-                out = list(ex.map(post, range(len(specs))))
+                for si, res in zip(first, ex.map(post, first)):
+                    out[si] = res
         _trace("post-processing (JSD thresholds, binarise, bisilhouette)", t0)
         return out
 
